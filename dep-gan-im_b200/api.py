@@ -1,0 +1,350 @@
+"""Host-side mirror of the reference's Keras surface for the DEP-GAN hot path.
+
+    netG = Gen_UNet2D((256, 256, nicg), (32, 1), 32, 1)        # TG:520 / EG:380 / TU:579 / EU:399
+    netG.load_weights('./models/netG_depgan_im_noSL_fold1.h5')  # EG:383 / EU:402
+    dem = netG.predict([x, z])                                  # EG:621 / EU:558
+    netD = Dis_C2D_FCN1((256, 256, 1)); netD.predict(x)         # TG:513,516,846-848
+
+The objects own a flat float32 parameter buffer on the GPU in Keras tensor layouts and drive the CUDA kernels
+through the C ABI (include/depgan_b200.h).  PyTorch is used only for device memory, streams and (in dp.py)
+torch.distributed; there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import synth
+
+__all__ = ["Gen_UNet2D", "Dis_C2D_FCN1", "conv2d_op", "launch_count"]
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("depgan_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _stream(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def launch_count():
+    return int(_lib.lib().depgan_launch_count())
+
+
+def manifest(model, cfg):
+    """[(name 'layer/weight', shape tuple, float offset, trainable)] from the native library (host only)."""
+    L = _lib.lib()
+    n = L.depgan_manifest_count(model, C.byref(cfg))
+    if n < 0:
+        raise RuntimeError("manifest: " + _lib.last_error())
+    out = []
+    name = C.create_string_buffer(256)
+    ndim, tr, off = C.c_int(), C.c_int(), C.c_longlong()
+    shape = (C.c_int * 4)()
+    for i in range(n):
+        _lib.check(L.depgan_manifest_entry(model, C.byref(cfg), i, name, 256, C.byref(ndim), shape, C.byref(off),
+                                           C.byref(tr)), "manifest_entry")
+        out.append((name.value.decode(), tuple(shape[k] for k in range(ndim.value)), int(off.value), bool(tr.value)))
+    return out, int(L.depgan_manifest_floats(model, C.byref(cfg)))
+
+
+class _Net:
+    """One generator or critic: flat parameters + workspace on one GPU and the native handle."""
+
+    def __init__(self, model, cfg, device, seed):
+        torch = _torch()
+        self._torch = torch
+        self.model, self.cfg = model, cfg
+        self.device = torch.device(device)
+        self.manifest, self.n_floats = manifest(model, cfg)
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            self.params = torch.zeros(self.n_floats, dtype=torch.float32, device=self.device)
+            self.grads = torch.zeros(self.n_floats, dtype=torch.float32, device=self.device) if cfg.training else None
+            ws = int(L.depgan_workspace_bytes(model, C.byref(cfg)))
+            if ws < 0:
+                raise RuntimeError("workspace_bytes: " + _lib.last_error())
+            self.workspace = torch.empty(ws, dtype=torch.uint8, device=self.device)
+            self.handle = L.depgan_net_create(model, C.byref(cfg), self.params.data_ptr(),
+                                              self.grads.data_ptr() if self.grads is not None else None,
+                                              self.workspace.data_ptr(), ws)
+            if not self.handle:
+                raise RuntimeError("net_create: " + _lib.last_error())
+        self.adam_m = self.adam_v = None
+        self.iterations = 0
+        man3 = [(n.split("/")[0], n.split("/")[1], s) for n, s, _, _ in self.manifest]
+        self.set_weights(synth.init_weights(man3, seed=seed))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().depgan_net_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------------------------------
+    def set_weights(self, weights):
+        """weights: dict 'layer/weight' -> array in Keras layout.  Every manifest entry must be present."""
+        torch = self._torch
+        flat = np.zeros(self.n_floats, np.float32)
+        for name, shape, off, _ in self.manifest:
+            if name not in weights:
+                raise KeyError("missing weight %s" % name)
+            w = np.asarray(weights[name], np.float32)
+            if tuple(w.shape) != tuple(shape):
+                raise ValueError("weight %s has shape %s, expected %s" % (name, w.shape, shape))
+            flat[off:off + w.size] = w.reshape(-1)
+        with torch.cuda.device(self.device):
+            self.params.copy_(torch.from_numpy(flat))
+            self.prepare()
+
+    def get_weights(self):
+        flat = self.params.detach().cpu().numpy()
+        return {name: flat[off:off + int(np.prod(shape))].reshape(shape).copy()
+                for name, shape, off, _ in self.manifest}
+
+    def get_grads(self):
+        flat = self.grads.detach().cpu().numpy()
+        return {name: flat[off:off + int(np.prod(shape))].reshape(shape).copy()
+                for name, shape, off, _ in self.manifest}
+
+    def count_params(self):
+        return int(sum(int(np.prod(s)) for _, s, _, _ in self.manifest))
+
+    def prepare(self):
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_net_prepare(self.handle, _stream(torch)), "net_prepare")
+
+    # ---- Keras-form Adam on the flat buffer (TG:549,568,594) ---------------------------------------------
+    def adam_step(self, lr=1e-4, beta_1=0.0, beta_2=0.9, eps=1e-7, grad_scale=1.0):
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            if self.adam_m is None:
+                self.adam_m = torch.zeros_like(self.params)
+                self.adam_v = torch.zeros_like(self.params)
+            self.iterations += 1
+            _lib.check(_lib.lib().depgan_adam_step(self.params.data_ptr(), self.grads.data_ptr(),
+                                                   self.adam_m.data_ptr(), self.adam_v.data_ptr(), self.n_floats,
+                                                   self.iterations, lr, beta_1, beta_2, eps, grad_scale,
+                                                   _stream(torch)), "adam_step")
+            self.prepare()
+
+    def debug_activation(self, name, n):
+        torch = self._torch
+        cap = int(n) * self.cfg.H * self.cfg.W * 256
+        buf = torch.empty(cap, dtype=torch.float32, device=self.device)
+        cnt = C.c_longlong()
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_debug_activation(self.handle, name.encode(), buf.data_ptr(), cap,
+                                                          C.byref(cnt), int(n), _stream(torch)), "debug_activation")
+        return buf[:cnt.value].cpu().numpy()
+
+    # ---- HDF5 (Keras 2.x full-model files, EG:383 / EU:402 / TG:892 / TU:622) ----------------------------
+    def load_weights(self, path):
+        from . import h5lite
+        self.set_weights(h5lite.load_keras_weights(path, [(n, s) for n, s, _, _ in self.manifest]))
+
+    def save(self, path):
+        from . import h5lite
+        h5lite.save_keras_weights(path, self.get_weights(), [n for n, _, _, _ in self.manifest])
+
+    save_weights = save
+
+
+def _prec(precision):
+    if precision in ("bf16", _lib.PREC_BF16):
+        return _lib.PREC_BF16
+    if precision in ("fp32", "f32", _lib.PREC_FP32):
+        return _lib.PREC_FP32
+    raise ValueError("precision must be 'bf16' or 'fp32'")
+
+
+class Gen_UNet2D(_Net):
+    """Drop-in for ``Gen_UNet2D(input_shape, noiseZ_shape, first_fm, nc_out)`` (TG:349-498, TU:291-428).
+
+    nc_out == 1 -> tanh head (DEP-GAN generator); nc_out == 4 -> softmax head (DEP-UResNet).
+    Extra keyword arguments choose the arithmetic ('bf16' tcgen05 path, 'fp32' CUDA-core path), the
+    workspace batch, the device and the synthetic-initialisation seed.
+    """
+
+    def __init__(self, input_shape=(256, 256, 1), noiseZ_shape=(32, 1), first_fm=32, nc_out=1, *, precision="bf16",
+                 max_batch=32, device="cuda:0", training=False, seed=0):
+        if first_fm != 32:
+            raise ValueError("first_fm must be 32 (first_fm_G, TG:36)")
+        if tuple(noiseZ_shape)[1:] != (1,):
+            raise ValueError("noiseZ_shape must be (L, 1)")
+        h, w, nicg = input_shape
+        cfg = _lib.Cfg(int(h), int(w), int(nicg), int(nc_out), int(noiseZ_shape[0]), int(max_batch), _prec(precision),
+                       int(bool(training)))
+        self.input_shape, self.noiseZ_shape, self.nc_out = tuple(input_shape), tuple(noiseZ_shape), int(nc_out)
+        super().__init__(_lib.MODEL_GEN, cfg, device, seed)
+
+    def forward_device(self, x, z, out=None):
+        """x (n,H,W,nicg), z (n,L,1) float32 CUDA tensors -> (n,H,W,nc_out) float32 CUDA tensor (async)."""
+        torch = self._torch
+        n = int(x.shape[0])
+        if out is None:
+            out = torch.empty((n, self.cfg.H, self.cfg.W, self.nc_out), dtype=torch.float32, device=self.device)
+        if not (x.is_contiguous() and z.is_contiguous() and x.dtype == torch.float32 and z.dtype == torch.float32):
+            raise ValueError("forward_device needs contiguous float32 tensors")
+        if tuple(x.shape[1:]) != self.input_shape or int(z.shape[0]) != n or tuple(z.shape[1:]) != self.noiseZ_shape:
+            raise ValueError("bad input shapes %s %s" % (tuple(x.shape), tuple(z.shape)))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_gen_forward(self.handle, x.data_ptr(), z.data_ptr(), out.data_ptr(), n,
+                                                     _stream(torch)), "gen_forward")
+        return out
+
+    def predict(self, inputs, batch_size=32, verbose=0):
+        """Keras ``model.predict([x, z])`` (EG:621, EU:558): numpy in, numpy float32 out, inference mode."""
+        torch = self._torch
+        x, z = inputs
+        x = np.ascontiguousarray(x, np.float32)
+        z = np.ascontiguousarray(z, np.float32)
+        if x.shape[0] != z.shape[0]:
+            raise ValueError("x and z must have the same number of samples")
+        n = x.shape[0]
+        bs = max(1, min(int(batch_size), self.cfg.max_batch))
+        out = np.empty((n, self.cfg.H, self.cfg.W, self.nc_out), np.float32)
+        for i in range(0, n, bs):
+            xb = torch.from_numpy(x[i:i + bs]).to(self.device, non_blocking=False)
+            zb = torch.from_numpy(z[i:i + bs]).to(self.device, non_blocking=False)
+            out[i:i + bs] = self.forward_device(xb, zb).cpu().numpy()
+        return out
+
+
+class Dis_C2D_FCN1(_Net):
+    """Drop-in for ``Dis_C2D_FCN1(input_shape)`` (TG:316-345): the WGAN-GP critic, (N,H,W,1) -> (N,1)."""
+
+    def __init__(self, input_shape=(256, 256, 1), *, precision="bf16", max_batch=32, device="cuda:0", training=False,
+                 seed=1):
+        h, w, c = input_shape
+        if c != 1:
+            raise ValueError("the critic takes one channel (TG:513,516)")
+        cfg = _lib.Cfg(int(h), int(w), 1, 1, 32, int(max_batch), _prec(precision), int(bool(training)))
+        self.input_shape = tuple(input_shape)
+        super().__init__(_lib.MODEL_CRITIC, cfg, device, seed)
+
+    def forward_device(self, x, out=None):
+        torch = self._torch
+        n = int(x.shape[0])
+        if out is None:
+            out = torch.empty((n, 1), dtype=torch.float32, device=self.device)
+        if not (x.is_contiguous() and x.dtype == torch.float32) or tuple(x.shape[1:]) != self.input_shape:
+            raise ValueError("forward_device needs a contiguous float32 (n,H,W,1) tensor")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_critic_forward(self.handle, x.data_ptr(), out.data_ptr(), n, _stream(torch)),
+                       "critic_forward")
+        return out
+
+    def predict(self, x, batch_size=32, verbose=0):
+        torch = self._torch
+        x = np.ascontiguousarray(x, np.float32)
+        n = x.shape[0]
+        bs = max(1, min(int(batch_size), self.cfg.max_batch))
+        out = np.empty((n, 1), np.float32)
+        for i in range(0, n, bs):
+            out[i:i + bs] = self.forward_device(torch.from_numpy(x[i:i + bs]).to(self.device)).cpu().numpy()
+        return out
+
+
+# ---- kernel-level op (tests / micro-benchmarks) -----------------------------------------------------------
+def conv2d_op(x, w, *, x1=None, scale=None, shift=None, relu=False, film=None, res=None, add=None, mask=None,
+              deconv=False, head=None, use_tc=True, want_pre=False):
+    """One fused convolution through depgan_op_conv2d.
+
+    x (N,H,W,C0) [, x1 (N,H,W,C1)] float32 CUDA tensors; w Keras HWIO (k,k,Cin,Cout) or, for deconv, Keras
+    Conv2DTranspose layout (2,2,Cout,Cin).  use_tc=True runs the tcgen05 path on bf16 copies, else the fp32
+    CUDA-core path.  film = (gamma (N,C), beta (N,C)); head = (w (C,nc), b (nc), act).  Returns float32 tensors:
+    out, or (out, extras dict) when head / want_pre are used.
+    """
+    torch = _torch()
+    L = _lib.lib()
+    st = _stream(torch)
+    dev = x.device
+    N, H, W, C0 = x.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    if deconv:
+        cout, cin, ks, taps = w.shape[2], w.shape[3], 1, 1
+        ncols = 4 * cout
+        oh, ow = 2 * H, 2 * W
+    else:
+        ks, cin, cout = w.shape[0], w.shape[2], w.shape[3]
+        taps, ncols = ks * ks, cout
+        oh, ow = H, W
+    assert cin == C0 + C1
+    keep = []
+
+    def dev_f32(t):
+        t = t.to(dev, torch.float32).contiguous()
+        keep.append(t)
+        return t
+
+    def to_act(t):
+        t = dev_f32(t)
+        if not use_tc:
+            return t
+        b = torch.empty(t.numel(), dtype=torch.bfloat16, device=dev)
+        _lib.check(L.depgan_op_f32_to_bf16(t.data_ptr(), b.data_ptr(), t.numel(), st), "f32_to_bf16")
+        keep.append(b)
+        return b
+
+    d = _lib.ConvDesc()
+    d.in0 = to_act(x).data_ptr()
+    d.C0, d.C1 = C0, C1
+    if x1 is not None:
+        d.in1 = to_act(x1).data_ptr()
+    wf = dev_f32(w)
+    if use_tc:
+        wb = torch.empty(wf.numel(), dtype=torch.bfloat16, device=dev)
+        if deconv:  # (2,2,Cout,Cin) is already [4*Cout][Cin]
+            _lib.check(L.depgan_op_f32_to_bf16(wf.data_ptr(), wb.data_ptr(), wf.numel(), st), "f32_to_bf16")
+        else:
+            _lib.check(L.depgan_op_pack_weights(wf.data_ptr(), wb.data_ptr(), taps, cin, cout, st), "pack_weights")
+        keep.append(wb)
+        d.w_bf16 = wb.data_ptr()
+    else:
+        assert not deconv, "the fp32 path runs the transposed conv through its own kernel"
+        d.w_f32 = wf.data_ptr()
+    if scale is not None:
+        d.scale = dev_f32(scale).data_ptr()
+    if shift is not None:
+        d.shift = dev_f32(shift).data_ptr()
+    odt = torch.bfloat16 if use_tc else torch.float32
+    out = torch.empty((N, oh, ow, cout), dtype=odt, device=dev)
+    d.out = out.data_ptr()
+    pre = None
+    if want_pre:
+        pre = torch.empty((N, oh, ow, cout), dtype=odt, device=dev)
+        d.out_pre = pre.data_ptr()
+    if film is not None:
+        g, b = dev_f32(film[0]), dev_f32(film[1])
+        d.film_g, d.film_b, d.film_stride = g.data_ptr(), b.data_ptr(), g.shape[1]
+        d.res = to_act(res).data_ptr()
+    if add is not None:
+        d.add_src = to_act(add).data_ptr()
+    if mask is not None:
+        d.mask_src = to_act(mask).data_ptr()
+    d.relu, d.deconv = int(relu), int(deconv)
+    hout = None
+    if head is not None:
+        hw, hb, act = head
+        hw, hb = dev_f32(hw), dev_f32(hb)
+        hout = torch.empty((N, H, W, hw.shape[1]), dtype=torch.float32, device=dev)
+        d.head_w, d.head_b, d.head_out = hw.data_ptr(), hb.data_ptr(), hout.data_ptr()
+        d.head_nc, d.head_act = hw.shape[1], int(act)
+    d.N, d.H, d.W, d.Cout, d.ks = N, H, W, cout, ks
+    d.in_bf16 = d.out_bf16 = int(use_tc)
+    d.use_tc = int(use_tc)
+    _lib.check(L.depgan_op_conv2d(C.byref(d), st), "op_conv2d")
+    torch.cuda.synchronize(dev)
+    outf = out.float()
+    if head is None and not want_pre:
+        return outf
+    return outf, {"head": hout, "pre": None if pre is None else pre.float()}

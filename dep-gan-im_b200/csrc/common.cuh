@@ -1,0 +1,113 @@
+// Shared declarations for the depgan_b200 CUDA sources (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (no exceptions across the C ABI) ----
+void depgan_set_error(const std::string& msg);
+extern long long g_launch_count;
+
+#define DG_CHECK_CUDA(expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess) {                                                                             \
+      depgan_set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" +      \
+                       std::to_string(__LINE__));                                                        \
+      return -1;                                                                                         \
+    }                                                                                                    \
+  } while (0)
+
+#define DG_LAUNCH_CHECK()                                                                                \
+  do {                                                                                                   \
+    ++g_launch_count;                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                                 \
+    if (_e != cudaSuccess) {                                                                             \
+      depgan_set_error(std::string("kernel launch: ") + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                       std::to_string(__LINE__));                                                        \
+      return -1;                                                                                         \
+    }                                                                                                    \
+  } while (0)
+
+#define DG_REQUIRE(cond, msg)                                        \
+  do {                                                               \
+    if (!(cond)) {                                                   \
+      depgan_set_error(std::string("requirement failed: ") + (msg)); \
+      return -2;                                                     \
+    }                                                                \
+  } while (0)
+
+#define DG_TRY(expr)           \
+  do {                         \
+    int _r = (expr);           \
+    if (_r != 0) return _r;    \
+  } while (0)
+
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---- typed load/store helpers ----
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- convolution argument block (SIMT and tcgen05 paths share it) ----
+// acc = conv(in0 || in1, w)  ('same' padding, stride 1, ks in {1,3,5});  then per output element (n,h,w,c):
+//   v = acc * scale[c] + shift[c]                       (folded bias + inference BatchNorm, TG:285-297)
+//   if out_pre : out_pre = v                            (pre-FiLM tensor kept for backward)
+//   if film_g  : v = relu(v * film_g[n,c] + film_b[n,c]) + res      (mul/add/relu/add_noiseZres, TG:403-407)
+//   if add_src : v += add_src
+//   if mask_src: v = mask_src > 0 ? v : 0               (ReLU / activation-pattern mask for dgrad and JVP)
+//   if relu    : v = max(v, 0)
+//   if out     : out = v
+//   if head_w  : head_out[n,h,w,:] = act(sum_c v[c] * head_w[c,:] + head_b)   (1x1 gen_segmentation, TG:494-495)
+// deconv = 1: ks must be 1; weights hold 4*Cout columns (a,b,co) and column (ab,co) of input pixel (h,w) is
+//   written to out[n, 2h+a, 2w+b, co] (Conv2DTranspose k2 s2, TG:307-312); scale/shift are indexed by co.
+struct ConvArgs {
+  const void* in0;
+  const void* in1;
+  int C0, C1;
+  const float* w;      // SIMT: [taps][Cin][Ncols] fp32   (deconv: [Cin][4*Cout])
+  const bf16* w_tc;    // tcgen05: [taps][Ncols][Cin] bf16 (K-major B operand)
+  const float* scale;  // [Cout] or nullptr (1)
+  const float* shift;  // [Cout] or nullptr (0)
+  void* out;
+  void* out_pre;
+  const float* film_g;
+  const float* film_b;
+  int film_stride;
+  const void* res;
+  const void* add_src;
+  const void* mask_src;
+  int relu;
+  int deconv;
+  const float* head_w;  // [Cout][head_nc] fp32
+  const float* head_b;  // [head_nc]
+  float* head_out;      // (N,H,W,head_nc) fp32
+  int head_nc, head_act;  // act: 0 tanh, 1 softmax, 2 linear
+  int N, H, W, Cout, ks;
+  int in_dt, out_dt;  // DType of in0/in1 and of out/out_pre/res/add_src/mask_src
+};
+
+int conv_fwd_simt(const ConvArgs& a, cudaStream_t st);
+int conv_fwd_tc(const ConvArgs& a, cudaStream_t st);  // tcgen05 path (bf16 in/out)
+bool conv_tc_supported(const ConvArgs& a);
+int conv_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
+
+// wgrad: dw[tap][ci][co] += alpha * sum_p x[p+off(tap)][ci] * dy[p][co]  (fp32 accumulate, atomics)
+struct WgradArgs {
+  const void* x0;
+  const void* x1;
+  int C0, C1;
+  const void* dy;
+  float* dw;  // [taps][Cin][Cout] fp32, accumulated into (caller zeroes)
+  int N, H, W, Cout, ks;
+  int x_dt, dy_dt;
+  float alpha;  // scale applied to the accumulated sum
+};
+int conv_wgrad_simt(const WgradArgs& a, cudaStream_t st);

@@ -1,0 +1,64 @@
+// Launchers for the non-convolution kernels of the hot path (defined in kernels_fwd.cu / kernels_bwd.cu).
+#pragma once
+#include "common.cuh"
+
+// ---- parameter preparation --------------------------------------------------------------------------
+// scale[c] = gamma/sqrt(var+eps), shift[c] = beta + (bias - mean)*scale  (bn != null) ; else scale=1, shift=bias
+int k_fold_bn(const float* bias, const float* gamma, const float* beta, const float* mean, const float* var,
+              float* scale, float* shift, float* inv_std, int C, cudaStream_t st);
+// dst_tc[tap][co][ci] (bf16) and dst_dgrad[flip(tap)][co][ci] (fp32) from src HWIO [tap][ci][co]
+// (dgrad variants: taps flipped, multiplied by scale[co] when scale != nullptr)
+int k_pack_conv_weights(const float* src, const float* scale, bf16* dst_tc, float* dst_dgrad, bf16* dst_tc_dgrad,
+                        int taps, int Cin, int Cout, cudaStream_t st);
+
+// ---- forward -----------------------------------------------------------------------------------------
+int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt, cudaStream_t st);
+// Conv2DTranspose k2 s2 'valid' + folded BN + ReLU (TG:307-312).  w: Keras (2,2,Cout,Cin) fp32.
+int k_deconv_fwd(const void* in, const float* w, const float* scale, const float* shift, void* out, int N, int H,
+                 int W, int Cin, int Cout, int dt, cudaStream_t st);
+// 1x1 conv (Cin -> nc_out<=4) + tanh / softmax, fp32 output (TG:494-495, TU:423-424). seg_out optional (pre-act)
+int k_head_fwd(const void* in, const float* w, const float* b, float* out, long long npix, int Cin, int nc_out,
+               int head, int dt, cudaStream_t st);
+
+struct FilmMlpArgs {          // noise path TG:353-395
+  const float* z;             // (N, L, 1)
+  const float* k0; const float* s0; const float* t0;   // dense 1->F kernel (F), folded scale/shift incl. bias (F)
+  const float* k1; const float* s1; const float* t1;   // dense F->F kernel (F,F) (in,out), folded scale/shift
+  const float* const* head_w; // device array [n_heads] of kernels (L*F, C_h) fp32
+  const float* const* head_s; // device array [n_heads] folded scale (C_h)
+  const float* const* head_t; // device array [n_heads] folded shift (C_h)
+  const int* head_c;          // device array [n_heads] widths
+  const int* head_off;        // device array [n_heads] column offset in `out`
+  int n_heads, total_c;
+  float* h1;                  // (N, L, F) post-ReLU activations (kept for backward)
+  float* h2;                  // (N, L*F) flattened post-ReLU activations
+  float* out;                 // (N, total_c): all heads side by side
+  int N, L, F;
+};
+int k_film_mlp_fwd(const FilmMlpArgs& a, cudaStream_t st);
+
+// critic tail: dis_9 (1x1, C->1) + Flatten + Dense(1) (TG:339-342). in: (N, HW, C); out (N)
+int k_critic_head_fwd(const void* in, const float* w9, const float* b9, const float* wd, const float* bd, float* out,
+                      int N, int HW, int C, int dt, cudaStream_t st);
+
+// dst(T) = src(f32) ; optional channel selection (src has cs channels, take channel 0)
+int k_convert_in(const float* src, void* dst, long long n, int dt, cudaStream_t st);
+
+// ---- train-step input preparation (TG:528-538, 556-557) ------------------------------------------------
+// which=0 (Y2 critic): real = real2, fake = base + dem ; which=1 (DEM critic): real = real2 - base, fake = dem
+// writes batch3 = [real | fake | mixed] (3N,H,W,1) in dtype dt, mixed = ep*real + (1-ep)*fake
+int k_critic_inputs(const float* real2, const float* x1, int nicg, const float* dem, const float* ep, int which,
+                    void* batch3, int N, long long hw, int dt, cudaStream_t st);
+
+// ---- inference accumulation / post-processing (EG:616-628, 673-741; EU:559-570, 597-600) ---------------
+int k_dem_accumulate(double* acc, const float* pred, const float* mask, long long n, int chan, cudaStream_t st);
+int k_dem_postproc(const float* x, int nicg, const double* acc, double n_repeat, const float* mask, double thr,
+                   double* dem_out, double* fake2_out, unsigned char* labels, unsigned long long* count,
+                   long long npix, cudaStream_t st);
+int k_uresnet_labels(const double* acc, double n_repeat, int chan, unsigned char* labels,
+                     unsigned long long* count, long long npix, cudaStream_t st);
+
+int k_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
+           float gscale, cudaStream_t st);
+
+int k_copy_to_f32(const void* src, float* dst, long long n, int dt, cudaStream_t st);

@@ -1,0 +1,458 @@
+// Forward-side non-convolution kernels: BN folding / weight packing, max-pool, k2s2 transposed conv,
+// 1x1 heads, the FiLM noise MLP, critic tail, inference accumulation and bit-exact DEM post-processing.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr float BN_EPS = 1e-3f;  // Keras BatchNormalization default epsilon
+
+template <typename T>
+__device__ __forceinline__ float ldx(const void* p, size_t i) {
+  return ldf(reinterpret_cast<const T*>(p) + i);
+}
+template <typename T>
+__device__ __forceinline__ void stx(void* p, size_t i, float v) {
+  stf(reinterpret_cast<T*>(p) + i, v);
+}
+
+__global__ void fold_bn_kernel(const float* bias, const float* gamma, const float* beta, const float* mean,
+                               const float* var, float* scale, float* shift, float* inv_std, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float b = bias ? bias[c] : 0.f;
+  if (gamma) {
+    const float is = 1.0f / sqrtf(var[c] + BN_EPS);
+    const float s = gamma[c] * is;
+    scale[c] = s;
+    shift[c] = beta[c] + (b - mean[c]) * s;
+    if (inv_std) inv_std[c] = is;
+  } else {
+    scale[c] = 1.f;
+    shift[c] = b;
+    if (inv_std) inv_std[c] = 1.f;
+  }
+}
+
+__global__ void pack_conv_kernel(const float* src, const float* scale, bf16* dst_tc, float* dst_dgrad,
+                                 bf16* dst_tc_dgrad, int taps, int Cin, int Cout) {
+  size_t total = (size_t)taps * Cin * Cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int co = i % Cout;
+    int ci = (i / Cout) % Cin;
+    int tap = i / ((size_t)Cout * Cin);
+    float v = src[i];
+    if (dst_tc) dst_tc[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);
+    // data-gradient operands: spatially flipped taps, in/out channels swapped, BN scale of the forward
+    // output channel folded in (it multiplies dy before the contraction)
+    int ft = taps - 1 - tap;
+    const float vs = scale ? v * scale[co] : v;
+    if (dst_dgrad) dst_dgrad[((size_t)ft * Cout + co) * Cin + ci] = vs;
+    if (dst_tc_dgrad) dst_tc_dgrad[((size_t)ft * Cin + ci) * Cout + co] = __float2bfloat16_rn(vs);
+  }
+}
+
+template <typename T>
+__global__ void maxpool_fwd_kernel(const T* in, T* out, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2;
+  size_t total = (size_t)N * Ho * Wo * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = i % C;
+    size_t p = i / C;
+    int wo = p % Wo;
+    int ho = (p / Wo) % Ho;
+    int n = p / ((size_t)Wo * Ho);
+    const T* b = in + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C + c;
+    float v = fmaxf(fmaxf(ldf(b), ldf(b + C)), fmaxf(ldf(b + (size_t)W * C), ldf(b + (size_t)W * C + C)));
+    stf(out + i, v);
+  }
+}
+
+// Transposed conv k2 s2: one CTA = 16 input pixels; thread o -> output (a,b,co) index, 16 pixel accumulators.
+template <typename T>
+__global__ void __launch_bounds__(128) deconv_fwd_kernel(const T* in, const float* w, const float* scale,
+                                                         const float* shift, T* out, int N, int H, int W, int Cin,
+                                                         int Cout) {
+  extern __shared__ float s_x[];  // [16][Cin]
+  const size_t npix = (size_t)N * H * W;
+  const size_t p0 = (size_t)blockIdx.x * 16;
+  for (int idx = threadIdx.x; idx < 16 * Cin; idx += blockDim.x) {
+    size_t p = p0 + idx / Cin;
+    s_x[idx] = p < npix ? ldf(in + p * Cin + idx % Cin) : 0.f;
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < 4 * Cout; o += blockDim.x) {
+    const int co = o % Cout, ab = o / Cout;
+    const float* wr = w + (size_t)o * Cin;  // Keras (2,2,Cout,Cin): [(a*2+b)*Cout + co][ci]
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float wv = wr[ci];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(s_x[i * Cin + ci], wv, acc[i]);
+    }
+    const float s = scale[co], t = shift[co];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      size_t p = p0 + i;
+      if (p >= npix) break;
+      int wi = p % W;
+      int hi = (p / W) % H;
+      size_t n = p / ((size_t)W * H);
+      size_t op = ((n * 2 * H + 2 * hi + (ab >> 1)) * 2 * W + 2 * wi + (ab & 1));
+      stf(out + op * Cout + co, fmaxf(fmaf(acc[i], s, t), 0.f));
+    }
+  }
+}
+
+template <typename T>
+__global__ void head_fwd_kernel(const T* in, const float* w, const float* b, float* out, long long npix, int Cin,
+                                int nc_out, int head) {
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= npix) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const T* x = in + p * Cin;
+  for (int c = 0; c < Cin; ++c) {
+    float v = ldf(x + c);
+    for (int k = 0; k < nc_out; ++k) acc[k] = fmaf(v, w[c * nc_out + k], acc[k]);
+  }
+  for (int k = 0; k < nc_out; ++k) acc[k] += b[k];
+  if (head == 0) {
+    for (int k = 0; k < nc_out; ++k) out[p * nc_out + k] = tanhf(acc[k]);
+  } else if (head == 1) {
+    float m = acc[0];
+    for (int k = 1; k < nc_out; ++k) m = fmaxf(m, acc[k]);
+    float e[4], s = 0.f;
+    for (int k = 0; k < nc_out; ++k) { e[k] = expf(acc[k] - m); s += e[k]; }
+    for (int k = 0; k < nc_out; ++k) out[p * nc_out + k] = e[k] / s;
+  } else {
+    for (int k = 0; k < nc_out; ++k) out[p * nc_out + k] = acc[k];
+  }
+}
+
+// FiLM MLP stage A: one CTA per sample, L*F threads (<=1024).
+__global__ void film_stage_a_kernel(FilmMlpArgs a) {
+  extern __shared__ float s_h1[];  // [L][F]
+  const int n = blockIdx.x, L = a.L, Fd = a.F;
+  const int l = threadIdx.x / Fd, f = threadIdx.x % Fd;
+  float v = a.z[(size_t)n * L + l] * a.k0[f];
+  v = fmaxf(fmaf(v, a.s0[f], a.t0[f]), 0.f);
+  s_h1[l * Fd + f] = v;
+  a.h1[((size_t)n * L + l) * Fd + f] = v;
+  __syncthreads();
+  float acc = 0.f;
+  for (int k = 0; k < Fd; ++k) acc = fmaf(s_h1[l * Fd + k], a.k1[k * Fd + f], acc);
+  a.h2[((size_t)n * L + l) * Fd + f] = fmaxf(fmaf(acc, a.s1[f], a.t1[f]), 0.f);
+}
+
+// FiLM MLP stage B: out[n, off_h + c] = s_h[c] * sum_k h2[n,k] W_h[k,c] + t_h[c].
+// CTA = 32 columns x 8 samples; 128 threads = 32 columns x 4 k-slices.
+__global__ void __launch_bounds__(128) film_stage_b_kernel(FilmMlpArgs a) {
+  extern __shared__ float s_h2[];  // [8][K]
+  __shared__ float s_red[4][8][32];
+  const int K = a.L * a.F;
+  const int col0 = blockIdx.x * 32, n0 = blockIdx.y * 8;
+  int h = 0;
+  for (int i = 0; i < a.n_heads; ++i)
+    if (col0 >= a.head_off[i]) h = i;
+  const int C = a.head_c[h], cl0 = col0 - a.head_off[h];
+  const float* W = a.head_w[h];
+  for (int idx = threadIdx.x; idx < 8 * K; idx += blockDim.x) {
+    int s = idx / K;
+    s_h2[idx] = (n0 + s < a.N) ? a.h2[(size_t)(n0 + s) * K + idx % K] : 0.f;
+  }
+  __syncthreads();
+  const int cx = threadIdx.x & 31, kq = threadIdx.x >> 5;
+  float acc[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) acc[s] = 0.f;
+  const int kpart = (K + 3) / 4;
+  const int k_end = min(K, (kq + 1) * kpart);
+  for (int k = kq * kpart; k < k_end; ++k) {
+    const float wv = W[(size_t)k * C + cl0 + cx];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) acc[s] = fmaf(s_h2[s * K + k], wv, acc[s]);
+  }
+#pragma unroll
+  for (int s = 0; s < 8; ++s) s_red[kq][s][cx] = acc[s];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 8 * 32; idx += blockDim.x) {
+    int s = idx >> 5, c = idx & 31;
+    if (n0 + s >= a.N) continue;
+    float v = s_red[0][s][c] + s_red[1][s][c] + s_red[2][s][c] + s_red[3][s][c];
+    a.out[(size_t)(n0 + s) * a.total_c + col0 + c] = fmaf(v, a.head_s[h][cl0 + c], a.head_t[h][cl0 + c]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) critic_head_fwd_kernel(const T* in, const float* w9, const float* b9,
+                                                              const float* wd, const float* bd, float* out, int HW,
+                                                              int C) {
+  __shared__ float s_part[8];
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float acc = 0.f;
+  for (int p = warp; p < HW; p += 8) {
+    const T* x = in + ((size_t)n * HW + p) * C;
+    float d = 0.f;
+    for (int c = lane; c < C; c += 32) d = fmaf(ldf(x + c), w9[c], d);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    acc = fmaf(d + b9[0], wd[p], acc);
+  }
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = bd[0];
+    for (int i = 0; i < 8; ++i) s += s_part[i];
+    out[n] = s;
+  }
+}
+
+template <typename T>
+__global__ void convert_in_kernel(const float* src, T* dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    stf(dst + i, src[i]);
+}
+template <typename T>
+__global__ void copy_to_f32_kernel(const T* src, float* dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = ldf(src + i);
+}
+
+template <typename T>
+__global__ void critic_inputs_kernel(const float* real2, const float* x1, int nicg, const float* dem,
+                                     const float* ep, int which, T* batch3, int N, long long hw) {
+  const long long total = (long long)N * hw;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float base = x1[i * nicg];
+    const float d = dem[i];
+    float real, fake;
+    if (which == 0) { real = real2[i]; fake = base + d; }
+    else { real = real2[i] - base; fake = d; }
+    const float e = ep[i / hw];
+    stf(batch3 + i, real);
+    stf(batch3 + total + i, fake);
+    stf(batch3 + 2 * total + i, e * real + (1.f - e) * fake);
+  }
+}
+
+// ---- inference accumulation / post-processing: integer / label results must be bit-exact (EG:617-741) ----
+__global__ void dem_accumulate_kernel(double* acc, const float* pred, const float* mask, long long n, int chan) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float prod = __fmul_rn(pred[i], mask[i / chan]);  // float32 multiply, as np.multiply(f32, f32)
+    acc[i] = __dadd_rn(acc[i], (double)prod);               // float64 accumulate (np.zeros default dtype)
+  }
+}
+
+__global__ void dem_postproc_kernel(const float* x, int nicg, const double* acc, double n_repeat, const float* mask,
+                                    double thr, double* dem_out, double* fake2_out, unsigned char* labels,
+                                    unsigned long long* count, long long npix) {
+  const float thr32 = (float)thr;  // NumPy compares a float32 array with a Python float in float32
+  unsigned long long local = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double dem = __ddiv_rn(acc[i], n_repeat);         // EG:628
+    const float base = x[i * nicg];
+    double f2 = __dadd_rn((double)base, dem);               // EG:675
+    if (f2 < -1.0) f2 = -1.0;                               // EG:676
+    if (f2 > 1.0) f2 = 1.0;                                 // EG:677
+    if (dem_out) dem_out[i] = dem;
+    if (fake2_out) fake2_out[i] = f2;
+    if (f2 > thr && mask[i] != 0.f) ++local;                // EG:679-682 (strict >, times mask, count_nonzero)
+    const bool f_ge = f2 >= thr, f_lt = f2 < thr;           // EG:723-741 (NaN: every comparison false)
+    const bool b_ge = base >= thr32, b_lt = base < thr32;
+    unsigned char lab = 0;
+    if (f_lt && b_ge) lab = 1;
+    if (f_ge && b_lt) lab = 2;
+    if (f_ge && b_ge) lab = 3;
+    if (labels) labels[i] = lab;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+__global__ void uresnet_labels_kernel(const double* acc, double n_repeat, int chan, unsigned char* labels,
+                                      unsigned long long* count, long long npix) {
+  unsigned long long local = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
+       i += (long long)gridDim.x * blockDim.x) {
+    int best = 0;
+    double bv = __ddiv_rn(acc[i * chan], n_repeat);
+    for (int k = 1; k < chan; ++k) {
+      double v = __ddiv_rn(acc[i * chan + k], n_repeat);
+      if (v > bv) { bv = v; best = k; }  // np.argmax: first maximum wins (EU:180)
+    }
+    labels[i] = (unsigned char)best;
+    if (best > 0) ++local;                // EU:597-600
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
+}
+
+__global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
+                            float eps, float gscale) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * gscale;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+inline int grid_for(long long n, int block = 256, int cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace
+
+int k_fold_bn(const float* bias, const float* gamma, const float* beta, const float* mean, const float* var,
+              float* scale, float* shift, float* inv_std, int C, cudaStream_t st) {
+  fold_bn_kernel<<<(C + 127) / 128, 128, 0, st>>>(bias, gamma, beta, mean, var, scale, shift, inv_std, C);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_pack_conv_weights(const float* src, const float* scale, bf16* dst_tc, float* dst_dgrad, bf16* dst_tc_dgrad,
+                        int taps, int Cin, int Cout, cudaStream_t st) {
+  if (!dst_tc && !dst_dgrad && !dst_tc_dgrad) return 0;
+  pack_conv_kernel<<<grid_for((long long)taps * Cin * Cout), 256, 0, st>>>(src, scale, dst_tc, dst_dgrad, dst_tc_dgrad,
+                                                                         taps, Cin, Cout);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt, cudaStream_t st) {
+  long long total = (long long)N * (H / 2) * (W / 2) * C;
+  if (total == 0) return 0;
+  if (dt == DT_F32)
+    maxpool_fwd_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)in, (float*)out, N, H, W, C);
+  else
+    maxpool_fwd_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)in, (bf16*)out, N, H, W, C);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_deconv_fwd(const void* in, const float* w, const float* scale, const float* shift, void* out, int N, int H,
+                 int W, int Cin, int Cout, int dt, cudaStream_t st) {
+  long long npix = (long long)N * H * W;
+  if (npix == 0) return 0;
+  int grid = (int)((npix + 15) / 16);
+  size_t smem = 16 * Cin * sizeof(float);
+  if (dt == DT_F32)
+    deconv_fwd_kernel<float><<<grid, 128, smem, st>>>((const float*)in, w, scale, shift, (float*)out, N, H, W, Cin, Cout);
+  else
+    deconv_fwd_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)in, w, scale, shift, (bf16*)out, N, H, W, Cin, Cout);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_head_fwd(const void* in, const float* w, const float* b, float* out, long long npix, int Cin, int nc_out,
+               int head, int dt, cudaStream_t st) {
+  if (npix == 0) return 0;
+  DG_REQUIRE(nc_out >= 1 && nc_out <= 4, "head: nc_out must be 1..4");
+  int grid = (int)((npix + 127) / 128);
+  if (dt == DT_F32)
+    head_fwd_kernel<float><<<grid, 128, 0, st>>>((const float*)in, w, b, out, npix, Cin, nc_out, head);
+  else
+    head_fwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)in, w, b, out, npix, Cin, nc_out, head);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_film_mlp_fwd(const FilmMlpArgs& a, cudaStream_t st) {
+  if (a.N == 0) return 0;
+  DG_REQUIRE(a.L * a.F <= 1024, "film mlp: L*F must be <= 1024");
+  DG_REQUIRE(a.total_c % 32 == 0, "film mlp: head widths must be multiples of 32");
+  film_stage_a_kernel<<<a.N, a.L * a.F, a.L * a.F * sizeof(float), st>>>(a);
+  DG_LAUNCH_CHECK();
+  dim3 grid(a.total_c / 32, (a.N + 7) / 8);
+  film_stage_b_kernel<<<grid, 128, 8 * a.L * a.F * sizeof(float), st>>>(a);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_critic_head_fwd(const void* in, const float* w9, const float* b9, const float* wd, const float* bd, float* out,
+                      int N, int HW, int C, int dt, cudaStream_t st) {
+  if (N == 0) return 0;
+  if (dt == DT_F32)
+    critic_head_fwd_kernel<float><<<N, 256, 0, st>>>((const float*)in, w9, b9, wd, bd, out, HW, C);
+  else
+    critic_head_fwd_kernel<bf16><<<N, 256, 0, st>>>((const bf16*)in, w9, b9, wd, bd, out, HW, C);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_convert_in(const float* src, void* dst, long long n, int dt, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (dt == DT_F32)
+    convert_in_kernel<float><<<grid_for(n), 256, 0, st>>>(src, (float*)dst, n);
+  else
+    convert_in_kernel<bf16><<<grid_for(n), 256, 0, st>>>(src, (bf16*)dst, n);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_copy_to_f32(const void* src, float* dst, long long n, int dt, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (dt == DT_F32)
+    copy_to_f32_kernel<float><<<grid_for(n), 256, 0, st>>>((const float*)src, dst, n);
+  else
+    copy_to_f32_kernel<bf16><<<grid_for(n), 256, 0, st>>>((const bf16*)src, dst, n);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_critic_inputs(const float* real2, const float* x1, int nicg, const float* dem, const float* ep, int which,
+                    void* batch3, int N, long long hw, int dt, cudaStream_t st) {
+  long long total = (long long)N * hw;
+  if (total == 0) return 0;
+  if (dt == DT_F32)
+    critic_inputs_kernel<float><<<grid_for(total), 256, 0, st>>>(real2, x1, nicg, dem, ep, which, (float*)batch3, N, hw);
+  else
+    critic_inputs_kernel<bf16><<<grid_for(total), 256, 0, st>>>(real2, x1, nicg, dem, ep, which, (bf16*)batch3, N, hw);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_dem_accumulate(double* acc, const float* pred, const float* mask, long long n, int chan, cudaStream_t st) {
+  if (n == 0) return 0;
+  dem_accumulate_kernel<<<grid_for(n), 256, 0, st>>>(acc, pred, mask, n, chan);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_dem_postproc(const float* x, int nicg, const double* acc, double n_repeat, const float* mask, double thr,
+                   double* dem_out, double* fake2_out, unsigned char* labels, unsigned long long* count,
+                   long long npix, cudaStream_t st) {
+  DG_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
+  if (npix == 0) return 0;
+  dem_postproc_kernel<<<grid_for(npix), 256, 0, st>>>(x, nicg, acc, n_repeat, mask, thr, dem_out, fake2_out, labels,
+                                                      count, npix);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_uresnet_labels(const double* acc, double n_repeat, int chan, unsigned char* labels, unsigned long long* count,
+                     long long npix, cudaStream_t st) {
+  DG_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
+  if (npix == 0) return 0;
+  uresnet_labels_kernel<<<grid_for(npix), 256, 0, st>>>(acc, n_repeat, chan, labels, count, npix);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
+           float gscale, cudaStream_t st) {
+  if (n == 0) return 0;
+  adam_kernel<<<grid_for(n), 256, 0, st>>>(p, g, m, v, n, lr_t, b1, b2, eps, gscale);
+  DG_LAUNCH_CHECK();
+  return 0;
+}

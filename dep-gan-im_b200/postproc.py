@@ -1,0 +1,83 @@
+"""Inference repeat loop and DEM post-processing on the GPU (EG:616-628, 673-741; EU:553-570, 597-600).
+
+The float64 accumulation order (repeat 0, 1, ...) and every comparison follow the reference's NumPy code, so the
+label maps and WMH voxel counts are bit-exact given the same predictions.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .api import _stream, _torch
+
+
+class DemAccumulator:
+    """acc = zeros(float64); acc += float64(pred_f32 * mask_f32) per repeat; mean = acc / n (EG:617-628)."""
+
+    def __init__(self, shape, device="cuda:0"):
+        torch = _torch()
+        self.torch, self.device = torch, torch.device(device)
+        self.shape = tuple(shape)
+        self.acc = torch.zeros(self.shape, dtype=torch.float64, device=self.device)
+        self.n = 0
+
+    def add(self, pred, mask):
+        """pred (Z,H,W[,C]) float32 CUDA tensor, mask (Z,H,W) float32 CUDA tensor."""
+        torch = self.torch
+        chan = pred.numel() // max(1, mask.numel()) if mask.numel() else 1
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_dem_accumulate(self.acc.data_ptr(), pred.data_ptr(), mask.data_ptr(),
+                                                        pred.numel(), int(chan), _stream(torch)), "dem_accumulate")
+        self.n += 1
+
+
+def dem_postproc_device(x, nicg, acc, n_repeat, mask, thr):
+    """Returns (dem f64, fake2 f64, labels u8, count tensor u64[1]) CUDA tensors for a (Z,H,W) volume."""
+    torch = _torch()
+    dev = acc.device
+    npix = acc.numel()
+    dem = torch.empty_like(acc)
+    fake2 = torch.empty_like(acc)
+    labels = torch.empty(acc.shape, dtype=torch.uint8, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().depgan_dem_postproc(x.data_ptr(), int(nicg), acc.data_ptr(), float(n_repeat),
+                                                  mask.data_ptr(), float(thr), dem.data_ptr(), fake2.data_ptr(),
+                                                  labels.data_ptr(), count.data_ptr(), npix, _stream(torch)),
+                   "dem_postproc")
+    return dem, fake2, labels, count
+
+
+def dem_pipeline(x1, preds, mask, thr, nicg=1, device="cuda:0"):
+    """NumPy convenience wrapper: x1 (Z,H,W,nicg) f32, preds list of (Z,H,W) f32, mask (Z,H,W) f32.
+    Returns (dem f64, fake2 f64, labels uint8, count int) as the reference computes them."""
+    torch = _torch()
+    dev = torch.device(device)
+    x = torch.from_numpy(np.ascontiguousarray(x1, np.float32)).to(dev)
+    m = torch.from_numpy(np.ascontiguousarray(mask, np.float32)).to(dev)
+    acc = DemAccumulator(m.shape, dev)
+    for p in preds:
+        acc.add(torch.from_numpy(np.ascontiguousarray(p, np.float32)).to(dev), m)
+    dem, fake2, labels, count = dem_postproc_device(x, nicg, acc.acc, float(len(preds)), m, thr)
+    return dem.cpu().numpy(), fake2.cpu().numpy(), labels.cpu().numpy(), int(count.item())
+
+
+def uresnet_pipeline(preds, mask, device="cuda:0"):
+    """preds list of (Z,H,W,C) f32 softmax maps, mask (Z,H,W).  Returns (mean f64, labels uint8, count)."""
+    torch = _torch()
+    dev = torch.device(device)
+    m = torch.from_numpy(np.ascontiguousarray(mask, np.float32)).to(dev)
+    chan = preds[0].shape[-1]
+    acc = DemAccumulator(preds[0].shape, dev)
+    for p in preds:
+        acc.add(torch.from_numpy(np.ascontiguousarray(p, np.float32)).to(dev), m)
+    labels = torch.empty(m.shape, dtype=torch.uint8, device=dev)
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().depgan_uresnet_labels(acc.acc.data_ptr(), float(len(preds)), int(chan),
+                                                    labels.data_ptr(), count.data_ptr(), m.numel(), _stream(torch)),
+                   "uresnet_labels")
+    mean = (acc.acc / float(len(preds))).cpu().numpy()
+    return mean, labels.cpu().numpy(), int(count.item())

@@ -1,0 +1,147 @@
+/* depgan_b200 -- C ABI of the B200-native DEP-GAN / DEP-UResNet hot path.
+ *
+ * The reference (febrianrachmadi/dep-gan-im) has no FFI of its own: its boundary is the Keras object surface
+ * its four scripts use.  Every entry point below cites the reference call it replaces
+ * (TG = DEP-GAN_PROB_IM_twoCritics_training_4fold.py, EG = DEP-GAN_testing_4fold.py,
+ *  TU = DEP-UResNet-wNoises-training-4fold.py, EU = DEP-UResNet_testing_4fold.py).
+ *
+ * Conventions: plain pointers and sizes only; all *_dev pointers are CUDA device pointers owned by the caller;
+ * every compute call is asynchronous on `stream` (a cudaStream_t passed as void*); return 0 = ok, <0 = error
+ * (message via depgan_last_error()); no exceptions cross the boundary; no allocation after *_create.
+ * One handle per (device, network); a handle is not thread-safe, distinct handles are.
+ * Layouts: images NHWC float32; noise (N,L,1) float32; parameters = one flat float32 buffer in Keras tensor
+ * layouts (Conv2D HWIO, Conv2DTranspose (kh,kw,Cout,Cin), Dense (in,out), BN gamma/beta/mean/var) at the
+ * offsets reported by depgan_manifest_entry().
+ */
+#ifndef DEPGAN_B200_H
+#define DEPGAN_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEPGAN_MODEL_GEN 0     /* Gen_UNet2D   TG:349-498 / TU:291-428 */
+#define DEPGAN_MODEL_CRITIC 1  /* Dis_C2D_FCN1 TG:316-345 */
+
+#define DEPGAN_PREC_FP32 0 /* fp32 activations, fp32 CUDA-core implicit GEMM (the <=1e-4 variant) */
+#define DEPGAN_PREC_BF16 1 /* bf16 activations, tcgen05/TMEM implicit GEMM, fp32 accumulate (<=1e-2) */
+
+#define DEPGAN_HEAD_TANH 0    /* DEP-GAN generator TG:494-495 */
+#define DEPGAN_HEAD_SOFTMAX 1 /* DEP-UResNet TU:423-424 */
+
+typedef struct depgan_cfg {
+  int H, W;       /* slice size (256,256 in the reference, TG:40); multiples of 16 */
+  int nicg;       /* generator input channels TG:22 (critic: ignored, always 1) */
+  int nc_out;     /* generator output channels: 1 = tanh head, 4 = softmax head */
+  int noise_len;  /* noiseSize TG:41 (32) */
+  int max_batch;  /* workspace is sized for this many slices per call */
+  int precision;  /* DEPGAN_PREC_* */
+  int training;   /* 1: also reserve backward / double-backward buffers */
+} depgan_cfg;
+
+typedef struct depgan_net depgan_net; /* opaque: one generator or one critic */
+
+const char* depgan_last_error(void);
+int depgan_abi_version(void);
+
+/* ---- weight manifest (host only; mirrors Keras layer/weight names of the reference) ---- */
+int depgan_manifest_count(int model, const depgan_cfg* cfg);
+/* name: "<keras layer>/<weight>" e.g. "conv2d_gen_0/kernel"; shape has ndim (<=4) entries;
+ * offset = float offset into the flat parameter buffer; trainable = 0 for BN moving statistics. */
+int depgan_manifest_entry(int model, const depgan_cfg* cfg, int idx, char* name, int name_cap, int* ndim,
+                          int* shape, long long* offset, int* trainable);
+long long depgan_manifest_floats(int model, const depgan_cfg* cfg); /* flat buffer length incl. padding */
+
+/* ---- network handles ---- */
+long long depgan_workspace_bytes(int model, const depgan_cfg* cfg);
+/* Replaces Gen_UNet2D(...) TG:520/EG:380/TU:579/EU:399 and Dis_C2D_FCN1(...) TG:513,516.
+ * params_dev: flat parameters (caller-owned, may be updated in place by depgan_adam_step);
+ * grads_dev: flat gradient buffer of the same length (may be NULL when cfg->training == 0). */
+depgan_net* depgan_net_create(int model, const depgan_cfg* cfg, float* params_dev, float* grads_dev,
+                              void* workspace_dev, long long workspace_bytes);
+void depgan_net_destroy(depgan_net* h);
+/* Re-derive folded BN scale/shift and packed (bf16 / dgrad) weights after the flat parameters changed.
+ * Replaces the implicit variable read of every session.run; call after load_weights (EG:383) / Adam. */
+int depgan_net_prepare(depgan_net* h, void* stream);
+
+/* ---- forward: model.predict([x, z]) EG:621, EU:558, TG:848 ; critic.predict(x) TG:846-848 ---- */
+int depgan_gen_forward(depgan_net* g, const float* x_dev, const float* z_dev, float* out_dev, int n, void* stream);
+int depgan_critic_forward(depgan_net* d, const float* x_dev, float* out_dev, int n, void* stream);
+
+/* ---- train-step graphs (gradients only; the optimizer is depgan_adam_step) ----
+ * depgan_critic_grads: netD_y2_train (which=0, TG:532-552) / netD_dem_train (which=1, TG:554-571) without the
+ *   update: runs G forward (phase 0), critic on real/fake/mixed, gradient penalty double-backward, writes
+ *   d loss / d theta_D into d's gradient buffer and {loss_real, loss_fake, grad_penalty, loss} to out4_dev.
+ * depgan_gen_eval: netG_no_update TG:595-596 -> {loss, loss_fake, loss_fake_dem, M1, M3, M4} (out6_dev);
+ *   sums_dev (3 doubles: sum wmh_real, sum wmh_fake, sum intersection) lets data-parallel callers all-reduce
+ *   the batch-global dice/volume terms; global_n = global batch for the means.
+ * depgan_gen_grads: netG_train TG:597-598 without the update. */
+int depgan_critic_grads(depgan_net* d, depgan_net* g, int which, const float* real2_dev, const float* x1_dev,
+                        const float* z_dev, const float* ep_dev, float* out4_dev, int n, int global_n, void* stream);
+int depgan_gen_eval(depgan_net* g, depgan_net* dy2, depgan_net* ddem, const float* x1_dev, const float* real2_dev,
+                    const float* z_dev, float thr, float* out6_dev, double* sums_dev, int n, int global_n,
+                    void* stream);
+int depgan_gen_grads(depgan_net* g, depgan_net* dy2, depgan_net* ddem, const float* x1_dev, const float* real2_dev,
+                     const float* z_dev, float thr, float* out6_dev, double* sums_dev, int n, int global_n,
+                     void* stream);
+/* Final generator-loss terms from (possibly all-reduced) partial sums: out6 = combine(partials). */
+int depgan_gen_loss_finalize(float* out6_dev, const double* sums_dev, void* stream);
+
+/* Keras-form Adam (keras.optimizers.Adam.get_updates; call sites TG:549,568,594; TU:427):
+ * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m=b1*m+(1-b1)*g; v=b2*v+(1-b2)*g^2; p -= lr_t*m/(sqrt(v)+eps).
+ * grad_scale multiplies g first (1/world after a sum all-reduce). t is 1-based. */
+int depgan_adam_step(float* params_dev, const float* grads_dev, float* m_dev, float* v_dev, long long n, int t,
+                     float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ---- inference accumulation + DEM post-processing (bit-exact integer/label work) ----
+ * depgan_dem_accumulate: acc_f64 += (double)(pred_f32 * mask_f32)      EG:622-624 / EU:559-560
+ *   (mask index = i / chan, so a (Z,H,W) mask broadcasts over nc_out channels).
+ * depgan_dem_postproc: dem = acc/n_repeat; fake2 = clip(base + dem, -1, 1); count = #((fake2 > thr) * mask != 0);
+ *   label 1/2/3 = shrink/grow/stay                                     EG:628, 673-686, 711-741
+ *   base is channel 0 of x (stride nicg floats).  count_dev: one unsigned long long (zeroed by the call).
+ * depgan_uresnet_labels: argmax over 4 mean probabilities (first max wins) + count(label>0)  EU:570, 597-600 */
+int depgan_dem_accumulate(double* acc_dev, const float* pred_dev, const float* mask_dev, long long n, int chan,
+                          void* stream);
+int depgan_dem_postproc(const float* x_dev, int nicg, const double* acc_dev, double n_repeat,
+                        const float* mask_dev, double thr, double* dem_out_dev, double* fake2_out_dev,
+                        unsigned char* labels_dev, unsigned long long* count_dev, long long npix, void* stream);
+int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, unsigned char* labels_dev,
+                          unsigned long long* count_dev, long long npix, void* stream);
+
+/* ---- introspection for tests / profiling ---- */
+/* Number of kernels this library launched since load (all handles). */
+long long depgan_launch_count(void);
+/* Copy an internal activation of the last forward over n slices (by keras layer suffix, e.g. "gen_0",
+ * "gen_noise_m1" = the ResBlock sum, "de_gen_9", "conv2d_dis_3", or "film" = all FiLM vectors) to out_dev as
+ * float32. */
+int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, long long cap_floats,
+                            long long* n_floats, int n, void* stream);
+
+/* ---- kernel-level entry points (parity tests and micro-benchmarks of the convolution kernels) ----
+ * One fused 'same' stride-1 convolution (Keras Conv2D TG:285-304 / Conv2DTranspose k2s2 TG:307-312 when
+ * deconv=1) on caller-owned device buffers.  Epilogue order: v = acc*scale+shift; out_pre=v;
+ * FiLM: v = relu(v*film_g[n,c]+film_b[n,c]) + res; v += add_src; v = mask_src>0 ? v : 0; relu; out = v;
+ * head: head_out = act(v . head_w + head_b) (act 0 tanh, 1 softmax, 2 linear).
+ * use_tc=1: tcgen05/TMEM path (bf16 in/out, w_bf16 [taps][Ncols][Cin]); use_tc=0: fp32 CUDA-core path
+ * (w_f32 [taps][Cin][Cout], any dtype combination). */
+typedef struct depgan_conv_desc {
+  const void* in0; const void* in1; int C0, C1;
+  const float* w_f32; const void* w_bf16;
+  const float* scale; const float* shift;
+  void* out; void* out_pre;
+  const float* film_g; const float* film_b; int film_stride; const void* res;
+  const void* add_src; const void* mask_src;
+  int relu, deconv;
+  const float* head_w; const float* head_b; float* head_out; int head_nc, head_act;
+  int N, H, W, Cout, ks;
+  int in_bf16, out_bf16, use_tc;
+} depgan_conv_desc;
+int depgan_op_conv2d(const depgan_conv_desc* d, void* stream);
+int depgan_op_pack_weights(const float* w_f32_dev, void* w_bf16_dev, int taps, int cin, int cout, void* stream);
+int depgan_op_f32_to_bf16(const float* src_dev, void* dst_dev, long long n, void* stream);
+int depgan_op_bf16_to_f32(const void* src_dev, float* dst_dev, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,138 @@
+"""Kernel-level parity of the convolution kernels (through the C ABI, depgan_op_conv2d) against torch-CPU fp32
+references of the same Keras ops (Conv2D 'same' TG:285-304, Conv2DTranspose k2s2 TG:307-312)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def ref_conv(x, w, x1=None, scale=None, shift=None, relu=False, film=None, res=None, add=None, mask=None):
+    """x NHWC fp32 (cpu), w HWIO.  Mirrors the epilogue order documented in include/depgan_b200.h."""
+    if x1 is not None:
+        x = torch.cat([x, x1], dim=3)
+    k = w.shape[0]
+    y = F.conv2d(x.permute(0, 3, 1, 2).double(), w.permute(3, 2, 0, 1).double(), padding=k // 2).permute(0, 2, 3, 1)
+    if scale is not None:
+        y = y * scale.double()
+    if shift is not None:
+        y = y + shift.double()
+    pre = y.clone()
+    if film is not None:
+        y = torch.relu(y * film[0][:, None, None, :].double() + film[1][:, None, None, :].double()) + res.double()
+    if add is not None:
+        y = y + add.double()
+    if mask is not None:
+        y = torch.where(mask > 0, y, torch.zeros_like(y))
+    if relu:
+        y = torch.relu(y)
+    return y.float(), pre.float()
+
+
+def ref_deconv(x, w, scale, shift):
+    """Keras Conv2DTranspose k2 s2 valid, kernel (2,2,Cout,Cin), then affine + relu."""
+    y = F.conv_transpose2d(x.permute(0, 3, 1, 2).double(), w.permute(3, 2, 0, 1).double(), stride=2).permute(0, 2, 3, 1)
+    return torch.relu(y * scale.double() + shift.double()).float()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(shape, generator=g) * scale
+
+
+@pytest.mark.parametrize("ks,c0,c1,cout", [(3, 1, 0, 32), (3, 2, 0, 32), (3, 32, 0, 32), (5, 1, 0, 16), (5, 16, 0, 16),
+                                           (1, 32, 0, 4), (3, 24, 8, 40), (3, 16, 0, 1)])
+def test_simt_conv_matches_fp32_reference(ks, c0, c1, cout):
+    from depgan_b200 import conv2d_op
+    N, H, W = 2, 32, 48
+    x = _rand((N, H, W, c0), 1)
+    x1 = _rand((N, H, W, c1), 2) if c1 else None
+    w = _rand((ks, ks, c0 + c1, cout), 3, 0.2)
+    sc, sh = 1 + 0.1 * _rand((cout,), 4), 0.1 * _rand((cout,), 5)
+    got = conv2d_op(x.cuda(), w.cuda(), x1=None if x1 is None else x1.cuda(), scale=sc, shift=sh, relu=True,
+                    use_tc=False).cpu()
+    want, _ = ref_conv(x, w, x1, sc, sh, relu=True)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4), float((got - want).abs().max())
+
+
+def test_simt_conv_film_mask_epilogues():
+    from depgan_b200 import conv2d_op
+    N, H, W, c = 2, 16, 32, 32
+    x, w = _rand((N, H, W, c), 1), _rand((3, 3, c, c), 2, 0.1)
+    g, b, res = 1 + 0.3 * _rand((N, c), 3), 0.2 * _rand((N, c), 4), _rand((N, H, W, c), 5)
+    got, ex = conv2d_op(x.cuda(), w.cuda(), film=(g, b), res=res.cuda(), use_tc=False, want_pre=True)
+    want, pre = ref_conv(x, w, film=(g, b), res=res)
+    assert torch.allclose(got.cpu(), want, atol=2e-4, rtol=1e-4)
+    assert torch.allclose(ex["pre"].cpu(), pre, atol=2e-4, rtol=1e-4)
+    mask, add = _rand((N, H, W, c), 6), _rand((N, H, W, c), 7)
+    got = conv2d_op(x.cuda(), w.cuda(), add=add.cuda(), mask=mask.cuda(), use_tc=False).cpu()
+    want, _ = ref_conv(x, w, add=add, mask=mask)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
+
+
+TC_CASES = [  # ks, c0, c1, cout, H, W   (kc = 64 / 32 / 16 chunking, two sources, n-split)
+    (3, 64, 0, 64, 32, 32), (3, 32, 0, 32, 32, 48), (3, 96, 0, 96, 16, 32), (3, 16, 0, 16, 32, 32),
+    (5, 16, 0, 32, 32, 32), (5, 32, 0, 32, 16, 16), (3, 64, 32, 32, 32, 32), (3, 128, 96, 96, 16, 16),
+    (3, 128, 0, 256, 16, 16), (3, 256, 0, 256, 16, 16), (1, 64, 0, 64, 16, 32), (3, 96, 64, 64, 32, 16),
+]
+
+
+@pytest.mark.parametrize("ks,c0,c1,cout,H,W", TC_CASES)
+def test_tcgen05_conv_matches_reference(ks, c0, c1, cout, H, W):
+    from depgan_b200 import conv2d_op
+    N = 3
+    x = _bf(_rand((N, H, W, c0), 1))
+    x1 = _bf(_rand((N, H, W, c1), 2)) if c1 else None
+    w = _bf(_rand((ks, ks, c0 + c1, cout), 3, 1.0 / np.sqrt(ks * ks * (c0 + c1))))
+    sc, sh = 1 + 0.1 * _rand((cout,), 4), 0.1 * _rand((cout,), 5)
+    got = conv2d_op(x.cuda(), w.cuda(), x1=None if x1 is None else x1.cuda(), scale=sc, shift=sh, relu=True,
+                    use_tc=True).cpu()
+    want, _ = ref_conv(x, w, x1, sc, sh, relu=True)
+    err = float((got - want).abs().max())
+    assert err <= 1e-2 * max(1.0, float(want.abs().max())), err  # bf16 output rounding: 2^-9 relative
+
+
+def test_tcgen05_conv_film_residual_and_mask():
+    from depgan_b200 import conv2d_op
+    N, H, W, c = 2, 32, 32, 64
+    x, w = _bf(_rand((N, H, W, c), 1)), _bf(_rand((3, 3, c, c), 2, 0.05))
+    g, b, res = 1 + 0.3 * _rand((N, c), 3), 0.2 * _rand((N, c), 4), _bf(_rand((N, H, W, c), 5))
+    got, ex = conv2d_op(x.cuda(), w.cuda(), film=(g, b), res=res.cuda(), use_tc=True, want_pre=True)
+    want, pre = ref_conv(x, w, film=(g, b), res=res)
+    assert float((got.cpu() - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
+    assert float((ex["pre"].cpu() - pre).abs().max()) <= 2e-2 * max(1.0, float(pre.abs().max()))
+    mask, add = _bf(_rand((N, H, W, c), 6)), _bf(_rand((N, H, W, c), 7))
+    got = conv2d_op(x.cuda(), w.cuda(), add=add.cuda(), mask=mask.cuda(), use_tc=True).cpu()
+    want, _ = ref_conv(x, w, add=add, mask=mask)
+    assert float((got - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("c", [64, 96, 128])
+def test_tcgen05_transposed_conv(c):
+    from depgan_b200 import conv2d_op
+    N, H, W = 2, 16, 32
+    x = _bf(_rand((N, H, W, c), 1))
+    w = _bf(_rand((2, 2, c, c), 2, 1.0 / np.sqrt(c)))
+    sc, sh = 1 + 0.1 * _rand((c,), 4), 0.1 * _rand((c,), 5)
+    got = conv2d_op(x.cuda(), w.cuda(), scale=sc, shift=sh, relu=True, deconv=True, use_tc=True).cpu()
+    want = ref_deconv(x, w, sc, sh)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= 1e-2 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("nc,act", [(1, 0), (4, 1)])
+def test_tcgen05_conv_fused_head(nc, act):
+    from depgan_b200 import conv2d_op
+    N, H, W, c = 2, 32, 32, 32
+    x, w = _bf(_rand((N, H, W, c), 1)), _bf(_rand((3, 3, c, c), 2, 0.08))
+    hw, hb = _rand((c, nc), 3, 0.3), 0.1 * _rand((nc,), 4)
+    got, ex = conv2d_op(x.cuda(), w.cuda(), relu=True, head=(hw, hb, act), use_tc=True)
+    y, _ = ref_conv(x, w, relu=True)
+    seg = y.double() @ hw.double() + hb.double()
+    want = torch.tanh(seg) if act == 0 else torch.softmax(seg, dim=-1)
+    assert float((ex["head"].cpu().double() - want).abs().max()) <= 1e-2

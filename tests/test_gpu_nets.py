@@ -1,0 +1,107 @@
+"""Whole-network parity through the Keras-like surface / C ABI against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from depgan_b200 import synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("nicg,nc_out,head", [(1, 1, "tanh"), (2, 1, "tanh"), (1, 4, "softmax")])
+def test_generator_fp32_matches_oracle(nicg, nc_out, head):
+    from depgan_b200 import Gen_UNet2D
+    H = W = 64
+    P = util.gen_weights(nicg, nc_out, seed=3)
+    x, _, _ = synth.make_im_pair(3, H, W, nicg=nicg, seed=1)
+    z = synth.make_noise(3, seed=2)
+    g = Gen_UNet2D((H, W, nicg), (32, 1), 32, nc_out, precision="fp32", max_batch=4)
+    g.set_weights(P)
+    got = g.predict([x, z])
+    want = util.oracle_gen(P, x, z, head)
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.abs(got - want).max() <= 1e-4, np.abs(got - want).max()  # FP32-accumulate variant (BASELINE.json)
+
+
+@pytest.mark.parametrize("nicg,nc_out,head", [(1, 1, "tanh"), (2, 1, "tanh"), (1, 4, "softmax")])
+def test_generator_bf16_tcgen05_matches_oracle(nicg, nc_out, head):
+    from depgan_b200 import Gen_UNet2D
+    H = W = 64
+    P = util.gen_weights(nicg, nc_out, seed=3)
+    x, _, _ = synth.make_im_pair(3, H, W, nicg=nicg, seed=1)
+    z = synth.make_noise(3, seed=2)
+    g = Gen_UNet2D((H, W, nicg), (32, 1), 32, nc_out, precision="bf16", max_batch=4)
+    g.set_weights(P)
+    got = g.predict([x, z])
+    want = util.oracle_gen(P, x, z, head)
+    assert np.abs(got - want).max() <= 1e-2, np.abs(got - want).max()  # DEM tolerance of BASELINE.json
+
+
+def test_generator_intermediate_activations_fp32():
+    from depgan_b200 import Gen_UNet2D
+    from oracle import depgan_oracle as O
+    H = W = 32
+    P = util.gen_weights(1, 1, seed=5)
+    x, _, _ = synth.make_im_pair(2, H, W, seed=1)
+    z = synth.make_noise(2, seed=2)
+    g = Gen_UNet2D((H, W, 1), precision="fp32", max_batch=2)
+    g.set_weights(P)
+    g.predict([x, z])
+    Pt = O.to_torch(P, torch.float64)
+    with torch.no_grad():
+        film = O.film_params(Pt, torch.as_tensor(z, dtype=torch.float64))
+        _, acts = O.gen_forward(Pt, torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(z, dtype=torch.float64),
+                                return_acts=True)
+    got_film = g.debug_activation("film", 2).reshape(2, -1)
+    off = 0
+    for bi, suf in enumerate(["_m1", "_m2", "_m3", "", "_p3", "_p2", "_p1"]):
+        for k in range(2):
+            want = film[suf][k].numpy()
+            c = want.shape[1]
+            assert np.abs(got_film[:, off:off + c] - want).max() <= 1e-4, (suf, k)
+            off += c
+    for name in ["gen_0", "gen_1", "gen_3", "gen_9", "de_gen_9", "gen_10", "gen_17"]:
+        want = acts[name].permute(0, 2, 3, 1).numpy()
+        got = g.debug_activation(name, 2).reshape(want.shape)
+        assert np.abs(got - want).max() <= 2e-4, name
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_critic_matches_oracle(precision, tol):
+    from depgan_b200 import Dis_C2D_FCN1
+    H = W = 64
+    P = util.critic_weights(H, W, seed=7)
+    _, y2, _ = synth.make_im_pair(3, H, W, seed=4)
+    d = Dis_C2D_FCN1((H, W, 1), precision=precision, max_batch=4)
+    d.set_weights(P)
+    got = d.predict(y2)
+    want = util.oracle_critic(P, y2)
+    scale = max(1.0, float(np.abs(want).max()))
+    assert got.shape == (3, 1)
+    assert np.abs(got - want).max() <= tol * scale, (got.ravel(), want.ravel())
+
+
+def test_predict_batching_does_not_change_results():
+    from depgan_b200 import Gen_UNet2D
+    H = W = 32
+    x, _, _ = synth.make_im_pair(5, H, W, seed=1)
+    z = synth.make_noise(5, seed=2)
+    g = Gen_UNet2D((H, W, 1), precision="bf16", max_batch=8)
+    a = g.predict([x, z], batch_size=8)
+    b = g.predict([x, z], batch_size=2)
+    assert np.array_equal(a, b)
+
+
+def test_full_size_generator_bf16_256():
+    """BASELINE config 1 shape (256x256, batch 16 here reduced to 4 for oracle time) within the DEM tolerance."""
+    from depgan_b200 import Gen_UNet2D
+    H = W = 256
+    P = util.gen_weights(1, 1, seed=11, trained_like=False)
+    x, _, _ = synth.make_im_pair(2, H, W, seed=1)
+    z = synth.make_noise(2, seed=2)
+    g = Gen_UNet2D((H, W, 1), precision="bf16", max_batch=2)
+    g.set_weights(P)
+    got = g.predict([x, z])
+    want = util.oracle_gen(P, x, z, dtype=torch.float32)
+    assert np.abs(got - want).max() <= 1e-2, np.abs(got - want).max()
