@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DEP-GAN hot path on B200 (contract: see the task statement / DESIGN.md).
+
+Workloads (BASELINE.json configs):
+  uresnet_infer   (default, configs[1]) DEP-UResNet inference, 256x256, batch 64 per GPU, bf16 tcgen05 path
+  depgan_infer    (configs[0])          DEP-GAN generator inference, 256x256 IM slices, batch 16
+  depgan_train    (configs[2])          DEP-GAN two-critic generator iteration, batch 32 (when built)
+
+One "step" = one pass of the hot path over one batch of synthetic slices.  `value` = slices/s with inputs
+resident in HBM; `e2e` = the same through the Keras-like public call with pinned host buffers (H2D + D2H inside
+the timed region).  N > 1 (torchrun): every rank runs its own batch, no data-path collective (weak scaling).
+`--impl reference` times the CPU oracle (torch fp32 restatement of the Keras graph; the reference itself cannot
+run here) on the host cores with the same metric/config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+G_FLOP = {(1, 1): 23.513e9, (2, 1): 23.551e9, (1, 4): 23.526e9}  # per slice
+
+WORKLOADS = {
+    "uresnet_infer": dict(nicg=1, nc_out=4, batch=64, head="softmax",
+                          desc="DEP-UResNet (wNoises) inference, 256x256, batch 64 per GPU (BASELINE configs[1])"),
+    "depgan_infer": dict(nicg=1, nc_out=1, batch=16, head="tanh",
+                         desc="DEP-GAN generator inference, 256x256 IM slices, batch 16 (BASELINE configs[0])"),
+}
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [t.strip() for t in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(w, n, seed):
+    from depgan_b200 import synth
+    if w["nc_out"] == 4:
+        x, _ = synth.make_flair(n, 256, 256, seed=seed)
+    else:
+        x, _, _ = synth.make_im_pair(n, 256, 256, nicg=w["nicg"], seed=seed)
+    return x, synth.make_noise(n, seed=seed + 1)
+
+
+def make_weights(w):
+    from depgan_b200 import synth
+    from oracle import depgan_oracle as O  # manifest only (names/shapes), shared with the tests
+    return synth.init_weights(O.gen_manifest(w["nicg"], w["nc_out"]), seed=0, trained_like=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arms (oracle): cpu_baseline leg and --impl reference
+# ---------------------------------------------------------------------------------------------------------
+def cpu_forward_rate(w, P, sample, reps):
+    import torch
+    from oracle import depgan_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    Pt = O.to_torch(P, torch.float32)
+    x, z = make_inputs(w, sample, seed=5)
+    xt, zt = torch.from_numpy(x), torch.from_numpy(z)
+    times = []
+    with torch.no_grad():
+        O.gen_forward(Pt, xt[:2], zt[:2], w["head"])  # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            O.gen_forward(Pt, xt, zt, w["head"])
+            times.append(time.perf_counter() - t0)
+    return sample / statistics.median(times), times
+
+
+def run_reference(args, w, rank):
+    if rank != 0:
+        return
+    P = make_weights(w)
+    sample = 8
+    import torch
+    from oracle import depgan_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    Pt = O.to_torch(P, torch.float32)
+    x, z = make_inputs(w, sample, seed=5)
+    xt, zt = torch.from_numpy(x), torch.from_numpy(z)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.gen_forward(Pt, xt[:2], zt[:2], w["head"])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.gen_forward(Pt, xt, zt, w["head"])
+        dt = time.perf_counter() - t0
+    val = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "256x256 slices/sec (gen inference)", "value": val, "unit": "slices/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "batch_per_step_sample": sample},
+            "cpu_baseline": {"value": val, "unit": "slices/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d-slice batches x %d steps of the torch-CPU fp32 oracle "
+                                       "(Keras reference not runnable here)" % (sample, args.steps)},
+            "e2e": {"value": val, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_gpu(args, w, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from depgan_b200 import Gen_UNet2D, _lib, launch_count
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or w["batch"]
+    P = make_weights(w)
+    g = Gen_UNet2D((256, 256, w["nicg"]), (32, 1), 32, w["nc_out"], precision=args.precision, max_batch=B,
+                   device=str(dev))
+    # weights travel through the Keras-h5 layout, as load_weights would read the shipped files
+    h5 = Path("/tmp/depgan_bench_rank%d.h5" % rank)
+    from depgan_b200 import h5lite
+    h5lite.save_keras_weights(str(h5), P, [n for n, _, _, _ in g.manifest])
+    g.load_weights(str(h5))
+
+    x, z = make_inputs(w, B, seed=100 + rank)
+    xd, zd = torch.from_numpy(x).to(dev), torch.from_numpy(z).to(dev)
+    out = torch.empty((B, 256, 256, w["nc_out"]), dtype=torch.float32, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ----
+    for _ in range(args.warmup):
+        g.forward_device(xd, zd, out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        g.forward_device(xd, zd, out)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end through predict-like public path: pinned host -> device -> host ----
+    xh, zh = torch.from_numpy(x).pin_memory(), torch.from_numpy(z).pin_memory()
+    oh = torch.empty((B, 256, 256, w["nc_out"]), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        zd.copy_(zh, non_blocking=True)
+        g.forward_device(xd, zd, out)
+        oh.copy_(out, non_blocking=True)
+
+    for _ in range(max(3, args.warmup)):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- roofline leg: per-launch CUDA events around every convolution of the same step ----
+    roof = None
+    if rank == 0:
+        L = _lib.lib()
+        ncls = 4
+        arr_ms, arr_fl, arr_by = (C.c_double * ncls)(), (C.c_double * ncls)(), (C.c_double * ncls)()
+        arr_n = (C.c_longlong * ncls)()
+        L.depgan_profile_begin()
+        psteps = 3
+        for _ in range(psteps):
+            g.forward_device(xd, zd, out)
+        _lib.check(L.depgan_profile_end(arr_ms, arr_fl, arr_by, arr_n, ncls), "profile_end")
+        pk = peaks()
+        k = 0  # class 0 = tcgen05 3x3 convolutions: the dominant kernel (conv_tc_kernel<3>)
+        if arr_n[k] > 0 and arr_ms[k] > 0:
+            achieved = arr_fl[k] / (arr_ms[k] * 1e-3) / 1e12
+            conv_share = arr_ms[k] / max(1e-9, sum(arr_ms))
+            roof = {"kernel": "conv_tc_kernel<3> (tcgen05 implicit-GEMM 3x3 conv, %d launches/step)" % (arr_n[k] // psteps),
+                    "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tf_sust"], "peak_source": pk["src"] + " (sustained bf16)",
+                    "traffic": None, "avg_launch_ms": arr_ms[k] / arr_n[k],
+                    "flops_per_launch": arr_fl[k] / arr_n[k],
+                    "hbm_gbs_same_kernel": arr_by[k] / (arr_ms[k] * 1e-3) / 1e9,
+                    "share_of_conv_time": conv_share,
+                    "other_classes_ms_per_step": {"tc5x5": arr_ms[1] / psteps, "tc_deconv": arr_ms[2] / psteps,
+                                                  "simt": arr_ms[3] / psteps, "tc3x3": arr_ms[0] / psteps}}
+        prof_path = ROOT / "profiles" / "ncu_traffic_r01.json"
+        if roof and prof_path.exists():
+            try:
+                roof["traffic"] = json.loads(prof_path.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline (oracle port) on a bounded sample ----
+    cpu = None
+    if not args.no_cpu:
+        sample = 8
+        rate, times = cpu_forward_rate(w, P, sample, reps=3)
+        cpu = {"value": rate, "unit": "slices/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d slices x %d reps (median) of the torch-CPU fp32 oracle of the same graph" % (sample, len(times))}
+
+    slices = B * args.steps * world
+    value = slices / (ms * 1e-3)
+    flop = G_FLOP[(w["nicg"], w["nc_out"])]
+    line = {
+        "metric": "256x256 slices/sec (gen inference)", "value": value, "unit": "slices/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "data": "synthetic",
+        "config": {"workload": w["desc"], "batch_per_gpu": B, "precision": args.precision,
+                   "weights": "synthetic (seeded), round-tripped through the Keras-h5 layout",
+                   "l2": "per-step activation working set (~%.1f GB) >> 126 MB L2; no explicit flush" % (B * 0.1137),
+                   "parallelism": "slices sharded across %d GPU(s), no collective" % world},
+        "tflops_effective": value * flop / 1e12,
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": slices / (ms_e2e * 1e-3), "unit": "slices/s",
+                "h2d_bytes_per_step": int(xh.numel() * 4 + zh.numel() * 4), "d2h_bytes_per_step": int(oh.numel() * 4)},
+        "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="uresnet_infer", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w, rank)
+        return
+    run_gpu(args, w, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

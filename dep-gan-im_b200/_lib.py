@@ -57,8 +57,10 @@ SIGNATURES = {
     "depgan_adam_step": (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _P]),
     "depgan_dem_accumulate": (_I, [_P, _P, _P, _LL, _I, _P]),
     "depgan_dem_postproc": (_I, [_P, _I, _P, _D, _P, _D, _P, _P, _P, _P, _LL, _P]),
-    "depgan_uresnet_labels": (_I, [_P, _D, _I, _P, _P, _LL, _P]),
+    "depgan_uresnet_labels": (_I, [_P, _D, _I, _P, _P, _P, _LL, _P]),
     "depgan_launch_count": (_LL, []),
+    "depgan_profile_begin": (_I, []),
+    "depgan_profile_end": (_I, [_P, _P, _P, _P, _I]),
     "depgan_debug_activation": (_I, [_P, C.c_char_p, _P, _LL, C.POINTER(_LL), _I, _P]),
     "depgan_op_conv2d": (_I, [C.POINTER(ConvDesc), _P]),
     "depgan_op_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),

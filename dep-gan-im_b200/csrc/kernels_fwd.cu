@@ -273,15 +273,17 @@ __global__ void dem_postproc_kernel(const float* x, int nicg, const double* acc,
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
 }
 
-__global__ void uresnet_labels_kernel(const double* acc, double n_repeat, int chan, unsigned char* labels,
-                                      unsigned long long* count, long long npix) {
+__global__ void uresnet_labels_kernel(const double* acc, double n_repeat, int chan, double* mean_out,
+                                      unsigned char* labels, unsigned long long* count, long long npix) {
   unsigned long long local = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix;
        i += (long long)gridDim.x * blockDim.x) {
     int best = 0;
     double bv = __ddiv_rn(acc[i * chan], n_repeat);
+    if (mean_out) mean_out[i * chan] = bv;
     for (int k = 1; k < chan; ++k) {
       double v = __ddiv_rn(acc[i * chan + k], n_repeat);
+      if (mean_out) mean_out[i * chan + k] = v;
       if (v > bv) { bv = v; best = k; }  // np.argmax: first maximum wins (EU:180)
     }
     labels[i] = (unsigned char)best;
@@ -440,11 +442,11 @@ int k_dem_postproc(const float* x, int nicg, const double* acc, double n_repeat,
   return 0;
 }
 
-int k_uresnet_labels(const double* acc, double n_repeat, int chan, unsigned char* labels, unsigned long long* count,
-                     long long npix, cudaStream_t st) {
+int k_uresnet_labels(const double* acc, double n_repeat, int chan, double* mean_out, unsigned char* labels,
+                     unsigned long long* count, long long npix, cudaStream_t st) {
   DG_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
   if (npix == 0) return 0;
-  uresnet_labels_kernel<<<grid_for(npix), 256, 0, st>>>(acc, n_repeat, chan, labels, count, npix);
+  uresnet_labels_kernel<<<grid_for(npix), 256, 0, st>>>(acc, n_repeat, chan, mean_out, labels, count, npix);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -265,6 +265,45 @@ int fold_dense(depgan_net* h, DenseL& D, cudaStream_t st) {
 }  // namespace
 
 // =========================================================================================================
+// optional per-launch timing (bench.py roofline leg): CUDA events around every convolution launch
+// =========================================================================================================
+namespace {
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+int conv_class(const ConvArgs& a, bool tc) {
+  if (!tc) return 3;
+  if (a.deconv) return 2;
+  return a.ks == 5 ? 1 : a.ks == 3 ? 0 : 2;
+}
+}  // namespace
+
+struct ProfScope {
+  bool on;
+  ProfRec r;
+  cudaStream_t st;
+  ProfScope(const ConvArgs& a, bool tc, cudaStream_t s) : on(g_prof_on), st(s) {
+    if (!on) return;
+    const double px = (double)a.N * a.H * a.W, cin = a.C0 + a.C1;
+    const double ncols = a.deconv ? 4.0 * a.Cout : (double)a.Cout;
+    r.cls = conv_class(a, tc);
+    r.flops = 2.0 * px * a.ks * a.ks * cin * ncols;
+    const double ies = dt_size(a.in_dt), oes = dt_size(a.out_dt);
+    r.bytes = px * cin * ies + (a.out ? px * ncols * oes : 0.0) + (a.out_pre ? px * ncols * oes : 0.0) +
+              (a.res ? px * ncols * oes : 0.0) + (a.add_src ? px * ncols * oes : 0.0) +
+              (a.mask_src ? px * ncols * oes : 0.0) + (a.head_out ? px * a.head_nc * 4.0 : 0.0);
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, st);
+    g_prof.push_back(r);
+  }
+};
+
+// =========================================================================================================
 // forward executors
 // =========================================================================================================
 int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void* in1, int C1, int in_dt, ConvArgs a,
@@ -275,7 +314,9 @@ int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void*
   a.shift = L.shift;
   a.N = n; a.H = h->lvl_h(L.lvl); a.W = h->lvl_w(L.lvl); a.Cout = L.cout; a.ks = L.ks;
   a.in_dt = in_dt; a.out_dt = h->act_dt;
-  if (h->act_dt == DT_BF16 && conv_tc_supported(a)) return conv_fwd_tc(a, st);
+  const bool tc = h->act_dt == DT_BF16 && conv_tc_supported(a);
+  ProfScope prof(a, tc, st);
+  if (tc) return conv_fwd_tc(a, st);
   if (a.head_w) {  // unfused fallback: conv, then the 1x1 head
     ConvArgs b = a;
     b.head_w = nullptr;
@@ -292,7 +333,10 @@ static int net_deconv(depgan_net* h, const ConvL& L, const void* in, void* out, 
     ConvArgs a{};
     a.in0 = in; a.C0 = L.cin; a.w_tc = L.w_tc; a.scale = L.scale; a.shift = L.shift; a.out = out; a.relu = 1;
     a.deconv = 1; a.N = n; a.H = H; a.W = W; a.Cout = L.cout; a.ks = 1; a.in_dt = DT_BF16; a.out_dt = DT_BF16;
-    if (conv_tc_supported(a)) return conv_fwd_tc(a, st);
+    if (conv_tc_supported(a)) {
+      ProfScope prof(a, true, st);
+      return conv_fwd_tc(a, st);
+    }
   }
   return k_deconv_fwd(in, h->P(L.k_off), L.scale, L.shift, out, n, H, W, L.cin, L.cout, h->act_dt, st);
 }
@@ -508,13 +552,35 @@ int depgan_dem_postproc(const float* x_dev, int nicg, const double* acc_dev, dou
   return k_dem_postproc(x_dev, nicg, acc_dev, n_repeat, mask_dev, thr, dem_out_dev, fake2_out_dev, labels_dev,
                         count_dev, npix, (cudaStream_t)stream);
 }
-int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, unsigned char* labels_dev,
-                          unsigned long long* count_dev, long long npix, void* stream) {
+int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, double* mean_out_dev,
+                          unsigned char* labels_dev, unsigned long long* count_dev, long long npix, void* stream) {
   DG_REQUIRE(chan >= 1 && labels_dev && count_dev, "uresnet_labels: bad arguments");
-  return k_uresnet_labels(acc_dev, n_repeat, chan, labels_dev, count_dev, npix, (cudaStream_t)stream);
+  return k_uresnet_labels(acc_dev, n_repeat, chan, mean_out_dev, labels_dev, count_dev, npix, (cudaStream_t)stream);
 }
 
 long long depgan_launch_count(void) { return g_launch_count; }
+
+int depgan_profile_begin(void) {
+  for (auto& r : g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+int depgan_profile_end(double* ms, double* flops, double* bytes, long long* launches, int ncls) {
+  g_prof_on = false;
+  DG_REQUIRE(ms && flops && bytes && launches && ncls >= 1, "profile_end: bad arguments");
+  for (int i = 0; i < ncls; ++i) { ms[i] = flops[i] = bytes[i] = 0.0; launches[i] = 0; }
+  DG_CHECK_CUDA(cudaDeviceSynchronize());
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    DG_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (r.cls < ncls) { ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, long long cap_floats, long long* n_floats,
                             int n, void* stream) {

@@ -76,8 +76,8 @@ def uresnet_pipeline(preds, mask, device="cuda:0"):
     labels = torch.empty(m.shape, dtype=torch.uint8, device=dev)
     count = torch.zeros(1, dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
+        mean = torch.empty_like(acc.acc)  # IEEE division in our kernel (torch.div by a scalar multiplies by 1/n)
         _lib.check(_lib.lib().depgan_uresnet_labels(acc.acc.data_ptr(), float(len(preds)), int(chan),
-                                                    labels.data_ptr(), count.data_ptr(), m.numel(), _stream(torch)),
-                   "uresnet_labels")
-    mean = (acc.acc / float(len(preds))).cpu().numpy()
-    return mean, labels.cpu().numpy(), int(count.item())
+                                                    mean.data_ptr(), labels.data_ptr(), count.data_ptr(), m.numel(),
+                                                    _stream(torch)), "uresnet_labels")
+    return mean.cpu().numpy(), labels.cpu().numpy(), int(count.item())

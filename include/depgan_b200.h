@@ -99,18 +99,26 @@ int depgan_adam_step(float* params_dev, const float* grads_dev, float* m_dev, fl
  * depgan_dem_postproc: dem = acc/n_repeat; fake2 = clip(base + dem, -1, 1); count = #((fake2 > thr) * mask != 0);
  *   label 1/2/3 = shrink/grow/stay                                     EG:628, 673-686, 711-741
  *   base is channel 0 of x (stride nicg floats).  count_dev: one unsigned long long (zeroed by the call).
- * depgan_uresnet_labels: argmax over 4 mean probabilities (first max wins) + count(label>0)  EU:570, 597-600 */
+ * depgan_uresnet_labels: mean = acc/n_repeat (optional output, IEEE division as NumPy), argmax over the
+ *   chan mean probabilities (first max wins) + count(label>0)                      EU:564, 570, 597-600 */
 int depgan_dem_accumulate(double* acc_dev, const float* pred_dev, const float* mask_dev, long long n, int chan,
                           void* stream);
 int depgan_dem_postproc(const float* x_dev, int nicg, const double* acc_dev, double n_repeat,
                         const float* mask_dev, double thr, double* dem_out_dev, double* fake2_out_dev,
                         unsigned char* labels_dev, unsigned long long* count_dev, long long npix, void* stream);
-int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, unsigned char* labels_dev,
-                          unsigned long long* count_dev, long long npix, void* stream);
+int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, double* mean_out_dev,
+                          unsigned char* labels_dev, unsigned long long* count_dev, long long npix, void* stream);
 
 /* ---- introspection for tests / profiling ---- */
 /* Number of kernels this library launched since load (all handles). */
 long long depgan_launch_count(void);
+/* Per-launch device timing of the convolution kernels (bench.py roofline leg): between begin and end every
+ * convolution launch is bracketed by CUDA events on its stream.  Classes: 0 = tcgen05 3x3, 1 = tcgen05 5x5,
+ * 2 = tcgen05 1x1 / transposed conv, 3 = fp32 CUDA-core conv.  flops/bytes are the algorithmic figures of
+ * DESIGN.md (2*k*k*Cin*Cout per pixel; activation bytes read + written once). */
+int depgan_profile_begin(void);
+int depgan_profile_end(double* ms_by_class, double* flops_by_class, double* bytes_by_class,
+                       long long* launches_by_class, int ncls);
 /* Copy an internal activation of the last forward over n slices (by keras layer suffix, e.g. "gen_0",
  * "gen_noise_m1" = the ResBlock sum, "de_gen_9", "conv2d_dis_3", or "film" = all FiLM vectors) to out_dev as
  * float32. */
