@@ -341,7 +341,7 @@ class OracleTrainer:
         self.last_gp = float(gp.detach())
         if update:
             opt.step(PD, gd)
-        return [float(lr_), float(lf_)]
+        return [float(lr_.detach()), float(lf_.detach())]
 
     def netD_y2_train(self, inputs, update=True):
         return self._critic_train(self.PDy2, self.optDy2, "y2", inputs, update)
@@ -364,7 +364,7 @@ class OracleTrainer:
         self.last_grads = {k: v.detach().clone() for k, v in gd.items()}
         if update:
             self.optG.step(self.PG, gd)
-        return [float(v) for v in out]
+        return [float(v.detach()) for v in out]
 
     def gen_iteration(self, crit_y2_batches, crit_dem_batches, x1, real2, noises):
         """One steady-state generator iteration TG:796-878: critic updates on the given batches
