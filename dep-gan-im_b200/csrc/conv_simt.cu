@@ -126,6 +126,100 @@ int launch_fwd(const ConvArgs& a, cudaStream_t st) {
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// First-layer direct convolution (conv2d_gen_0: nicg -> 32, conv2d_dis_0a: 1 -> 16).  K = ks*ks*Cin <= 25 is
+// far too small for tensor cores; the layer is HBM-bound (4*Cin B in, 2*Cout B out per pixel), so: one thread
+// per pixel, fp32 input halo tile and all weights in shared memory, Cout accumulators in registers, 128-bit
+// vectorised NHWC stores.
+// ------------------------------------------------------------------------------------------------------
+template <typename TO, int KS, int CIN, int COUT>
+__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ scale,
+                                                         const float* __restrict__ shift, TO* __restrict__ out, int H,
+                                                         int W, int relu) {
+  constexpr int PAD = KS / 2, IT = 16 + KS - 1, TAPS = KS * KS;
+  __shared__ float s_in[IT][IT + 1][CIN];
+  __shared__ __align__(16) float s_w[TAPS * CIN][COUT];
+  __shared__ float s_sc[COUT], s_sh[COUT];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tiles_w = W / 16;
+  const int w0 = (blockIdx.x % tiles_w) * 16, h0 = (blockIdx.x / tiles_w) * 16, n = blockIdx.y;
+  for (int i = tid; i < TAPS * CIN * COUT; i += 256) (&s_w[0][0])[i] = w[i];
+  for (int i = tid; i < COUT; i += 256) {
+    s_sc[i] = scale ? scale[i] : 1.f;
+    s_sh[i] = shift ? shift[i] : 0.f;
+  }
+  for (int i = tid; i < IT * IT * CIN; i += 256) {
+    const int ci = i % CIN, c = (i / CIN) % IT, r = i / (CIN * IT);
+    const int h = h0 + r - PAD, ww = w0 + c - PAD;
+    s_in[r][c][ci] = (h >= 0 && h < H && ww >= 0 && ww < W) ? x[(((size_t)n * H + h) * W + ww) * CIN + ci] : 0.f;
+  }
+  __syncthreads();
+  float acc[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < TAPS; ++tap) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      const float v = s_in[ty + tap / KS][tx + tap % KS][ci];
+      const float4* wp = reinterpret_cast<const float4*>(&s_w[tap * CIN + ci][0]);
+#pragma unroll
+      for (int q = 0; q < COUT / 4; ++q) {
+        const float4 w4 = wp[q];
+        acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
+        acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
+        acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) {
+    acc[i] = fmaf(acc[i], s_sc[i], s_sh[i]);
+    if (relu) acc[i] = fmaxf(acc[i], 0.f);
+  }
+  TO* o = out + (((size_t)n * H + h0 + ty) * W + w0 + tx) * COUT;
+  if constexpr (sizeof(TO) == 2) {
+    uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+    for (int q = 0; q < COUT / 8; ++q) {
+      uint4 pk;
+      __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) hp[k] = __floats2bfloat162_rn(acc[8 * q + 2 * k], acc[8 * q + 2 * k + 1]);
+      o4[q] = pk;
+    }
+  } else {
+    float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+    for (int q = 0; q < COUT / 4; ++q) o4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+}
+
+template <typename TO, int KS, int CIN, int COUT>
+int launch_first(const ConvArgs& a, cudaStream_t st) {
+  dim3 grid((a.W / 16) * (a.H / 16), a.N);
+  conv_first_kernel<TO, KS, CIN, COUT><<<grid, 256, 0, st>>>((const float*)a.in0, a.w, a.scale, a.shift, (TO*)a.out,
+                                                              a.H, a.W, a.relu);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// returns 1 when the call was taken by a first-layer specialisation, 0 otherwise, <0 on error
+template <typename TO>
+int try_first(const ConvArgs& a, cudaStream_t st) {
+  if (a.in_dt != DT_F32 || a.C1 != 0 || a.out_pre || a.film_g || a.add_src || a.mask_src || !a.out) return 0;
+  if (a.H % 16 || a.W % 16) return 0;
+  int r = 1;
+  if (a.ks == 3 && a.C0 == 1 && a.Cout == 32) r = launch_first<TO, 3, 1, 32>(a, st);
+  else if (a.ks == 3 && a.C0 == 2 && a.Cout == 32) r = launch_first<TO, 3, 2, 32>(a, st);
+  else if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) r = launch_first<TO, 5, 1, 16>(a, st);
+  else return 0;
+  return r < 0 ? r : 1;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // wgrad.  Work item = (tap, ci pair, co octet); each item keeps a 2x8 fp32 accumulator and walks the pixels
 // of the CTA's tiles; one atomicAdd per output element per CTA at the end.
@@ -247,6 +341,10 @@ int launch_wgrad(const WgradArgs& a, cudaStream_t st) {
 int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
   if (a.N <= 0) return 0;
   DG_REQUIRE(!a.deconv && !a.head_w, "conv_fwd_simt: deconv/head fusion are tcgen05-path epilogues");
+  {
+    const int r = a.out_dt == DT_BF16 ? try_first<bf16>(a, st) : try_first<float>(a, st);
+    if (r != 0) return r < 0 ? r : 0;
+  }
   if (a.in_dt == DT_F32 && a.out_dt == DT_F32) return launch_fwd<float, float>(a, st);
   if (a.in_dt == DT_F32 && a.out_dt == DT_BF16) return launch_fwd<float, bf16>(a, st);
   if (a.in_dt == DT_BF16 && a.out_dt == DT_BF16) return launch_fwd<bf16, bf16>(a, st);

@@ -16,10 +16,13 @@
 //     as long as the TMA destination is pattern (1024 B) aligned.  Activations are read from L2/HBM once per
 //     tile (x1.27 halo overhead) instead of once per tap.
 //   * B (weights, [tap][n][k] bf16) streams through its own TMA ring, one (tap, chunk) tile per stage.
-//   * warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (tcgen05.mma.cta_group::1.kind::f16),
-//     then all four warps run the fused epilogue straight out of TMEM (tcgen05.ld 32x32b.x16).
-//   * 2 CTAs/SM are co-resident (<= ~110 KB smem, <= 256 TMEM columns each for ncta <= 128), so one CTA's
-//     epilogue overlaps the other's MMA stream.
+//     When every (chunk, tap) tile of the layer fits next to the activation ring (32->32 ... 96->96 3x3 layers)
+//     the weights are loaded ONCE per CTA and stay resident.
+//   * Persistent: grid = min(#work items, #SMs), one CTA per SM looping over (tile, n-split) items.
+//     warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (tcgen05.mma.cta_group::1.kind::f16), warps 2..9 =
+//     fused epilogue straight out of TMEM (tcgen05.ld 32x32b.x16).  Two TMEM accumulator stages (when
+//     4*ncta <= 512 columns) overlap the epilogue of item i with the MMA stream of item i+1; the producer runs
+//     ahead across items, so prologue latency is paid once per CTA, not once per tile.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,6 +33,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 148;
 
 struct TcGeom {
   int tiles_w, tiles_h;
@@ -42,6 +46,8 @@ struct TcGeom {
   uint32_t a_bytes, b_bytes;  // stage strides (1024-aligned)
   uint32_t a_tx, b_tx;        // TMA transaction bytes per stage
   uint32_t layout;            // UMMA smem layout type (2 = SW128, 4 = SW64, 6 = SW32)
+  int b_resident;             // 1: all (chunk, tap) weight tiles live in smem for the CTA's lifetime
+  int acc_stages;             // TMEM accumulator stages (2 when 4*ncta <= 512)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -134,6 +140,18 @@ __device__ __forceinline__ void ld16_bf16(const void* base, size_t elem_off, flo
     v[2 * i + 1] = f.y;
   }
 }
+struct Packed16 {  // 16 bf16 values as loaded (two 128-bit words)
+  uint4 q[2];
+  __device__ __forceinline__ void load(const void* base, size_t elem_off) {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem_off);
+    q[0] = __ldg(p);
+    q[1] = __ldg(p + 1);
+  }
+  __device__ __forceinline__ float get(int i) const {
+    const uint32_t w = reinterpret_cast<const uint32_t*>(q)[i >> 1];
+    return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
+  }
+};
 __device__ __forceinline__ void st16_bf16(void* base, size_t elem_off, const float (&v)[16]) {
   uint4 q[2];
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
@@ -153,13 +171,39 @@ __device__ __forceinline__ void ld16_f32(const float* p, float (&v)[16]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// kernel
+// kernel: persistent, warp-specialised.  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
+// warps 2..9 = epilogue (warp w reads TMEM lane quarter w%4 of strip (w-2)/4).  Two TMEM accumulator stages let
+// the epilogue of work item i overlap the MMA stream of item i+1.
 // ---------------------------------------------------------------------------------------------------------
-template <int KS>
-__global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                      const __grid_constant__ CUtensorMap tmA1,
-                                                      const __grid_constant__ CUtensorMap tmB, const ConvArgs a,
-                                                      const TcGeom g) {
+constexpr int TC_THREADS = 320;
+
+struct Ring {
+  int idx = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++idx == n) { idx = 0; phase ^= 1u; }
+  }
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+template <int KS, int KSTEPS, bool RES>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                const __grid_constant__ CUtensorMap tmA1,
+                                                                const __grid_constant__ CUtensorMap tmB,
+                                                                const ConvArgs a, const TcGeom g) {
   constexpr int PAD = KS / 2, HT = 16 + KS - 1, TAPS = KS * KS;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -169,17 +213,26 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
   const uint32_t bar_base = b_base + g.nb * g.b_bytes;
   const uint32_t fullA = bar_base, emptyA = fullA + 8 * g.na;
   const uint32_t fullB = emptyA + 8 * g.na, emptyB = fullB + 8 * g.nb;
-  const uint32_t accum = emptyB + 8 * g.nb;
-  const uint32_t tmem_slot = accum + 8;
+  const uint32_t accFull = emptyB + 8 * g.nb, accEmpty = accFull + 16;
+  const uint32_t tmem_slot = accEmpty + 16;
+  const uint32_t ss_off = tmem_slot + 16;  // scale / shift staging: 2 * ncols_total floats, then head weights
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_off - raw));
+  float* s_shift = s_scale + g.ncols_total;
+  float4* s_head = reinterpret_cast<float4*>(s_shift + g.ncols_total);  // [Cout] x (up to 4 head outputs)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rowb = g.kc * 2;
+  // warp index made provably warp-uniform so the role loops run on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr int rowb = KSTEPS * 32;  // bytes per pixel row of a chunk = one swizzle span (kc = 16*KSTEPS)
+  const int nchunks = g.nchunk0 + g.nchunk1;
+  const int nsplit = g.ncols_total / g.ncta;
+  const int tiles_per_img = g.tiles_w * g.tiles_h;
+  const int n_items = tiles_per_img * a.N * nsplit;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < g.na; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
     for (int i = 0; i < g.nb; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-    mbar_init(accum, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -187,154 +240,253 @@ __global__ void __launch_bounds__(128) conv_tc_kernel(const __grid_constant__ CU
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  {  // BN scale / shift (or bias) once per CTA
+    const int cmod = a.Cout;
+    for (int i = threadIdx.x; i < g.ncols_total; i += TC_THREADS) {
+      s_scale[i] = a.scale ? a.scale[i % cmod] : 1.f;
+      s_shift[i] = a.shift ? a.shift[i % cmod] : 0.f;
+    }
+    if (a.head_w) {
+      for (int i = threadIdx.x; i < a.Cout; i += TC_THREADS) {
+        float hv[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < a.head_nc; ++k) hv[k] = a.head_w[(size_t)i * a.head_nc + k];
+        s_head[i] = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const int acc_stride = g.acc_stages == 2 ? g.tmem_cols / 2 : 0;
 
-  const int t = blockIdx.x;
-  const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / (g.tiles_w * g.tiles_h);
-  const int w0 = tw * 16, h0 = th * 16;
-  const int n0 = blockIdx.y * g.ncta;
-  const int nchunks = g.nchunk0 + g.nchunk1;
-
-  if (warp == 0 && lane == 0) {
-    // ===== TMA producer: halo tiles run one chunk ahead of the weight stream =====
-    auto issueA = [&](int c) {
-      const int s = c % g.na;
-      mbar_wait(emptyA + 8 * s, ((c / g.na) & 1) ^ 1);
-      mbar_expect_tx(fullA + 8 * s, g.a_tx);
-      const bool first = c < g.nchunk0;
-      tma_load_4d(a_base + s * g.a_bytes, first ? &tmA0 : &tmA1, fullA + 8 * s,
-                  (first ? c : c - g.nchunk0) * g.kc, w0 - PAD, h0 - PAD, n);
-    };
-    issueA(0);
-    int bi = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      if (c + 1 < nchunks) issueA(c + 1);
-      const int kglob = c < g.nchunk0 ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
-      for (int tap = 0; tap < TAPS; ++tap, ++bi) {
-        const int s = bi % g.nb;
-        mbar_wait(emptyB + 8 * s, ((bi / g.nb) & 1) ^ 1);
-        mbar_expect_tx(fullB + 8 * s, g.b_tx);
-        tma_load_2d(b_base + s * g.b_bytes, &tmB, fullB + 8 * s, kglob, tap * g.ncols_total + n0);
+  if (warp == 0) {
+    // ===== TMA producer (whole warp runs the loops; one elected lane issues) =====
+    if (RES) {  // all weights of the layer stay in shared memory for the CTA's lifetime
+      if (elect_one()) {
+        mbar_expect_tx(fullB, g.b_tx * TAPS * nchunks);
+        for (int c = 0; c < nchunks; ++c) {
+          const int kglob = c < g.nchunk0 ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
+          for (int tap = 0; tap < TAPS; ++tap)
+            tma_load_2d(b_base + (c * TAPS + tap) * g.b_bytes, &tmB, fullB, kglob, tap * g.ncols_total);
+        }
       }
+      __syncwarp();
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = make_idesc(g.ncta);
-    const uint32_t sbo_a = HT * rowb, sbo_b = 8 * rowb;
-    const int ksteps = g.kc / 16;
-    int bi = 0;
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % g.na;
-      mbar_wait(fullA + 8 * s, (c / g.na) & 1);
-      for (int tap = 0; tap < TAPS; ++tap, ++bi) {
-        const int sb = bi % g.nb;
-        mbar_wait(fullB + 8 * sb, (bi / g.nb) & 1);
-        tc_fence_after();
-        const int dy = tap / KS, dx = tap % KS;
-        const uint32_t b_addr = b_base + sb * g.b_bytes;
-#pragma unroll
-        for (int strip = 0; strip < 2; ++strip) {
-          const uint32_t a_addr = a_base + s * g.a_bytes + (uint32_t)((dy * HT + dx + strip * 8) * rowb);
-          for (int k = 0; k < ksteps; ++k) {
-            tc_mma(tmem_base + strip * g.ncta, make_sdesc(a_addr + k * 32, sbo_a, g.layout),
-                   make_sdesc(b_addr + k * 32, sbo_b, g.layout), idesc, (c | tap | k) != 0);
+    Ring ra, rb;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int ns = it % nsplit, t = it / nsplit;
+      const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
+      const int w0 = tw * 16, h0 = th * 16, n0 = ns * g.ncta;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(emptyA + 8 * ra.idx, ra.phase ^ 1u);
+        const bool first = c < g.nchunk0;
+        if (elect_one()) {
+          mbar_expect_tx(fullA + 8 * ra.idx, g.a_tx);
+          tma_load_4d(a_base + ra.idx * g.a_bytes, first ? &tmA0 : &tmA1, fullA + 8 * ra.idx,
+                      (first ? c : c - g.nchunk0) * g.kc, w0 - PAD, h0 - PAD, n);
+        }
+        __syncwarp();
+        ra.advance(g.na);
+        if (!RES) {
+          const int kglob = first ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(emptyB + 8 * rb.idx, rb.phase ^ 1u);
+            if (elect_one()) {
+              mbar_expect_tx(fullB + 8 * rb.idx, g.b_tx);
+              tma_load_2d(b_base + rb.idx * g.b_bytes, &tmB, fullB + 8 * rb.idx, kglob, tap * g.ncols_total + n0);
+            }
+            __syncwarp();
+            rb.advance(g.nb);
           }
         }
-        tc_commit(emptyB + 8 * sb);
       }
-      tc_commit(emptyA + 8 * s);
     }
-    tc_commit(accum);
-  }
-  __syncwarp();
-
-  // ===== fused epilogue: TMEM -> registers -> global =====
-  mbar_wait(accum, 0);
-  tc_fence_after();
-
-  const int r = warp * 32 + lane;  // accumulator row = TMEM lane
-  const int ty = r >> 3;
-  const int Cout = a.Cout;
-  float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-  for (int strip = 0; strip < 2; ++strip) {
-    const int tx = strip * 8 + (r & 7);
-    const int h = h0 + ty, w = w0 + tx;
-    if (a.head_w) head_acc[0] = head_acc[1] = head_acc[2] = head_acc[3] = 0.f;
-#pragma unroll 1
-    for (int j = 0; j < g.ncta / 16; ++j) {
-      float v[16];
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(strip * g.ncta + j * 16), v);
-      const int col = n0 + j * 16;
-      int c0 = col;
-      size_t opix = ((size_t)n * a.H + h) * a.W + w;
-      if (a.deconv) {
-        const int ab = col / Cout;
-        c0 = col - ab * Cout;
-        opix = ((size_t)n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1);
-      }
-      const size_t off = opix * Cout + c0;
-      float t[16];
-      if (a.scale) {
-        ld16_f32(a.scale + c0, t);
+  } else if (warp == 1) {
+    // ===== MMA issuer (whole warp converged, one elected lane issues tcgen05.mma / commit) =====
+    // Descriptors: the high word (SBO, version, swizzle mode) is constant; per MMA only the 14-bit start
+    // address field of the low word moves, in 16-byte units.
+    const uint32_t idesc = make_idesc(g.ncta);
+    const uint32_t hiA = ((uint32_t)(HT * rowb) >> 4) | (1u << 14) | (g.layout << 29);
+    const uint32_t hiB = ((uint32_t)(8 * rowb) >> 4) | (1u << 14) | (g.layout << 29);
+    constexpr uint32_t LBO1 = 1u << 16;
+    constexpr uint32_t ROW16 = rowb / 16;  // one pixel row in descriptor units
+    Ring ra, rb;
+    int k_it = 0;
+    if (RES) mbar_wait(fullB, 0);
+    const uint32_t b_step = g.b_bytes >> 4;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_it) {
+      const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
+      const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
+      mbar_wait(accEmpty + 8 * as, (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + as * acc_stride, d1 = d0 + g.ncta;
+      for (int c = 0; c < nchunks; ++c) {
+        mbar_wait(fullA + 8 * ra.idx, ra.phase);
+        tc_fence_after();
+        const uint32_t a_lo = (((a_base + ra.idx * g.a_bytes) & 0x3FFFFu) >> 4) | LBO1;
+        const uint32_t accc = (uint32_t)(c != 0);
+        if (RES) {
+          // weights resident: the whole chunk (TAPS x 2 strips x KSTEPS MMAs) is issued back to back
+          const uint32_t b_lo0 = (((b_base + c * TAPS * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
+          if (elect_one()) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= t[i];
-      }
-      if (a.shift) {
-        ld16_f32(a.shift + c0, t);
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint32_t at = a_lo + (uint32_t)(((tap / KS) * HT + (tap % KS)) * ROW16);
+              const uint32_t b_lo = b_lo0 + tap * b_step;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += t[i];
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint32_t acc = (tap | k) != 0 ? 1u : accc;
+                tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
+                tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
+                       idesc, acc);
+              }
+            }
+            tc_commit(emptyA + 8 * ra.idx);
+          }
+          __syncwarp();
+        } else {
+#pragma unroll 1
+          for (int tap = 0; tap < TAPS; ++tap) {
+            mbar_wait(fullB + 8 * rb.idx, rb.phase);
+            tc_fence_after();
+            const uint32_t b_lo = (((b_base + rb.idx * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
+            const int dy = tap / KS, dx = tap - dy * KS;
+            const uint32_t at = a_lo + (uint32_t)((dy * HT + dx) * ROW16);
+            if (elect_one()) {
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint32_t acc = k != 0 ? 1u : (tap != 0 ? 1u : accc);
+                tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
+                tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
+                       idesc, acc);
+              }
+              tc_commit(emptyB + 8 * rb.idx);
+              if (tap == TAPS - 1) tc_commit(emptyA + 8 * ra.idx);
+            }
+            __syncwarp();
+            rb.advance(g.nb);
+          }
+        }
+        ra.advance(g.na);
       }
-      if (a.out_pre) st16_bf16(a.out_pre, off, v);
-      if (a.film_g) {
+      if (elect_one()) tc_commit(accFull + 8 * as);
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> global =====
+    const int ew = warp - 2;
+    const int strip = ew >> 2;
+    const int q = warp & 3;          // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;     // accumulator row
+    const int ty = r >> 3, tx = strip * 8 + (r & 7);
+    const int Cout = a.Cout;
+    int k_it = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_it) {
+      const int ns = it % nsplit, t = it / nsplit;
+      const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
+      const int h = th * 16 + ty, w = tw * 16 + tx, n0 = ns * g.ncta;
+      const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
+      const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
+      mbar_wait(accFull + 8 * as, use & 1u);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + as * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(strip * g.ncta);
+      float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+      for (int j = 0; j < g.ncta / 16; ++j) {
+        const int col = n0 + j * 16;
+        int c0 = col;
+        size_t opix = ((size_t)n * a.H + h) * a.W + w;
+        if (a.deconv) {
+          const int ab = col / Cout;
+          c0 = col - ab * Cout;
+          opix = ((size_t)n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1);
+        }
+        const size_t off = opix * Cout + c0;
+        // issue the global reads of this chunk before waiting on tensor memory
         float fg[16], fb[16];
-        ld16_f32(a.film_g + (size_t)n * a.film_stride + c0, fg);
-        ld16_f32(a.film_b + (size_t)n * a.film_stride + c0, fb);
-        ld16_bf16(a.res, off, t);
+        Packed16 rs, ad, mk;  // bf16 x 16, unpacked at use (keeps the prefetch cheap in registers)
+        if (a.film_g) {
+          ld16_f32(a.film_g + (size_t)n * a.film_stride + c0, fg);
+          ld16_f32(a.film_b + (size_t)n * a.film_stride + c0, fb);
+          rs.load(a.res, off);
+        }
+        if (a.add_src) ad.load(a.add_src, off);
+        if (a.mask_src) mk.load(a.mask_src, off);
+        float v[16];
+        tc_ld16(t_row + (uint32_t)(j * 16), v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], fg[i], fb[i]), 0.f) + t[i];
-      }
-      if (a.add_src) {
-        ld16_bf16(a.add_src, off, t);
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const float4 sc = reinterpret_cast<const float4*>(s_scale + col)[i4];
+          const float4 sh = reinterpret_cast<const float4*>(s_shift + col)[i4];
+          v[4 * i4 + 0] = fmaf(v[4 * i4 + 0], sc.x, sh.x);
+          v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc.y, sh.y);
+          v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
+          v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
+        }
+        if (a.out_pre) st16_bf16(a.out_pre, off, v);
+        if (a.film_g) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += t[i];
-      }
-      if (a.mask_src) {
-        ld16_bf16(a.mask_src, off, t);
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], fg[i], fb[i]), 0.f) + rs.get(i);
+        }
+        if (a.add_src) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = t[i] > 0.f ? v[i] : 0.f;
-      }
-      if (a.relu) {
+          for (int i = 0; i < 16; ++i) v[i] += ad.get(i);
+        }
+        if (a.mask_src) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-      }
-      if (a.out) st16_bf16(a.out, off, v);
-      if (a.head_w) {
-        for (int k = 0; k < a.head_nc; ++k) {
-          float s = head_acc[k];
+          for (int i = 0; i < 16; ++i) v[i] = mk.get(i) > 0.f ? v[i] : 0.f;
+        }
+        if (a.relu) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) s = fmaf(v[i], __ldg(a.head_w + (size_t)(c0 + i) * a.head_nc + k), s);
-          head_acc[k] = s;
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (a.out) st16_bf16(a.out, off, v);
+        if (a.head_w) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 hw = s_head[c0 + i];
+            head_acc[0] = fmaf(v[i], hw.x, head_acc[0]);
+            head_acc[1] = fmaf(v[i], hw.y, head_acc[1]);
+            head_acc[2] = fmaf(v[i], hw.z, head_acc[2]);
+            head_acc[3] = fmaf(v[i], hw.w, head_acc[3]);
+          }
         }
       }
-    }
-    if (a.head_w) {
-      const size_t pix = ((size_t)n * a.H + h) * a.W + w;
-      float o[4];
-      for (int k = 0; k < a.head_nc; ++k) o[k] = head_acc[k] + __ldg(a.head_b + k);
-      if (a.head_act == 0) {
-        for (int k = 0; k < a.head_nc; ++k) o[k] = tanhf(o[k]);
-      } else if (a.head_act == 1) {
-        float m = o[0];
-        for (int k = 1; k < a.head_nc; ++k) m = fmaxf(m, o[k]);
-        float s = 0.f;
-        for (int k = 0; k < a.head_nc; ++k) { o[k] = expf(o[k] - m); s += o[k]; }
-        for (int k = 0; k < a.head_nc; ++k) o[k] = o[k] / s;
+      // this warp is done with the accumulator stage: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(accEmpty + 8 * as);
+      if (a.head_w) {
+        const size_t pix = ((size_t)n * a.H + h) * a.W + w;
+        const int nc = a.head_nc;
+        float o0 = head_acc[0] + __ldg(a.head_b), o1 = 0.f, o2 = 0.f, o3 = 0.f;
+        if (nc > 1) o1 = head_acc[1] + __ldg(a.head_b + 1);
+        if (nc > 2) o2 = head_acc[2] + __ldg(a.head_b + 2);
+        if (nc > 3) o3 = head_acc[3] + __ldg(a.head_b + 3);
+        if (a.head_act == 0) {
+          o0 = tanhf(o0); o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3);
+        } else if (a.head_act == 1) {
+          float m = o0;
+          if (nc > 1) m = fmaxf(m, o1);
+          if (nc > 2) m = fmaxf(m, o2);
+          if (nc > 3) m = fmaxf(m, o3);
+          o0 = expf(o0 - m);
+          o1 = nc > 1 ? expf(o1 - m) : 0.f;
+          o2 = nc > 2 ? expf(o2 - m) : 0.f;
+          o3 = nc > 3 ? expf(o3 - m) : 0.f;
+          const float inv = 1.0f / (o0 + o1 + o2 + o3);
+          o0 *= inv; o1 *= inv; o2 *= inv; o3 *= inv;
+        }
+        if (nc == 4) {
+          *reinterpret_cast<float4*>(a.head_out + pix * 4) = make_float4(o0, o1, o2, o3);
+        } else {
+          float* op = a.head_out + pix * nc;
+          op[0] = o0;
+          if (nc > 1) op[1] = o1;
+          if (nc > 2) op[2] = o2;
+        }
       }
-      for (int k = 0; k < a.head_nc; ++k) a.head_out[pix * a.head_nc + k] = o[k];
     }
   }
 
@@ -384,33 +536,50 @@ int make_w_map(CUtensorMap* tm, const void* p, int Cin, int rows, int kc, int nc
 
 uint32_t round1024(uint32_t x) { return (x + 1023u) & ~1023u; }
 
-constexpr uint32_t SMEM_BUDGET = 108 * 1024;  // two CTAs per SM
+constexpr uint32_t SMEM_BUDGET = 220 * 1024;  // one persistent CTA per SM
 
 bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
-  const int ks = a.ks, ht = 16 + ks - 1;
+  const int ks = a.ks, ht = 16 + ks - 1, taps = ks * ks;
   const int ncols = a.deconv ? 4 * a.Cout : a.Cout;
   const int nsplit = (ncols + 255) / 256;
   if (ncols % nsplit) return false;
   const int ncta = ncols / nsplit;
   if (ncta % 16 || ncta < 16 || ncta > 256) return false;
   if (a.deconv && (ncta % a.Cout)) return false;
+  const int acc_stages = 4 * ncta <= 512 ? 2 : 1;
   int tmem_cols = 32;
-  while (tmem_cols < 2 * ncta) tmem_cols *= 2;
+  while (tmem_cols < 2 * ncta * acc_stages) tmem_cols *= 2;
+  const uint32_t fixed = 1024 + 8 * 64 + 64 + 2 * ncols * 4 + 16 * a.Cout + 64;
   for (int kc = 64; kc >= 16; kc /= 2) {
     if (a.C0 % kc || a.C1 % kc) continue;
+    const int nchunks = (a.C0 + a.C1) / kc;
     const uint32_t a_bytes = round1024((uint32_t)ht * ht * kc * 2), b_bytes = round1024((uint32_t)ncta * kc * 2);
-    const int na = 2;
-    if (na * a_bytes + 3 * b_bytes + 2048 > SMEM_BUDGET && kc > 16) continue;
-    int nb = (int)((SMEM_BUDGET - 2048 - na * a_bytes) / b_bytes);
-    if (nb > 8) nb = 8;
-    if (nb < 2) return false;
+    int na, nb, resident = 0;
+    const uint32_t w_all = (uint32_t)taps * nchunks * b_bytes;
+    if (nsplit == 1 && fixed + w_all + 2 * a_bytes <= SMEM_BUDGET) {
+      resident = 1;
+      nb = taps * nchunks;
+      na = (int)((SMEM_BUDGET - fixed - w_all) / a_bytes);
+      if (na > 6) na = 6;
+    } else {
+      na = 3;
+      if (fixed + na * a_bytes + 4 * b_bytes > SMEM_BUDGET) na = 2;
+      if (fixed + na * a_bytes + 3 * b_bytes > SMEM_BUDGET) {
+        if (kc > 16) continue;
+        return false;
+      }
+      nb = (int)((SMEM_BUDGET - fixed - na * a_bytes) / b_bytes);
+      if (nb > 12) nb = 12;
+    }
+    if (resident && nb > 56) continue;  // barrier area holds 64 slots
     g->tiles_w = a.W / 16; g->tiles_h = a.H / 16;
     g->nchunk0 = a.C0 / kc; g->nchunk1 = a.C1 / kc;
     g->kc = kc; g->ncols_total = ncols; g->ncta = ncta; g->tmem_cols = tmem_cols;
     g->na = na; g->nb = nb; g->a_bytes = a_bytes; g->b_bytes = b_bytes;
     g->a_tx = (uint32_t)ht * ht * kc * 2; g->b_tx = (uint32_t)ncta * kc * 2;
     g->layout = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
-    *smem_bytes = 1024 + na * a_bytes + nb * b_bytes + 8 * (2 * na + 2 * nb + 1) + 16;
+    g->b_resident = resident; g->acc_stages = acc_stages;
+    *smem_bytes = 1024 + na * a_bytes + nb * b_bytes + 8 * (2 * na + 2 * nb + 4) + 16 + 2 * ncols * 4 + 16 * a.Cout + 64;
     return true;
   }
   return false;
@@ -428,9 +597,18 @@ int conv_tc_init() {
     return -1;
   }
   g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int dev = 0;
+  DG_CHECK_CUDA(cudaGetDevice(&dev));
+  DG_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+#define DG_TC_ATTR(KS_, K_)                                                                                        \
+  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS_, K_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                     227 * 1024));                                                                 \
+  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS_, K_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                     227 * 1024))
+  DG_TC_ATTR(1, 1); DG_TC_ATTR(1, 2); DG_TC_ATTR(1, 4);
+  DG_TC_ATTR(3, 1); DG_TC_ATTR(3, 2); DG_TC_ATTR(3, 4);
+  DG_TC_ATTR(5, 1); DG_TC_ATTR(5, 2); DG_TC_ATTR(5, 4);
+#undef DG_TC_ATTR
   return 0;
 }
 
@@ -460,12 +638,27 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   if (a.C1 > 0) DG_TRY(make_act_map(&tmA1, a.in1, a.C1, a.W, a.H, a.N, g.kc, ht));
   else tmA1 = tmA0;
   DG_TRY(make_w_map(&tmB, a.w_tc, a.C0 + a.C1, a.ks * a.ks * g.ncols_total, g.kc, g.ncta));
-  dim3 grid(g.tiles_w * g.tiles_h * a.N, g.ncols_total / g.ncta);
-  switch (a.ks) {
-    case 1: conv_tc_kernel<1><<<grid, 128, smem, st>>>(tmA0, tmA1, tmB, a, g); break;
-    case 3: conv_tc_kernel<3><<<grid, 128, smem, st>>>(tmA0, tmA1, tmB, a, g); break;
-    case 5: conv_tc_kernel<5><<<grid, 128, smem, st>>>(tmA0, tmA1, tmB, a, g); break;
+  const int n_items = g.tiles_w * g.tiles_h * a.N * (g.ncols_total / g.ncta);
+  const int grid = n_items < g_num_sms ? n_items : g_num_sms;
+#define DG_TC_LAUNCH(KS_, K_)                                                                  \
+  do {                                                                                         \
+    if (g.b_resident) conv_tc_kernel<KS_, K_, true><<<grid, TC_THREADS, smem, st>>>(tmA0, tmA1, tmB, a, g);  \
+    else conv_tc_kernel<KS_, K_, false><<<grid, TC_THREADS, smem, st>>>(tmA0, tmA1, tmB, a, g);              \
+  } while (0)
+  const int key = a.ks * 10 + g.kc / 16;
+  switch (key) {
+    case 11: DG_TC_LAUNCH(1, 1); break;
+    case 12: DG_TC_LAUNCH(1, 2); break;
+    case 14: DG_TC_LAUNCH(1, 4); break;
+    case 31: DG_TC_LAUNCH(3, 1); break;
+    case 32: DG_TC_LAUNCH(3, 2); break;
+    case 34: DG_TC_LAUNCH(3, 4); break;
+    case 51: DG_TC_LAUNCH(5, 1); break;
+    case 52: DG_TC_LAUNCH(5, 2); break;
+    case 54: DG_TC_LAUNCH(5, 4); break;
+    default: depgan_set_error("conv_fwd_tc: no kernel for this (ks, kc)"); return -2;
   }
+#undef DG_TC_LAUNCH
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -2,6 +2,8 @@
 // include/depgan_b200.h.  Host-side orchestration only: every arithmetic step is one of our CUDA kernels.
 #include "net.h"
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -268,7 +270,7 @@ int fold_dense(depgan_net* h, DenseL& D, cudaStream_t st) {
 // optional per-launch timing (bench.py roofline leg): CUDA events around every convolution launch
 // =========================================================================================================
 namespace {
-struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; int ks, H, W, cin, cout, n; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 int conv_class(const ConvArgs& a, bool tc) {
@@ -292,6 +294,7 @@ struct ProfScope {
     r.bytes = px * cin * ies + (a.out ? px * ncols * oes : 0.0) + (a.out_pre ? px * ncols * oes : 0.0) +
               (a.res ? px * ncols * oes : 0.0) + (a.add_src ? px * ncols * oes : 0.0) +
               (a.mask_src ? px * ncols * oes : 0.0) + (a.head_out ? px * a.head_nc * 4.0 : 0.0);
+    r.ks = a.ks; r.H = a.H; r.W = a.W; r.cin = a.C0 + a.C1; r.cout = (int)ncols; r.n = a.N;
     cudaEventCreate(&r.e0);
     cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, st);
@@ -571,13 +574,20 @@ int depgan_profile_end(double* ms, double* flops, double* bytes, long long* laun
   DG_REQUIRE(ms && flops && bytes && launches && ncls >= 1, "profile_end: bad arguments");
   for (int i = 0; i < ncls; ++i) { ms[i] = flops[i] = bytes[i] = 0.0; launches[i] = 0; }
   DG_CHECK_CUDA(cudaDeviceSynchronize());
+  FILE* log = nullptr;
+  if (const char* path = getenv("DEPGAN_PROFILE_LOG")) log = fopen(path, "w");
+  if (log) fprintf(log, "class,ks,N,H,W,cin,ncols,ms,tflops,gbs\n");
   for (auto& r : g_prof) {
     float t = 0.f;
     DG_CHECK_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (log)
+      fprintf(log, "%d,%d,%d,%d,%d,%d,%d,%.4f,%.1f,%.1f\n", r.cls, r.ks, r.n, r.H, r.W, r.cin, r.cout, t,
+              r.flops / (t * 1e-3) / 1e12, r.bytes / (t * 1e-3) / 1e9);
     if (r.cls < ncls) { ms[r.cls] += t; flops[r.cls] += r.flops; bytes[r.cls] += r.bytes; launches[r.cls] += 1; }
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }
+  if (log) fclose(log);
   g_prof.clear();
   return 0;
 }
