@@ -62,3 +62,36 @@ int k_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t
            float gscale, cudaStream_t st);
 
 int k_copy_to_f32(const void* src, float* dst, long long n, int dt, cudaStream_t st);
+
+// ---- backward / loss kernels (kernels_bwd.cu) ------------------------------------------------------------
+int k_maxpool_bwd(const void* dy, const void* x, const void* add_src, void* dx, int N, int H, int W, int C, int dt,
+                  cudaStream_t st);
+int k_maxpool_select(const void* v, const void* x, void* out, int N, int H, int W, int C, int dt, cudaStream_t st);
+int k_channel_sum(const void* src, long long rows, int C, float* out, float alpha, int dt, cudaStream_t st);
+int k_param_grads(const float* W, const float* G, float* dW, const float* scale, const float* inv_std,
+                  const float* bias, const float* mean, const float* sum_dy, float* dgamma, float* dbeta, float* dbias,
+                  int K, int C, int trans, int Cin, cudaStream_t st);
+int k_critic_head_bwd(const void* h, const void* v, const float* go, const float* w9, const float* b9, const float* wd,
+                      void* dh, float* d_w9, float* d_b9, float* d_wd, float* d_bd, int rows, int n_reg, int HW, int C,
+                      int want_param_grads, int dt, cudaStream_t st);
+int k_gp(const float* g, float* u, float* gp_out, int n, long long hw, float delta, float inv_n, cudaStream_t st);
+int k_segment_sum(const float* src, int seg, int nseg, float* out, float alpha, cudaStream_t st);
+int k_gen_loss_sums(const float* dem, const float* x1, int nicg, const float* real2, float thr, float* fake2,
+                    float* l1g, float l1coef, double* sums, long long n, cudaStream_t st);
+int k_gen_loss_finalize(float* out6, const double* sums, cudaStream_t st);
+int k_gen_head_bwd(const float* gy2, const float* gdem, const float* l1g, const float* dem, const void* o,
+                   const float* w, void* d_o, float* d_w, float* d_b, long long npix, int C, int dt, cudaStream_t st);
+int k_film_bwd(const void* d_r, const void* y, const float* fg, const float* fb, int fstride, void* d_y, float* dgam,
+               float* dbet, int N, int HW, int C, int dt, cudaStream_t st);
+int k_add_mask(const void* a, const void* b, const void* m, void* out, long long n, int dt, cudaStream_t st);
+int k_s2d_mask(const void* d_up, int dstride, const void* up, void* out, int N, int H, int W, int C, int dt,
+               cudaStream_t st);
+int k_slice_add(const void* src, int sstride, int off, const void* add, void* dst, long long rows, int C, int dt,
+                cudaStream_t st);
+int k_film_mlp_bwd(const FilmMlpArgs& a, const float* d_out, float* const* dW_heads, float* sum_d, float* d_h2,
+                   float* dk1raw, float* sum_d1, float* dk0raw, float* sum_d0, cudaStream_t st);
+int k_fill_go(float* go, int n, float v_real, float v_fake, float v_mixed, int rows, cudaStream_t st);
+int k_critic_loss_finalize(float* out4, float delta, cudaStream_t st);
+int k_scores_to_sums(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw, cudaStream_t st);
+int k_pack_deconv_dgrad(const float* src, const float* scale, float* dst_f32, bf16* dst_bf16, int Cin, int Cout,
+                        cudaStream_t st);

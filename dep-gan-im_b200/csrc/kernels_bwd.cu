@@ -643,3 +643,59 @@ int k_film_mlp_bwd(const FilmMlpArgs& a, const float* d_out, float* const* dW_he
   DG_LAUNCH_CHECK();
   return 0;
 }
+
+namespace {
+__global__ void fill_go_kernel(float* go, int n, float v_real, float v_fake, float v_mixed, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) go[i] = i < n ? v_real : (i < 2 * n ? v_fake : v_mixed);
+}
+__global__ void critic_loss_finalize_kernel(float* out4, float delta) {
+  out4[3] = out4[1] - out4[0] + delta * out4[2];  // loss_fake - loss_real + delta * GP  (TG:547 / 566)
+}
+}  // namespace
+
+int k_fill_go(float* go, int n, float v_real, float v_fake, float v_mixed, int rows, cudaStream_t st) {
+  if (rows == 0) return 0;
+  fill_go_kernel<<<(rows + 127) / 128, 128, 0, st>>>(go, n, v_real, v_fake, v_mixed, rows);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+int k_critic_loss_finalize(float* out4, float delta, cudaStream_t st) {
+  critic_loss_finalize_kernel<<<1, 1, 0, st>>>(out4, delta);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+namespace {
+__global__ void scores_to_sums_kernel(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw) {
+  double a = 0.0, b = 0.0;
+  for (int i = 0; i < n; ++i) { a += (double)sy2[i]; b += (double)sdem[i]; }
+  sums[0] = a; sums[1] = b; sums[6] = gn; sums[7] = hw;
+}
+// Transposed-conv data-gradient operands from the Keras kernel (2,2,Cout,Cin) and the BN scale s[co]:
+//   dst_f32 [(ab,co)][ci] = W*s (CUDA-core 1x1 conv, [K][N]);  dst_bf16 [ci][(ab,co)] = W*s (tcgen05 B operand)
+__global__ void pack_deconv_dgrad_kernel(const float* src, const float* scale, float* dst_f32, bf16* dst_bf16, int Cin,
+                                         int Cout) {
+  const size_t total = (size_t)4 * Cout * Cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = i % Cin;
+    const int k = i / Cin;  // (ab, co)
+    const float v = src[i] * (scale ? scale[k % Cout] : 1.f);
+    if (dst_f32) dst_f32[i] = v;
+    if (dst_bf16) dst_bf16[(size_t)ci * (4 * Cout) + k] = __float2bfloat16_rn(v);
+  }
+}
+}  // namespace
+
+int k_scores_to_sums(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw, cudaStream_t st) {
+  scores_to_sums_kernel<<<1, 1, 0, st>>>(sy2, sdem, n, sums, gn, hw);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+int k_pack_deconv_dgrad(const float* src, const float* scale, float* dst_f32, bf16* dst_bf16, int Cin, int Cout,
+                        cudaStream_t st) {
+  if (!dst_f32 && !dst_bf16) return 0;
+  pack_deconv_dgrad_kernel<<<grid_for((long long)4 * Cin * Cout), 256, 0, st>>>(src, scale, dst_f32, dst_bf16, Cin, Cout);
+  DG_LAUNCH_CHECK();
+  return 0;
+}

@@ -151,10 +151,8 @@ void alloc_conv_derived(depgan_net* h, ConvL& L, Bump& b) {
   if (h->act_dt == DT_BF16) L.w_tc = b.arr<bf16>(nw);
   if (h->cfg.training) {
     L.inv_std = b.arr<float>(L.cout);
-    if (!L.deconv) {
-      L.w_dg = b.arr<float>(nw);
-      if (h->act_dt == DT_BF16) L.w_dg_tc = b.arr<bf16>(nw);
-    }
+    L.w_dg = b.arr<float>(nw);
+    if (h->act_dt == DT_BF16) L.w_dg_tc = b.arr<bf16>(nw);
   }
 }
 void alloc_dense_derived(depgan_net* h, DenseL& D, Bump& b) {
@@ -254,6 +252,7 @@ int fold_conv(depgan_net* h, ConvL& L, cudaStream_t st) {
                    L.inv_std, L.cout, st));
   if (L.deconv) {
     if (L.w_tc) DG_TRY(k_convert_in(h->P(L.k_off), L.w_tc, (long long)4 * L.cin * L.cout, DT_BF16, st));
+    DG_TRY(k_pack_deconv_dgrad(h->P(L.k_off), L.scale, L.w_dg, L.w_dg_tc, L.cin, L.cout, st));
   } else {
     DG_TRY(k_pack_conv_weights(h->P(L.k_off), L.scale, L.w_tc, L.w_dg, L.w_dg_tc, L.ks * L.ks, L.cin, L.cout, st));
   }

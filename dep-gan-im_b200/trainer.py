@@ -1,0 +1,150 @@
+"""The four ``K.function`` callables of the DEP-GAN training script (TG:550-552, 569-571, 595-598) and the step
+schedule around them (TG:780-878), driving the CUDA train-step graphs through the C ABI.
+
+    tr = DepGanTrainer(netG, netD_y2, netD_dem, IM_TRSH)
+    loss_real, loss_fake = tr.netD_y2_train([real_2tp, real_1tp, noise, ep])        # TG:809
+    loss_real, loss_fake = tr.netD_dem_train([real_2tp, real_1tp, noise, ep])       # TG:824
+    loss, lf, lfd, M1, M3, M4 = tr.netG_no_update([real_1tp, real_2tp, noise])      # TG:873
+    loss, lf, lfd, M1, M3, M4 = tr.netG_train([real_1tp, real_2tp, noise])          # TG:878
+
+Argument orders follow the reference (critics: [real_2tp, real_1tp, noise, ep]; generator: [real_1tp, real_2tp,
+noise]).  Returned values are computed from the pre-update weights; each ``*_train`` call performs exactly one
+Keras-form Adam step (lr 1e-4, beta_1 0, beta_2 0.9; TG:549,568,594) on exactly one network.
+
+Data parallel: when ``torch.distributed`` is initialised with world size W, every rank passes its
+shard of the global batch; gradients are summed with one NCCL all-reduce of the flat bucket, the loss partial sums
+(incl. the batch-global dice / volume terms) with a tiny all-reduce, so every rank reports the global-batch values
+and applies the identical update.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .api import _stream, _torch
+
+__all__ = ["DepGanTrainer"]
+
+
+class DepGanTrainer:
+    def __init__(self, netG, netD_y2, netD_dem, thr, lrD=1e-4, lrG=1e-4, beta_1=0.0, beta_2=0.9, distributed=None):
+        torch = _torch()
+        self.torch = torch
+        self.G, self.Dy2, self.Ddem = netG, netD_y2, netD_dem
+        for net in (netG, netD_y2, netD_dem):
+            if not net.cfg.training:
+                raise ValueError("networks must be created with training=True")
+        self.thr = float(np.float32(thr))
+        self.lrD, self.lrG, self.b1, self.b2 = lrD, lrG, beta_1, beta_2
+        self.device = netG.device
+        dist = torch.distributed
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        self.dist = dist if distributed else None
+        self.world = dist.get_world_size() if distributed else 1
+        self.out4 = torch.zeros(4, dtype=torch.float32, device=self.device)
+        self.out6 = torch.zeros(6, dtype=torch.float32, device=self.device)
+        self.sums = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self.gen_iterations = 0
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _dev(self, a, dtype=None):
+        torch = self.torch
+        if isinstance(a, torch.Tensor):
+            t = a.to(self.device, torch.float32)
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, np.float32)).to(self.device)
+        return t.contiguous()
+
+    def _allreduce_grads(self, net):
+        if self.dist is not None:
+            self.dist.all_reduce(net.grads, op=self.dist.ReduceOp.SUM)
+
+    # ---- critics (TG:523-571) -------------------------------------------------------------------------
+    def critic_grads_device(self, which, real2, x1, z, ep):
+        """Device tensors in; leaves dLoss/dtheta in the critic's flat gradient buffer and returns the float32
+        CUDA tensor [loss_real, loss_fake, gradient_penalty, loss] for the GLOBAL batch."""
+        torch = self.torch
+        D = self.Dy2 if which == 0 else self.Ddem
+        n = int(real2.shape[0])
+        if 3 * n > D.cfg.max_batch:
+            raise ValueError("the critic needs max_batch >= 3 * batch (real | fake | mixed rows)")
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_critic_grads(D.handle, self.G.handle, which, real2.data_ptr(), x1.data_ptr(),
+                                                      z.data_ptr(), ep.data_ptr(), self.out4.data_ptr(), n,
+                                                      n * self.world, _stream(torch)), "critic_grads")
+        if self.dist is not None:
+            self.dist.all_reduce(self.out4, op=self.dist.ReduceOp.SUM)
+            self._allreduce_grads(D)
+        return self.out4
+
+    def _critic_train(self, which, inputs, update=True):
+        real2, x1, z, ep = [self._dev(a) for a in inputs]
+        ep = ep.reshape(-1).contiguous()
+        out = self.critic_grads_device(which, real2, x1, z, ep)
+        vals = out.cpu().numpy().copy()
+        if update:
+            D = self.Dy2 if which == 0 else self.Ddem
+            D.adam_step(self.lrD, self.b1, self.b2)
+        self.last_gp = float(vals[2])
+        return [np.float32(vals[0]), np.float32(vals[1])]
+
+    def netD_y2_train(self, inputs, update=True):
+        return self._critic_train(0, inputs, update)
+
+    def netD_dem_train(self, inputs, update=True):
+        return self._critic_train(1, inputs, update)
+
+    # ---- generator (TG:573-598) -----------------------------------------------------------------------
+    def gen_device(self, x1, real2, z, grads):
+        torch = self.torch
+        n = int(x1.shape[0])
+        L = _lib.lib()
+        fn = L.depgan_gen_grads if grads else L.depgan_gen_eval
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self.G.handle, self.Dy2.handle, self.Ddem.handle, x1.data_ptr(), real2.data_ptr(),
+                          z.data_ptr(), self.thr, self.out6.data_ptr(), self.sums.data_ptr(), n, n * self.world,
+                          _stream(torch)), "gen_grads" if grads else "gen_eval")
+            if self.dist is not None:  # batch-global dice / volume / means need the summed partials
+                part = self.sums[:6].clone()
+                self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM)
+                self.sums[:6] = part
+                _lib.check(L.depgan_gen_loss_finalize(self.out6.data_ptr(), self.sums.data_ptr(), _stream(torch)),
+                           "gen_loss_finalize")
+                if grads:
+                    self._allreduce_grads(self.G)
+        return self.out6
+
+    def netG_no_update(self, inputs):
+        x1, real2, z = [self._dev(a) for a in inputs]
+        return [np.float32(v) for v in self.gen_device(x1, real2, z, False).cpu().numpy()]
+
+    def netG_train(self, inputs, update=True):
+        x1, real2, z = [self._dev(a) for a in inputs]
+        vals = self.gen_device(x1, real2, z, True).cpu().numpy().copy()
+        if update:
+            self.G.adam_step(self.lrG, self.b1, self.b2)
+        return [np.float32(v) for v in vals]
+
+    # ---- one generator iteration of the reference schedule (TG:796-878) --------------------------------
+    def diters(self, Diters=5):
+        """Critic iterations for the current generator iteration (TG:792-795)."""
+        return 100 if (self.gen_iterations < 25 or self.gen_iterations % 500 == 0) else Diters
+
+    def gen_iteration(self, crit_y2_batches, crit_dem_batches, x1, real2, noises):
+        """Critic updates on the given batches (each [real_2tp, real_1tp, noise, ep]), then k_noise forward-only
+        evaluations, argmin over the total loss, one generator update with the selected noise (TG:867-878)."""
+        for b in crit_y2_batches:
+            self.netD_y2_train(b)
+        for b in crit_dem_batches:
+            self.netD_dem_train(b)
+        x1d, r2d = self._dev(x1), self._dev(real2)
+        losses = []
+        for nz in noises:
+            losses.append(float(self.gen_device(x1d, r2d, self._dev(nz), False)[0].item()))
+        k = int(np.array(losses).argmin(0))
+        out = self.netG_train([x1d, r2d, self._dev(noises[k])])
+        self.gen_iterations += 1
+        return k, losses, out
