@@ -300,13 +300,101 @@ def run_gpu(args, w, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_train(args, rank, world, local_rank):
+    """BASELINE configs[2]/[3]: DEP-GAN two-critic training, one step = one generator iteration of the reference
+    schedule (5 Y2-critic + 5 DEM-critic updates, 10 noise evaluations, 1 generator update; TG:796-878)."""
+    import torch
+    import torch.distributed as dist
+    from depgan_b200 import Dis_C2D_FCN1, Gen_UNet2D, launch_count, synth
+    from depgan_b200.trainer import DepGanTrainer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch or 32
+    nicg = 2 if args.workload == "depgan_train_pf" else 1
+    thr = 0.5 if nicg == 2 else 0.178
+    G = Gen_UNet2D((256, 256, nicg), (32, 1), 32, 1, precision=args.precision, max_batch=B, device=str(dev),
+                   training=True, seed=0)
+    D1 = Dis_C2D_FCN1((256, 256, 1), precision=args.precision, max_batch=3 * B, device=str(dev), training=True, seed=1)
+    D2 = Dis_C2D_FCN1((256, 256, 1), precision=args.precision, max_batch=3 * B, device=str(dev), training=True, seed=2)
+    tr = DepGanTrainer(G, D1, D2, thr)
+
+    def batch(seed):
+        x1, y2, _ = synth.make_im_pair(B, 256, 256, nicg=nicg, thr=thr, seed=seed)
+        z, ep = synth.make_noise(B, seed=seed + 1), synth.make_eps(B, seed=seed + 2).reshape(-1)
+        return tuple(torch.from_numpy(a).to(dev) for a in (y2, x1, z, ep))
+
+    nb = 3
+    batches = [batch(1000 * rank + 10 * i) for i in range(nb)]
+    noises = torch.from_numpy(np.stack([synth.make_noise(B, seed=7000 + 100 * rank + k) for k in range(10)])).to(dev)
+
+    def step(i):
+        by2 = [batches[(i + j) % nb] for j in range(5)]
+        bdem = [batches[(i + j + 1) % nb] for j in range(5)]
+        y2, x1, _, _ = bdem[-1]  # the generator trains on the last DEM-critic batch (TG:873-878)
+        return tr.gen_iteration_device(by2, bdem, x1, y2, noises)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        losses, out = step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    if rank == 0:
+        flop_per_slice = 1013.3e9  # BASELINE.md section 2: 10 critic updates + 10 evals + 1 G update
+        line = {
+            "metric": "DEP-GAN train steps/sec (generator iterations: 5+5 critic updates, 10 noise evals, 1 G update)",
+            "value": args.steps / (ms * 1e-3), "unit": "gen-iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "DEP-GAN %s two-critic training, random init, batch %d per GPU, global batch %d "
+                                   "(BASELINE configs[%s])" % ("PROB+FLAIR" if nicg == 2 else "IM", B, B * world,
+                                                               "3" if nicg == 2 else "2"),
+                       "precision": args.precision,
+                       "parallelism": "data parallel over %d GPU(s): NCCL all-reduce of the flat gradient bucket + "
+                                      "loss partial sums" % world,
+                       "l2": "per-step working set >> 126 MB L2; no explicit flush"},
+            "slices_per_s": args.steps * B * world / (ms * 1e-3),
+            "tflops_effective": args.steps * B * world * flop_per_slice / (ms * 1e-3) / 1e12,
+            "last_losses": [float(v) for v in out.cpu().numpy()],
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="uresnet_infer", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="uresnet_infer",
+                    choices=sorted(WORKLOADS) + ["depgan_train", "depgan_train_pf"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
@@ -315,6 +403,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload.startswith("depgan_train"):
+        run_train(args, rank, world, local_rank)
+        return
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w, rank)

@@ -128,6 +128,31 @@ class DepGanTrainer:
             self.G.adam_step(self.lrG, self.b1, self.b2)
         return [np.float32(v) for v in vals]
 
+    # ---- fully asynchronous device-side variants (no host round trip inside a generator iteration) -------
+    def critic_update_device(self, which, real2, x1, z, ep):
+        """One critic update (grads + all-reduce + Adam) on CUDA tensors; returns the loss tensor (no sync)."""
+        out = self.critic_grads_device(which, real2, x1, z, ep)
+        (self.Dy2 if which == 0 else self.Ddem).adam_step(self.lrD, self.b1, self.b2)
+        return out
+
+    def gen_iteration_device(self, crit_y2_batches, crit_dem_batches, x1, real2, noises):
+        """TG:796-878 on CUDA tensors.  crit_*_batches: lists of (real2, x1, z, ep); noises: (k,N,L,1) tensor.
+        The argmin over the k candidate losses and the gather of the selected noise stay on the device."""
+        torch = self.torch
+        for b in crit_y2_batches:
+            self.critic_update_device(0, *b)
+        for b in crit_dem_batches:
+            self.critic_update_device(1, *b)
+        losses = torch.empty(noises.shape[0], dtype=torch.float32, device=self.device)
+        for k in range(noises.shape[0]):
+            losses[k] = self.gen_device(x1, real2, noises[k], False)[0]
+        sel = torch.argmin(losses)                        # TG:875-876
+        z = noises.index_select(0, sel.reshape(1))[0].contiguous()
+        out = self.gen_device(x1, real2, z, True)
+        self.G.adam_step(self.lrG, self.b1, self.b2)
+        self.gen_iterations += 1
+        return losses, out
+
     # ---- one generator iteration of the reference schedule (TG:796-878) --------------------------------
     def diters(self, Diters=5):
         """Critic iterations for the current generator iteration (TG:792-795)."""

@@ -1,0 +1,116 @@
+"""Inference driver (EG:616-741 / EU:553-603) and data-parallel training on real GPUs."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from depgan_b200 import synth
+from oracle import depgan_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+THR = 0.178
+
+
+def test_subject_driver_is_bit_exact_given_the_predictions():
+    from depgan_b200 import Gen_UNet2D
+    from depgan_b200.infer import predict_subject_dem
+    H, Z, R = 64, 6, 4
+    P = util.gen_weights(1, 1, seed=3)
+    vol, _, mask = synth.make_im_pair(Z, H, H, thr=THR, seed=1)
+    noises = [synth.make_noise(Z, seed=50 + r) for r in range(R)]
+    g = Gen_UNet2D((H, H, 1), precision="bf16", max_batch=4)  # Z > max_batch exercises the chunking
+    g.set_weights(P)
+    res = predict_subject_dem(g, vol, mask, THR, n_repeat=R, noises=noises)
+    preds = [g.predict([vol, nz])[..., 0] for nz in noises]          # the same GPU predictions, via predict()
+    dem_o = O.inference_mean(preds, mask)
+    count_o, labels_o, fake2_o = O.dem_postproc(vol[..., 0], dem_o, mask, THR)
+    assert np.array_equal(res["dem"], dem_o) and np.array_equal(res["fake2"], fake2_o)
+    assert np.array_equal(res["labels"], labels_o.astype(np.uint8)) and res["wmh_voxels"] == count_o
+    # and the DEM itself is within the bf16 tolerance of the oracle network
+    want = np.mean([util.oracle_gen(P, vol, nz)[..., 0] * mask for nz in noises], axis=0)
+    assert np.abs(res["dem"] - want).max() <= 1e-2
+
+
+def test_subject_driver_uresnet():
+    from depgan_b200 import Gen_UNet2D
+    from depgan_b200.infer import predict_subject_uresnet
+    H, Z, R = 32, 3, 3
+    vol, mask = synth.make_flair(Z, H, H, seed=2)
+    noises = [synth.make_noise(Z, seed=60 + r) for r in range(R)]
+    g = Gen_UNet2D((H, H, 1), (32, 1), 32, 4, precision="bf16", max_batch=4)
+    res = predict_subject_uresnet(g, vol, mask, n_repeat=R, noises=noises)
+    preds = [g.predict([vol, nz]) for nz in noises]
+    mean_o = O.inference_mean(preds, mask[..., None])
+    lab_o, cnt_o = O.uresnet_labels(mean_o)
+    assert np.array_equal(res["prob_mean"], mean_o) and np.array_equal(res["labels"], lab_o)
+    assert res["wmh_voxels"] == cnt_o
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from depgan_b200 import Dis_C2D_FCN1, Gen_UNet2D
+    from depgan_b200.infer import shard_range
+    from depgan_b200.trainer import DepGanTrainer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    H, N = 32, 4
+    dev = "cuda:%d" % rank
+    PG, PD1, PD2 = util.gen_weights(1, 1, seed=1), util.critic_weights(H, H, seed=2), util.critic_weights(H, H, seed=3)
+    x1, y2, _ = synth.make_im_pair(N, H, H, thr=THR, seed=4)
+    z, ep = synth.make_noise(N, seed=5), synth.make_eps(N, seed=6)
+    lo, hi = shard_range(N, rank, world)
+    n = hi - lo
+    G = Gen_UNet2D((H, H, 1), precision="fp32", max_batch=n, device=dev, training=True)
+    D1 = Dis_C2D_FCN1((H, H, 1), precision="fp32", max_batch=3 * n, device=dev, training=True)
+    D2 = Dis_C2D_FCN1((H, H, 1), precision="fp32", max_batch=3 * n, device=dev, training=True)
+    G.set_weights(PG), D1.set_weights(PD1), D2.set_weights(PD2)
+    tr = DepGanTrainer(G, D1, D2, THR)
+    assert tr.world == world
+    r = {}
+    r["d"] = [float(v) for v in tr.netD_y2_train([y2[lo:hi], x1[lo:hi], z[lo:hi], ep[lo:hi]], update=False)]
+    r["gp"] = tr.last_gp
+    r["d_grads"] = D1.get_grads()
+    r["g"] = [float(v) for v in tr.netG_train([x1[lo:hi], y2[lo:hi], z[lo:hi]], update=False)]
+    r["g_grads"] = G.get_grads()
+    if rank == 0:
+        out.update(r)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_data_parallel_two_gpus_reproduce_global_batch_step():
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    H, N = 32, 4
+    PG, PD1, PD2 = util.gen_weights(1, 1, seed=1), util.critic_weights(H, H, seed=2), util.critic_weights(H, H, seed=3)
+    x1, y2, _ = synth.make_im_pair(N, H, H, thr=THR, seed=4)
+    z, ep = synth.make_noise(N, seed=5), synth.make_eps(N, seed=6)
+    ora = O.OracleTrainer(PG, PD1, PD2, THR)
+    want = ora.netD_y2_train([y2, x1, z, ep], update=False)
+    assert np.allclose(out["d"], want, rtol=1e-4, atol=1e-5), (out["d"], want)
+    assert abs(out["gp"] - ora.last_gp) <= 1e-4 * max(1.0, abs(ora.last_gp))
+    for k, w in ora.last_grads.items():
+        w = w.numpy()
+        if np.linalg.norm(w) > 1e-9:
+            assert np.linalg.norm(out["d_grads"][k] - w) / np.linalg.norm(w) < 2e-3, k
+    want = ora.netG_train([x1, y2, z], update=False)
+    assert np.allclose(out["g"], want, rtol=1e-4, atol=1e-5), (out["g"], want)
+    for k, w in ora.last_grads.items():
+        w = w.numpy()
+        if np.linalg.norm(w) > 1e-9:
+            assert np.linalg.norm(out["g_grads"][k] - w) / np.linalg.norm(w) < 2e-3, k
