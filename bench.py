@@ -345,6 +345,21 @@ def run_train(args, rank, world, local_rank):
     for i in range(args.warmup):
         step(i)
     barrier()
+    prof = None
+    if rank == 0 and os.environ.get("DEPGAN_PROFILE_LOG"):
+        from depgan_b200 import _lib
+        L = _lib.lib()
+        ncls = 6
+        a_ms, a_fl, a_by = (C.c_double * ncls)(), (C.c_double * ncls)(), (C.c_double * ncls)()
+        a_n = (C.c_longlong * ncls)()
+        L.depgan_profile_begin()
+        step(0)
+        _lib.check(L.depgan_profile_end(a_ms, a_fl, a_by, a_n, ncls), "profile_end")
+        names = ["tc3x3", "tc5x5", "tc1x1_deconv", "simt_conv", "simt_wgrad", "tc_wgrad"]
+        prof = {nm: {"ms": a_ms[i], "launches": int(a_n[i]),
+                     "tflops": (a_fl[i] / (a_ms[i] * 1e-3) / 1e12) if a_ms[i] > 0 else None}
+                for i, nm in enumerate(names)}
+        barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -380,7 +395,7 @@ def run_train(args, rank, world, local_rank):
             "slices_per_s": args.steps * B * world / (ms * 1e-3),
             "tflops_effective": args.steps * B * world * flop_per_slice / (ms * 1e-3) / 1e12,
             "last_losses": [float(v) for v in out.cpu().numpy()],
-            "clocks": clocks, "gpu_launches": int(launches),
+            "clocks": clocks, "gpu_launches": int(launches), "conv_time_per_iteration": prof,
         }
         print(json.dumps(line))
     if world > 1:

@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 from . import synth
 
-__all__ = ["Gen_UNet2D", "Dis_C2D_FCN1", "conv2d_op", "launch_count"]
+__all__ = ["Gen_UNet2D", "Dis_C2D_FCN1", "conv2d_op", "wgrad_op", "launch_count"]
 
 
 def _torch():
@@ -348,3 +348,34 @@ def conv2d_op(x, w, *, x1=None, scale=None, shift=None, relu=False, film=None, r
     if head is None and not want_pre:
         return outf
     return outf, {"head": hout, "pre": None if pre is None else pre.float()}
+
+
+def wgrad_op(x, dy, ks, *, x1=None, use_tc=True):
+    """Weight gradient of a 'same' stride-1 convolution through depgan_op_wgrad.
+    x (N,H,W,C0) [, x1 (N,H,W,C1)], dy (N,H,W,Cout) float32 CUDA tensors -> dw (ks,ks,C0+C1,Cout) float32."""
+    torch = _torch()
+    L = _lib.lib()
+    st = _stream(torch)
+    dev = x.device
+    N, H, W, C0 = x.shape
+    C1 = 0 if x1 is None else x1.shape[3]
+    cout = dy.shape[3]
+    keep = []
+
+    def conv(t):
+        t = t.to(dev, torch.float32).contiguous()
+        keep.append(t)
+        if not use_tc:
+            return t
+        b = torch.empty(t.numel(), dtype=torch.bfloat16, device=dev)
+        _lib.check(L.depgan_op_f32_to_bf16(t.data_ptr(), b.data_ptr(), t.numel(), st), "f32_to_bf16")
+        keep.append(b)
+        return b
+
+    xa, da = conv(x), conv(dy)
+    x1a = conv(x1) if x1 is not None else None
+    dw = torch.zeros((ks, ks, C0 + C1, cout), dtype=torch.float32, device=dev)
+    _lib.check(L.depgan_op_wgrad(xa.data_ptr(), None if x1a is None else x1a.data_ptr(), C0, C1, da.data_ptr(),
+                                 dw.data_ptr(), N, H, W, cout, ks, int(use_tc), st), "op_wgrad")
+    torch.cuda.synchronize(dev)
+    return dw

@@ -111,3 +111,6 @@ struct WgradArgs {
   float alpha;  // scale applied to the accumulated sum
 };
 int conv_wgrad_simt(const WgradArgs& a, cudaStream_t st);
+int conv_wgrad_tc(const WgradArgs& a, cudaStream_t st);  // tcgen05 path (bf16 x and dy)
+bool wgrad_tc_supported(const WgradArgs& a);
+int wgrad_tc_init();

@@ -136,8 +136,8 @@ int launch_fwd(const ConvArgs& a, cudaStream_t st) {
 template <typename TO, int KS, int CIN, int COUT>
 __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ scale,
-                                                         const float* __restrict__ shift, TO* __restrict__ out, int H,
-                                                         int W, int relu) {
+                                                         const float* __restrict__ shift, TO* __restrict__ out,
+                                                         const TO* __restrict__ mask, int H, int W, int relu) {
   constexpr int PAD = KS / 2, IT = 16 + KS - 1, TAPS = KS * KS;
   __shared__ float s_in[IT][IT + 1][CIN];
   __shared__ __align__(16) float s_w[TAPS * CIN][COUT];
@@ -180,7 +180,12 @@ __global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict
     acc[i] = fmaf(acc[i], s_sc[i], s_sh[i]);
     if (relu) acc[i] = fmaxf(acc[i], 0.f);
   }
-  TO* o = out + (((size_t)n * H + h0 + ty) * W + w0 + tx) * COUT;
+  const size_t obase = (((size_t)n * H + h0 + ty) * W + w0 + tx) * COUT;
+  if (mask) {  // activation-pattern mask of the JVP pass (TG:543: the critic linearised at the mixed sample)
+#pragma unroll
+    for (int i = 0; i < COUT; ++i) acc[i] = ldf(mask + obase + i) > 0.f ? acc[i] : 0.f;
+  }
+  TO* o = out + obase;
   if constexpr (sizeof(TO) == 2) {
     uint4* o4 = reinterpret_cast<uint4*>(o);
 #pragma unroll
@@ -202,7 +207,7 @@ template <typename TO, int KS, int CIN, int COUT>
 int launch_first(const ConvArgs& a, cudaStream_t st) {
   dim3 grid((a.W / 16) * (a.H / 16), a.N);
   conv_first_kernel<TO, KS, CIN, COUT><<<grid, 256, 0, st>>>((const float*)a.in0, a.w, a.scale, a.shift, (TO*)a.out,
-                                                              a.H, a.W, a.relu);
+                                                              (const TO*)a.mask_src, a.H, a.W, a.relu);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -210,7 +215,7 @@ int launch_first(const ConvArgs& a, cudaStream_t st) {
 // returns 1 when the call was taken by a first-layer specialisation, 0 otherwise, <0 on error
 template <typename TO>
 int try_first(const ConvArgs& a, cudaStream_t st) {
-  if (a.in_dt != DT_F32 || a.C1 != 0 || a.out_pre || a.film_g || a.add_src || a.mask_src || !a.out) return 0;
+  if (a.in_dt != DT_F32 || a.C1 != 0 || a.out_pre || a.film_g || a.add_src || !a.out) return 0;
   if (a.H % 16 || a.W % 16) return 0;
   int r = 1;
   if (a.ks == 3 && a.C0 == 1 && a.Cout == 32) r = launch_first<TO, 3, 1, 32>(a, st);
@@ -218,6 +223,118 @@ int try_first(const ConvArgs& a, cudaStream_t st) {
   else if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) r = launch_first<TO, 5, 1, 16>(a, st);
   else return 0;
   return r < 0 ? r : 1;
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// Single-output-channel convolution (the data gradient of conv2d_dis_0a: 16 -> 1, 5x5): dD/dx for the gradient
+// penalty and for the generator's adversarial terms.  HBM-bound (2*Cin B in, 4 B out per pixel): one thread per
+// pixel, the input halo tile in shared memory as fp32, weights broadcast from shared memory, fp32 output.
+// ------------------------------------------------------------------------------------------------------
+template <typename TI, int KS, int CIN>
+__global__ void __launch_bounds__(256) conv_last_kernel(const TI* __restrict__ in, const float* __restrict__ w,
+                                                        float* __restrict__ out, int H, int W) {
+  constexpr int PAD = KS / 2, IT = 16 + KS - 1, TAPS = KS * KS;
+  __shared__ float s_in[IT * IT][CIN + 1];
+  __shared__ float s_w[TAPS * CIN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tiles_w = W / 16;
+  const int w0 = (blockIdx.x % tiles_w) * 16, h0 = (blockIdx.x / tiles_w) * 16, n = blockIdx.y;
+  for (int i = tid; i < TAPS * CIN; i += 256) s_w[i] = w[i];  // [tap][ci][0]
+  for (int i = tid; i < IT * IT * CIN; i += 256) {
+    const int ci = i % CIN, p = i / CIN, c = p % IT, r = p / IT;
+    const int h = h0 + r - PAD, ww = w0 + c - PAD;
+    s_in[p][ci] = (h >= 0 && h < H && ww >= 0 && ww < W) ? ldf(in + (((size_t)n * H + h) * W + ww) * CIN + ci) : 0.f;
+  }
+  __syncthreads();
+  float acc = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < TAPS; ++tap) {
+    const float* xp = s_in[(ty + tap / KS) * IT + tx + tap % KS];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) acc = fmaf(xp[ci], s_w[tap * CIN + ci], acc);
+  }
+  out[((size_t)n * H + h0 + ty) * W + w0 + tx] = acc;
+}
+
+template <typename TI>
+int try_last(const ConvArgs& a, cudaStream_t st) {
+  if (a.out_dt != DT_F32 || a.Cout != 1 || a.C1 != 0 || a.scale || a.shift || a.out_pre || a.film_g || a.add_src ||
+      a.mask_src || a.relu || !a.out || a.H % 16 || a.W % 16)
+    return 0;
+  dim3 grid((a.W / 16) * (a.H / 16), a.N);
+  if (a.ks == 5 && a.C0 == 16)
+    conv_last_kernel<TI, 5, 16><<<grid, 256, 0, st>>>((const TI*)a.in0, a.w, (float*)a.out, a.H, a.W);
+  else
+    return 0;
+  DG_LAUNCH_CHECK();
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Weight gradient of a first layer (fp32 input with CIN <= 2 channels): dw[tap][ci][co] += sum_p x[p+off] dy[p][co].
+// The result is tiny (<= 25*2*32 floats) and the pass is HBM-bound on dy: CTA = one 16x16 tile, thread =
+// (tap, ci, co) item looping the tile's pixels out of shared memory, one atomic per item per CTA.
+// ------------------------------------------------------------------------------------------------------
+template <typename TD, int KS, int CIN, int COUT>
+__global__ void __launch_bounds__(256) wgrad_first_kernel(const float* __restrict__ x, const TD* __restrict__ dy,
+                                                          float* __restrict__ dw, int H, int W, int tiles, float alpha) {
+  constexpr int PAD = KS / 2, IT = 16 + KS - 1, TAPS = KS * KS, ITEMS = TAPS * CIN * COUT;
+  __shared__ float s_x[IT][IT + 1][CIN];
+  __shared__ float s_d[256][COUT + 1];
+  const int tid = threadIdx.x;
+  const int tiles_w = W / 16, tiles_per_img = tiles_w * (H / 16);
+  float acc[(ITEMS + 255) / 256];
+#pragma unroll
+  for (int k = 0; k < (ITEMS + 255) / 256; ++k) acc[k] = 0.f;
+  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int n = t / tiles_per_img, tt = t % tiles_per_img;
+    const int w0 = (tt % tiles_w) * 16, h0 = (tt / tiles_w) * 16;
+    __syncthreads();
+    for (int i = tid; i < IT * IT * CIN; i += 256) {
+      const int ci = i % CIN, c = (i / CIN) % IT, r = i / (CIN * IT);
+      const int h = h0 + r - PAD, ww = w0 + c - PAD;
+      s_x[r][c][ci] = (h >= 0 && h < H && ww >= 0 && ww < W) ? x[(((size_t)n * H + h) * W + ww) * CIN + ci] : 0.f;
+    }
+    for (int i = tid; i < 256 * COUT; i += 256) {
+      const int co = i % COUT, p = i / COUT;
+      s_d[p][co] = ldf(dy + (((size_t)n * H + h0 + p / 16) * W + w0 + p % 16) * COUT + co);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < (ITEMS + 255) / 256; ++k) {
+      const int item = tid + 256 * k;
+      if (item < ITEMS) {
+        const int co = item % COUT, ci = (item / COUT) % CIN, tap = item / (COUT * CIN);
+        const int dy_ = tap / KS, dx_ = tap % KS;
+        float a = 0.f;
+        for (int p = 0; p < 256; ++p) a = fmaf(s_x[(p >> 4) + dy_][(p & 15) + dx_][ci], s_d[p][co], a);
+        acc[k] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < (ITEMS + 255) / 256; ++k) {
+    const int item = tid + 256 * k;
+    if (item < ITEMS) atomicAdd(dw + item, alpha * acc[k]);
+  }
+}
+
+template <typename TD>
+int try_wgrad_first(const WgradArgs& a, cudaStream_t st) {
+  if (a.x_dt != DT_F32 || a.C1 != 0 || a.H % 16 || a.W % 16) return 0;
+  const int tiles = (a.W / 16) * (a.H / 16) * a.N;
+  const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
+#define DG_WF(KS_, CI_, CO_)                                                                                   \
+  wgrad_first_kernel<TD, KS_, CI_, CO_><<<grid, 256, 0, st>>>((const float*)a.x0, (const TD*)a.dy, a.dw, a.H, a.W, \
+                                                              tiles, a.alpha)
+  if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) DG_WF(5, 1, 16);
+  else if (a.ks == 3 && a.C0 == 1 && a.Cout == 32) DG_WF(3, 1, 32);
+  else if (a.ks == 3 && a.C0 == 2 && a.Cout == 32) DG_WF(3, 2, 32);
+  else return 0;
+#undef DG_WF
+  DG_LAUNCH_CHECK();
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -344,6 +461,8 @@ int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
   {
     const int r = a.out_dt == DT_BF16 ? try_first<bf16>(a, st) : try_first<float>(a, st);
     if (r != 0) return r < 0 ? r : 0;
+    const int r2 = a.in_dt == DT_BF16 ? try_last<bf16>(a, st) : try_last<float>(a, st);
+    if (r2 != 0) return r2 < 0 ? r2 : 0;
   }
   if (a.in_dt == DT_F32 && a.out_dt == DT_F32) return launch_fwd<float, float>(a, st);
   if (a.in_dt == DT_F32 && a.out_dt == DT_BF16) return launch_fwd<float, bf16>(a, st);
@@ -355,6 +474,10 @@ int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
 
 int conv_wgrad_simt(const WgradArgs& a, cudaStream_t st) {
   if (a.N <= 0) return 0;
+  {
+    const int r = a.dy_dt == DT_BF16 ? try_wgrad_first<bf16>(a, st) : try_wgrad_first<float>(a, st);
+    if (r != 0) return r < 0 ? r : 0;
+  }
   if (a.x_dt == DT_F32 && a.dy_dt == DT_F32) return launch_wgrad<float, float>(a, st);
   if (a.x_dt == DT_BF16 && a.dy_dt == DT_BF16) return launch_wgrad<bf16, bf16>(a, st);
   if (a.x_dt == DT_F32 && a.dy_dt == DT_BF16) return launch_wgrad<float, bf16>(a, st);

@@ -268,42 +268,40 @@ int fold_dense(depgan_net* h, DenseL& D, cudaStream_t st) {
 // =========================================================================================================
 // optional per-launch timing (bench.py roofline leg): CUDA events around every convolution launch
 // =========================================================================================================
-namespace {
-struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; int ks, H, W, cin, cout, n; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
-int conv_class(const ConvArgs& a, bool tc) {
-  if (!tc) return 3;
-  if (a.deconv) return 2;
-  return a.ks == 5 ? 1 : a.ks == 3 ? 0 : 2;
-}
-}  // namespace
 
-struct ProfScope {
-  bool on;
-  ProfRec r;
-  cudaStream_t st;
-  ProfScope(const ConvArgs& a, bool tc, cudaStream_t s) : on(g_prof_on), st(s) {
-    if (!on) return;
-    const double px = (double)a.N * a.H * a.W, cin = a.C0 + a.C1;
-    const double ncols = a.deconv ? 4.0 * a.Cout : (double)a.Cout;
-    r.cls = conv_class(a, tc);
-    r.flops = 2.0 * px * a.ks * a.ks * cin * ncols;
-    const double ies = dt_size(a.in_dt), oes = dt_size(a.out_dt);
-    r.bytes = px * cin * ies + (a.out ? px * ncols * oes : 0.0) + (a.out_pre ? px * ncols * oes : 0.0) +
-              (a.res ? px * ncols * oes : 0.0) + (a.add_src ? px * ncols * oes : 0.0) +
-              (a.mask_src ? px * ncols * oes : 0.0) + (a.head_out ? px * a.head_nc * 4.0 : 0.0);
-    r.ks = a.ks; r.H = a.H; r.W = a.W; r.cin = a.C0 + a.C1; r.cout = (int)ncols; r.n = a.N;
-    cudaEventCreate(&r.e0);
-    cudaEventCreate(&r.e1);
-    cudaEventRecord(r.e0, st);
-  }
-  ~ProfScope() {
-    if (!on) return;
-    cudaEventRecord(r.e1, st);
-    g_prof.push_back(r);
-  }
-};
+ProfScope::ProfScope(const ConvArgs& a, bool tc, cudaStream_t s) : on(g_prof_on), st(s) {
+  if (!on) return;
+  const double px = (double)a.N * a.H * a.W, cin = a.C0 + a.C1;
+  const double ncols = a.deconv ? 4.0 * a.Cout : (double)a.Cout;
+  r.cls = !tc ? 3 : (a.deconv ? 2 : (a.ks == 5 ? 1 : a.ks == 3 ? 0 : 2));
+  r.flops = 2.0 * px * a.ks * a.ks * cin * ncols;
+  const double ies = dt_size(a.in_dt), oes = dt_size(a.out_dt);
+  r.bytes = px * cin * ies + (a.out ? px * ncols * oes : 0.0) + (a.out_pre ? px * ncols * oes : 0.0) +
+            (a.res ? px * ncols * oes : 0.0) + (a.add_src ? px * ncols * oes : 0.0) +
+            (a.mask_src ? px * ncols * oes : 0.0) + (a.head_out ? px * a.head_nc * 4.0 : 0.0);
+  r.ks = a.ks; r.H = a.H; r.W = a.W; r.cin = a.C0 + a.C1; r.cout = (int)ncols; r.n = a.N;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+}
+ProfScope::ProfScope(const WgradArgs& a, bool tc, cudaStream_t s) : on(g_prof_on), st(s) {
+  if (!on) return;
+  const double px = (double)a.N * a.H * a.W, cin = a.C0 + a.C1;
+  r.cls = tc ? 5 : 4;
+  r.flops = 2.0 * px * a.ks * a.ks * cin * a.Cout;
+  r.bytes = px * cin * dt_size(a.x_dt) + px * a.Cout * dt_size(a.dy_dt);
+  r.ks = a.ks; r.H = a.H; r.W = a.W; r.cin = (int)cin; r.cout = a.Cout; r.n = a.N;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+}
+ProfScope::~ProfScope() {
+  if (!on) return;
+  cudaEventRecord(r.e1, st);
+  g_prof.push_back(r);
+}
 
 // =========================================================================================================
 // forward executors
@@ -644,6 +642,19 @@ int depgan_op_conv2d(const depgan_conv_desc* d, void* stream) {
     return conv_fwd_tc(a, (cudaStream_t)stream);
   }
   return conv_fwd_simt(a, (cudaStream_t)stream);
+}
+
+int depgan_op_wgrad(const void* x0, const void* x1, int C0, int C1, const void* dy, float* dw, int N, int H, int W,
+                    int Cout, int ks, int use_tc, void* stream) {
+  WgradArgs a{};
+  a.x0 = x0; a.x1 = x1; a.C0 = C0; a.C1 = C1; a.dy = dy; a.dw = dw; a.N = N; a.H = H; a.W = W; a.Cout = Cout;
+  a.ks = ks; a.alpha = 1.f;
+  a.x_dt = a.dy_dt = use_tc ? DT_BF16 : DT_F32;
+  if (use_tc) {
+    DG_REQUIRE(wgrad_tc_supported(a), "op_wgrad: shape not supported by the tcgen05 path");
+    return conv_wgrad_tc(a, (cudaStream_t)stream);
+  }
+  return conv_wgrad_simt(a, (cudaStream_t)stream);
 }
 
 // fp32 [taps][Cin][Cout] (Keras HWIO) -> bf16 [taps][Cout][Cin] (the tcgen05 B operand); tests / benchmarks.

@@ -119,6 +119,17 @@ static const char* const GEN_OUT[7] = {"gen_1", "gen_3", "gen_5", "gen_9", "gen_
 static const char* const GEN_SUF[7] = {"_m1", "_m2", "_m3", "", "_p3", "_p2", "_p1"};
 static const char* const GEN_DEC[3] = {"de_gen_9", "de_gen_11", "de_gen_15"};
 
+// per-launch timing records (bench.py roofline leg; see depgan_profile_begin/end)
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; int ks, H, W, cin, cout, n; };
+struct ProfScope {
+  bool on;
+  ProfRec r;
+  cudaStream_t st;
+  ProfScope(const ConvArgs& a, bool tc, cudaStream_t s);
+  ProfScope(const WgradArgs& a, bool tc, cudaStream_t s);
+  ~ProfScope();
+};
+
 int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void* in1, int C1, int in_dt, ConvArgs extra,
              int n, cudaStream_t st);
 int gen_forward_impl(depgan_net* g, const float* x, const float* z, float* out, int n, bool keep, cudaStream_t st);

@@ -109,7 +109,9 @@ int dgrad_conv(depgan_net* h, const ConvL& L, const void* dy, void* dx, int dx_d
   a.out = dx; a.add_src = add_src; a.mask_src = mask_src;
   a.N = n; a.H = h->lvl_h(L.lvl); a.W = h->lvl_w(L.lvl); a.Cout = L.cin; a.ks = L.ks;
   a.in_dt = h->act_dt; a.out_dt = dx_dt;
-  if (h->act_dt == DT_BF16 && conv_tc_supported(a)) return conv_fwd_tc(a, st);
+  const bool tc = h->act_dt == DT_BF16 && conv_tc_supported(a);
+  ProfScope prof(a, tc, st);
+  if (tc) return conv_fwd_tc(a, st);
   return conv_fwd_simt(a, st);
 }
 
@@ -119,6 +121,9 @@ int wgrad_conv(depgan_net* h, const ConvL& L, const void* x0, int C0, const void
   a.x0 = x0; a.x1 = x1; a.C0 = C0; a.C1 = C1; a.dy = dy; a.dw = dw;
   a.N = n; a.H = h->lvl_h(L.lvl); a.W = h->lvl_w(L.lvl); a.Cout = L.cout; a.ks = L.ks;
   a.x_dt = x_dt; a.dy_dt = h->act_dt; a.alpha = 1.f;
+  const bool tc = wgrad_tc_supported(a);
+  ProfScope prof(a, tc, st);
+  if (tc) return conv_wgrad_tc(a, st);
   return conv_wgrad_simt(a, st);
 }
 
@@ -212,8 +217,12 @@ int depgan_critic_grads(depgan_net* d, depgan_net* g, int which, const float* re
       a.mask_src = off_ptr((const void*)d->c_act[i], rows_off(d, L, 2 * n));
       a.N = n; a.H = d->lvl_h(L.lvl); a.W = d->lvl_w(L.lvl); a.Cout = L.cout; a.ks = L.ks;
       a.in_dt = vin_dt; a.out_dt = d->act_dt;
-      if (d->act_dt == DT_BF16 && conv_tc_supported(a)) DG_TRY(conv_fwd_tc(a, st));
-      else DG_TRY(conv_fwd_simt(a, st));
+      {
+        const bool tc = d->act_dt == DT_BF16 && conv_tc_supported(a);
+        ProfScope prof(a, tc, st);
+        if (tc) DG_TRY(conv_fwd_tc(a, st));
+        else DG_TRY(conv_fwd_simt(a, st));
+      }
       vin = T.v[i]; vin_dt = d->act_dt; C = L.cout;
       if (i == 1 || i == 3 || i == 5 || i == 7) {
         DG_TRY(k_maxpool_select(T.v[i], a.mask_src, T.vp[i / 2], n, a.H, a.W, C, d->act_dt, st));
@@ -368,7 +377,10 @@ int depgan_gen_grads(depgan_net* g, depgan_net* dy2, depgan_net* ddem, const flo
         wa.x0 = g->act_o[bi - 1]; wa.C0 = Ld.cin; wa.dy = T.s2d; wa.dw = T.g_raw;
         wa.N = n; wa.H = Hh; wa.W = Wh; wa.Cout = 4 * Ld.cout; wa.ks = 1;
         wa.x_dt = g->act_dt; wa.dy_dt = g->act_dt; wa.alpha = 1.f;
-        DG_TRY(conv_wgrad_simt(wa, st));
+        const bool tc = wgrad_tc_supported(wa);
+        ProfScope prof(wa, tc, st);
+        if (tc) DG_TRY(conv_wgrad_tc(wa, st));
+        else DG_TRY(conv_wgrad_simt(wa, st));
       }
       DG_CHECK_CUDA(cudaMemsetAsync(T.sum_dy, 0, sizeof(float) * 4 * Ld.cout, st));
       DG_TRY(k_channel_sum(T.s2d, pxh, 4 * Ld.cout, T.sum_dy, 1.f, g->act_dt, st));

@@ -114,7 +114,8 @@ int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, doub
 long long depgan_launch_count(void);
 /* Per-launch device timing of the convolution kernels (bench.py roofline leg): between begin and end every
  * convolution launch is bracketed by CUDA events on its stream.  Classes: 0 = tcgen05 3x3, 1 = tcgen05 5x5,
- * 2 = tcgen05 1x1 / transposed conv, 3 = fp32 CUDA-core conv.  flops/bytes are the algorithmic figures of
+ * 2 = tcgen05 1x1 / transposed conv, 3 = fp32 CUDA-core conv, 4 = CUDA-core weight gradient, 5 = tcgen05 weight
+ * gradient.  flops/bytes are the algorithmic figures of
  * DESIGN.md (2*k*k*Cin*Cout per pixel; activation bytes read + written once). */
 int depgan_profile_begin(void);
 int depgan_profile_end(double* ms_by_class, double* flops_by_class, double* bytes_by_class,
@@ -145,6 +146,10 @@ typedef struct depgan_conv_desc {
   int in_bf16, out_bf16, use_tc;
 } depgan_conv_desc;
 int depgan_op_conv2d(const depgan_conv_desc* d, void* stream);
+/* Weight gradient of one convolution: dw[tap][Cin][Cout] (fp32, Keras HWIO order) += sum_p x[p+off(tap)] (x) dy[p].
+ * use_tc=1: tcgen05 path (x, dy bf16); use_tc=0: fp32 CUDA-core path (x, dy float32).  The caller zeroes dw. */
+int depgan_op_wgrad(const void* x0, const void* x1, int C0, int C1, const void* dy, float* dw, int N, int H, int W,
+                    int Cout, int ks, int use_tc, void* stream);
 int depgan_op_pack_weights(const float* w_f32_dev, void* w_bf16_dev, int taps, int cin, int cout, void* stream);
 int depgan_op_f32_to_bf16(const float* src_dev, void* dst_dev, long long n, void* stream);
 int depgan_op_bf16_to_f32(const void* src_dev, float* dst_dev, long long n, void* stream);

@@ -46,7 +46,7 @@ def _rand(shape, seed, scale=1.0):
 
 
 @pytest.mark.parametrize("ks,c0,c1,cout", [(3, 1, 0, 32), (3, 2, 0, 32), (3, 32, 0, 32), (5, 1, 0, 16), (5, 16, 0, 16),
-                                           (1, 32, 0, 4), (3, 24, 8, 40), (3, 16, 0, 1)])
+                                           (1, 32, 0, 4), (3, 24, 8, 40), (3, 16, 0, 1), (5, 16, 0, 1)])
 def test_simt_conv_matches_fp32_reference(ks, c0, c1, cout):
     from depgan_b200 import conv2d_op
     N, H, W = 2, 32, 48
@@ -58,6 +58,21 @@ def test_simt_conv_matches_fp32_reference(ks, c0, c1, cout):
                     use_tc=False).cpu()
     want, _ = ref_conv(x, w, x1, sc, sh, relu=True)
     assert torch.allclose(got, want, atol=2e-4, rtol=1e-4), float((got - want).abs().max())
+
+
+def test_first_and_last_layer_specialisations():
+    """conv2d_dis_0a JVP (1 -> 16, 5x5, activation mask, no bias) and its data gradient (16 -> 1, fp32 out)."""
+    from depgan_b200 import conv2d_op
+    N, H, W = 2, 32, 48
+    x, w = _rand((N, H, W, 1), 1), _rand((5, 5, 1, 16), 2, 0.2)
+    mask = _rand((N, H, W, 16), 3)
+    got = conv2d_op(x.cuda(), w.cuda(), mask=mask.cuda(), use_tc=False).cpu()
+    want, _ = ref_conv(x, w, mask=mask)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
+    b, wd = _rand((N, H, W, 16), 4), _rand((5, 5, 16, 1), 5, 0.2)
+    got = conv2d_op(b.cuda(), wd.cuda(), use_tc=False).cpu()
+    want, _ = ref_conv(b, wd)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
 
 
 def test_simt_conv_film_mask_epilogues():
@@ -136,3 +151,47 @@ def test_tcgen05_conv_fused_head(nc, act):
     seg = y.double() @ hw.double() + hb.double()
     want = torch.tanh(seg) if act == 0 else torch.softmax(seg, dim=-1)
     assert float((ex["head"].cpu().double() - want).abs().max()) <= 1e-2
+
+
+def ref_wgrad(x, dy, ks):
+    """dw[a,b,ci,co] = sum_{n,h,w} xpad[n,h+a,w+b,ci] * dy[n,h,w,co]  (fp64)."""
+    p = ks // 2
+    xp = F.pad(x.permute(0, 3, 1, 2).double(), (p, p, p, p))
+    d = dy.double()
+    H, W = x.shape[1], x.shape[2]
+    out = torch.zeros(ks, ks, x.shape[3], dy.shape[3], dtype=torch.float64)
+    for a in range(ks):
+        for b in range(ks):
+            out[a, b] = torch.einsum("nchw,nhwo->co", xp[:, :, a:a + H, b:b + W], d)
+    return out.float()
+
+
+WG_CASES = [  # ks, c0, c1, cout, H, W
+    (3, 64, 0, 64, 32, 32), (3, 32, 0, 32, 32, 48), (5, 16, 0, 16, 32, 32), (5, 32, 0, 32, 32, 16),
+    (5, 16, 0, 32, 16, 32), (3, 32, 0, 64, 16, 16), (3, 96, 0, 96, 16, 32), (3, 64, 32, 32, 32, 32),
+    (3, 128, 96, 96, 16, 16), (3, 128, 0, 256, 16, 16), (3, 256, 0, 256, 16, 16), (1, 64, 0, 256, 16, 32),
+    (1, 96, 0, 384, 16, 16), (3, 96, 64, 64, 32, 16),
+]
+
+
+@pytest.mark.parametrize("ks,c0,c1,cout,H,W", WG_CASES)
+def test_tcgen05_wgrad_matches_reference(ks, c0, c1, cout, H, W):
+    from depgan_b200 import wgrad_op
+    N = 3
+    x = _bf(_rand((N, H, W, c0), 1))
+    x1 = _bf(_rand((N, H, W, c1), 2)) if c1 else None
+    dy = _bf(_rand((N, H, W, cout), 3))
+    got = wgrad_op(x.cuda(), dy.cuda(), ks, x1=None if x1 is None else x1.cuda(), use_tc=True).cpu()
+    xa = x if x1 is None else torch.cat([x, x1], dim=3)
+    want = ref_wgrad(xa, dy, ks)
+    err = float((got - want).abs().max())
+    assert err <= 2e-3 * float(want.abs().max()), (err, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("ks,c0,cout", [(3, 8, 16), (5, 1, 16), (3, 2, 32), (1, 24, 8)])
+def test_simt_wgrad_matches_reference(ks, c0, cout):
+    from depgan_b200 import wgrad_op
+    x, dy = _rand((2, 32, 16, c0), 1), _rand((2, 32, 16, cout), 2)
+    got = wgrad_op(x.cuda(), dy.cuda(), ks, use_tc=False).cpu()
+    want = ref_wgrad(x, dy, ks)
+    assert float((got - want).abs().max()) <= 1e-3 * float(want.abs().max())
