@@ -264,6 +264,13 @@ def run_gpu(args, w, rank, world, local_rank):
             except Exception:
                 pass
 
+    # ---- second headline metric: DEP-GAN train steps/s (configs[2]; data parallel when world > 1) ----
+    train = None
+    if not args.no_train:
+        del g, out, xd, zd
+        torch.cuda.empty_cache()
+        train = measure_train(args, rank, world, dev, steps=3, warmup=1)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -293,27 +300,24 @@ def run_gpu(args, w, rank, world, local_rank):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": slices / (ms_e2e * 1e-3), "unit": "slices/s",
                 "h2d_bytes_per_step": int(xh.numel() * 4 + zh.numel() * 4), "d2h_bytes_per_step": int(oh.numel() * 4)},
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu, "train": train,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_train(args, rank, world, local_rank):
+def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"):
     """BASELINE configs[2]/[3]: DEP-GAN two-critic training, one step = one generator iteration of the reference
-    schedule (5 Y2-critic + 5 DEM-critic updates, 10 noise evaluations, 1 generator update; TG:796-878)."""
+    schedule (5 Y2-critic + 5 DEM-critic updates, 10 noise evaluations, 1 generator update; TG:796-878).
+    Returns the result dict on rank 0 (None elsewhere).  The process group must already exist for world > 1."""
     import torch
     import torch.distributed as dist
     from depgan_b200 import Dis_C2D_FCN1, Gen_UNet2D, launch_count, synth
     from depgan_b200.trainer import DepGanTrainer
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch or 32
-    nicg = 2 if args.workload == "depgan_train_pf" else 1
+    B = args.train_batch
+    nicg = 2 if workload == "depgan_train_pf" else 1
     thr = 0.5 if nicg == 2 else 0.178
     G = Gen_UNet2D((256, 256, nicg), (32, 1), 32, 1, precision=args.precision, max_batch=B, device=str(dev),
                    training=True, seed=0)
@@ -342,7 +346,7 @@ def run_train(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         step(i)
     barrier()
     prof = None
@@ -359,14 +363,14 @@ def run_train(args, rank, world, local_rank):
         prof = {nm: {"ms": a_ms[i], "launches": int(a_n[i]),
                      "tflops": (a_fl[i] / (a_ms[i] * 1e-3) / 1e12) if a_ms[i] > 0 else None}
                 for i, nm in enumerate(names)}
-        barrier()
-    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
     l0 = launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         losses, out = step(i)
     e1.record()
     barrier()
@@ -377,26 +381,38 @@ def run_train(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
+    if rank != 0:
+        return None
+    flop_per_slice = 1013.3e9  # 10 critic updates + 10 evals + 1 G update
+    return {
+        "metric": "DEP-GAN train steps/sec (generator iterations: 5+5 critic updates, 10 noise evals, 1 G update)",
+        "value": steps / (ms * 1e-3), "unit": "gen-iterations/s", "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "data": "synthetic",
+        "config": {"workload": "DEP-GAN %s two-critic training, random init, batch %d per GPU, global batch %d "
+                               "(BASELINE configs[%s])" % ("PROB+FLAIR" if nicg == 2 else "IM", B, B * world,
+                                                           "3" if nicg == 2 else "2"),
+                   "precision": args.precision,
+                   "parallelism": "data parallel over %d GPU(s): NCCL all-reduce of the flat gradient bucket + "
+                                  "loss partial sums" % world,
+                   "l2": "per-step working set >> 126 MB L2; no explicit flush"},
+        "slices_per_s": steps * B * world / (ms * 1e-3),
+        "tflops_effective": steps * B * world * flop_per_slice / (ms * 1e-3) / 1e12,
+        "last_losses": [float(v) for v in out.cpu().numpy()],
+        "clocks": clocks, "gpu_launches": int(launches), "conv_time_per_iteration": prof,
+    }
+
+
+def run_train(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    line = measure_train(args, rank, world, dev, args.steps, args.warmup, args.workload)
     if rank == 0:
-        flop_per_slice = 1013.3e9  # 10 critic updates + 10 evals + 1 G update
-        line = {
-            "metric": "DEP-GAN train steps/sec (generator iterations: 5+5 critic updates, 10 noise evals, 1 G update)",
-            "value": args.steps / (ms * 1e-3), "unit": "gen-iterations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
-            "data": "synthetic",
-            "config": {"workload": "DEP-GAN %s two-critic training, random init, batch %d per GPU, global batch %d "
-                                   "(BASELINE configs[%s])" % ("PROB+FLAIR" if nicg == 2 else "IM", B, B * world,
-                                                               "3" if nicg == 2 else "2"),
-                       "precision": args.precision,
-                       "parallelism": "data parallel over %d GPU(s): NCCL all-reduce of the flat gradient bucket + "
-                                      "loss partial sums" % world,
-                       "l2": "per-step working set >> 126 MB L2; no explicit flush"},
-            "slices_per_s": args.steps * B * world / (ms * 1e-3),
-            "tflops_effective": args.steps * B * world * flop_per_slice / (ms * 1e-3) / 1e12,
-            "last_losses": [float(v) for v in out.cpu().numpy()],
-            "clocks": clocks, "gpu_launches": int(launches), "conv_time_per_iteration": prof,
-        }
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -413,12 +429,16 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-train", action="store_true", help="skip the DEP-GAN train-step leg of the default run")
+    ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the train-step leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.workload.startswith("depgan_train"):
+        if args.batch:
+            args.train_batch = args.batch
         run_train(args, rank, world, local_rank)
         return
     w = WORKLOADS[args.workload]

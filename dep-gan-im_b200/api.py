@@ -181,8 +181,9 @@ class Gen_UNet2D(_Net):
         if tuple(noiseZ_shape)[1:] != (1,):
             raise ValueError("noiseZ_shape must be (L, 1)")
         h, w, nicg = input_shape
+        tmode = 2 if training in ("fit", 2) else int(bool(training))
         cfg = _lib.Cfg(int(h), int(w), int(nicg), int(nc_out), int(noiseZ_shape[0]), int(max_batch), _prec(precision),
-                       int(bool(training)))
+                       tmode)
         self.input_shape, self.noiseZ_shape, self.nc_out = tuple(input_shape), tuple(noiseZ_shape), int(nc_out)
         super().__init__(_lib.MODEL_GEN, cfg, device, seed)
 
@@ -200,6 +201,81 @@ class Gen_UNet2D(_Net):
             _lib.check(_lib.lib().depgan_gen_forward(self.handle, x.data_ptr(), z.data_ptr(), out.data_ptr(), n,
                                                      _stream(torch)), "gen_forward")
         return out
+
+    # ---- DEP-UResNet supervised training: my_network.fit(...) TU:602-606 (model compiled at TU:427) ----------
+    def train_on_batch_device(self, x, z, onehot, keep):
+        """One Keras training-phase step on CUDA tensors (x (n,H,W,1) f32, z (n,L,1) f32, onehot (n,H,W,nc) f32,
+        keep (n,H/4,W/4,96) uint8 Dropout keep mask).  Gradients + Adam(1e-4, 0.9, 0.999); returns the loss tensor."""
+        torch = self._torch
+        if self.cfg.training != 2:
+            raise ValueError("create the model with training='fit' to use fit / train_on_batch")
+        n = int(x.shape[0])
+        if not hasattr(self, "_loss"):
+            self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_uresnet_grads(self.handle, x.data_ptr(), z.data_ptr(), onehot.data_ptr(),
+                                                       keep.data_ptr(), self._loss.data_ptr(), n, _stream(torch)),
+                       "uresnet_grads")
+        loss = self._loss.clone()
+        self.adam_step(1e-4, 0.9, 0.999)  # keras.optimizers.Adam(lr=1e-4) defaults (TU:427)
+        return loss
+
+    def evaluate_loss(self, x, z, onehot, batch_size=16):
+        """Mean categorical cross-entropy in inference mode (Keras validation_data handling, TU:606)."""
+        torch = self._torch
+        n = x.shape[0]
+        tot = torch.zeros(1, dtype=torch.float32, device=self.device)
+        npix_total = float(n * self.cfg.H * self.cfg.W)
+        for i in range(0, n, batch_size):
+            xb = torch.from_numpy(np.ascontiguousarray(x[i:i + batch_size], np.float32)).to(self.device)
+            zb = torch.from_numpy(np.ascontiguousarray(z[i:i + batch_size], np.float32)).to(self.device)
+            tb = torch.from_numpy(np.ascontiguousarray(onehot[i:i + batch_size], np.float32)).to(self.device)
+            prob = self.forward_device(xb, zb)
+            scratch = torch.empty_like(prob)
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().depgan_cce_loss(prob.data_ptr(), tb.data_ptr(), scratch.data_ptr(),
+                                                      tot.data_ptr(), prob.numel() // self.nc_out, self.nc_out,
+                                                      1.0 / npix_total, _stream(torch)), "cce_loss")
+        return float(tot.item())
+
+    def fit(self, inputs, onehot, epochs=1, batch_size=16, shuffle=True, validation_data=None, seed=0, verbose=0):
+        """Keras ``Model.fit([x, z], y, epochs, batch_size, shuffle, validation_data)`` (TU:602-606).  Returns an
+        object with ``.history = {"loss": [...], "val_loss": [...]}`` (one entry per epoch; the epoch loss is the
+        sample-weighted mean of the batch losses, as Keras reports).  The shuffle order and the Dropout keep masks
+        come from ``numpy.random.default_rng(seed)`` (the reference draws both unseeded)."""
+        torch = self._torch
+        x, z = inputs
+        x = np.ascontiguousarray(x, np.float32)
+        z = np.ascontiguousarray(z, np.float32)
+        y = np.ascontiguousarray(onehot, np.float32)
+        n = x.shape[0]
+        rng = np.random.default_rng(seed)
+        hist = {"loss": [], "val_loss": []}
+        bs = min(int(batch_size), self.cfg.max_batch)
+        for _ in range(int(epochs)):
+            order = rng.permutation(n) if shuffle else np.arange(n)
+            tot, cnt = 0.0, 0
+            for i in range(0, n, bs):
+                idx = order[i:i + bs]
+                if len(idx) < 2:
+                    continue  # batch statistics need at least two samples
+                keep = (rng.uniform(size=(len(idx), self.cfg.H // 4, self.cfg.W // 4, 96)) >= 0.25).astype(np.uint8)
+                loss = self.train_on_batch_device(torch.from_numpy(x[idx]).to(self.device),
+                                                  torch.from_numpy(z[idx]).to(self.device),
+                                                  torch.from_numpy(y[idx]).to(self.device),
+                                                  torch.from_numpy(keep).to(self.device))
+                tot += float(loss.item()) * len(idx)
+                cnt += len(idx)
+            hist["loss"].append(tot / max(cnt, 1))
+            if validation_data is not None:
+                (xv, zv), yv = validation_data
+                hist["val_loss"].append(self.evaluate_loss(xv, zv, yv, bs))
+
+        class History:
+            pass
+        h = History()
+        h.history = hist
+        return h
 
     def predict(self, inputs, batch_size=32, verbose=0):
         """Keras ``model.predict([x, z])`` (EG:621, EU:558): numpy in, numpy float32 out, inference mode."""

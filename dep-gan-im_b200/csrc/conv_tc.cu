@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_off - raw));
   float* s_shift = s_scale + g.ncols_total;
   float4* s_head = reinterpret_cast<float4*>(s_shift + g.ncols_total);  // [Cout] x (up to 4 head outputs)
+  // FiLM folded with BN per (sample, channel): [2 slots][2][ncta] floats, rebuilt per work item by the epilogue warps
+  float* s_film = reinterpret_cast<float*>(s_head + a.Cout);
 
   // warp index made provably warp-uniform so the role loops run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -388,15 +390,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int h = th * 16 + ty, w = tw * 16 + tx, n0 = ns * g.ncta;
       const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
       const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
+      // ---- everything that does not need the accumulator is issued BEFORE waiting for it ----
+      const size_t pix0 = ((size_t)n * a.H + h) * a.W + w;
+      float* sF = s_film + (k_it & 1) * 2 * g.ncta;
+      Packed16 rs_next;
+      if (a.film_g) {
+        // FiLM folded into the BN affine for this item's sample: v = relu(acc*(s*g) + (t*g + b)) + res
+        for (int c = ew * 32 + lane; c < g.ncta; c += 256) {
+          const float fgv = __ldg(a.film_g + (size_t)n * a.film_stride + n0 + c);
+          const float fbv = __ldg(a.film_b + (size_t)n * a.film_stride + n0 + c);
+          sF[c] = s_scale[n0 + c] * fgv;
+          sF[g.ncta + c] = fmaf(s_shift[n0 + c], fgv, fbv);
+        }
+        rs_next.load(a.res, pix0 * Cout + n0);
+        // all 8 epilogue warps: the slot is complete (and nobody still reads the other use of it)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(accFull + 8 * as, use & 1u);
       tc_fence_after();
       const uint32_t t_row = tmem_base + as * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(strip * g.ncta);
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const int nj = g.ncta / 16;
 #pragma unroll 1
-      for (int j = 0; j < g.ncta / 16; ++j) {
+      for (int j = 0; j < nj; ++j) {
         const int col = n0 + j * 16;
         int c0 = col;
-        size_t opix = ((size_t)n * a.H + h) * a.W + w;
+        size_t opix = pix0;
         if (a.deconv) {
           const int ab = col / Cout;
           c0 = col - ab * Cout;
@@ -404,30 +423,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         const size_t off = opix * Cout + c0;
         // issue the global reads of this chunk before waiting on tensor memory
-        float fg[16], fb[16];
         Packed16 rs, ad, mk;  // bf16 x 16, unpacked at use (keeps the prefetch cheap in registers)
         if (a.film_g) {
-          ld16_f32(a.film_g + (size_t)n * a.film_stride + c0, fg);
-          ld16_f32(a.film_b + (size_t)n * a.film_stride + c0, fb);
-          rs.load(a.res, off);
+          rs = rs_next;
+          if (j + 1 < nj) rs_next.load(a.res, off + 16);  // next chunk's residual while this one is processed
         }
         if (a.add_src) ad.load(a.add_src, off);
         if (a.mask_src) mk.load(a.mask_src, off);
         float v[16];
         tc_ld16(t_row + (uint32_t)(j * 16), v);
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const float4 sc = reinterpret_cast<const float4*>(s_scale + col)[i4];
-          const float4 sh = reinterpret_cast<const float4*>(s_shift + col)[i4];
-          v[4 * i4 + 0] = fmaf(v[4 * i4 + 0], sc.x, sh.x);
-          v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc.y, sh.y);
-          v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
-          v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
-        }
-        if (a.out_pre) st16_bf16(a.out_pre, off, v);
         if (a.film_g) {
+          if (a.out_pre) {
+            float vp[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(fmaf(v[i], fg[i], fb[i]), 0.f) + rs.get(i);
+            for (int i = 0; i < 16; ++i) vp[i] = fmaf(v[i], s_scale[col + i], s_shift[col + i]);
+            st16_bf16(a.out_pre, off, vp);
+          }
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 sc = reinterpret_cast<const float4*>(sF + j * 16)[i4];
+            const float4 sh = reinterpret_cast<const float4*>(sF + g.ncta + j * 16)[i4];
+            v[4 * i4 + 0] = fmaxf(fmaf(v[4 * i4 + 0], sc.x, sh.x), 0.f) + rs.get(4 * i4 + 0);
+            v[4 * i4 + 1] = fmaxf(fmaf(v[4 * i4 + 1], sc.y, sh.y), 0.f) + rs.get(4 * i4 + 1);
+            v[4 * i4 + 2] = fmaxf(fmaf(v[4 * i4 + 2], sc.z, sh.z), 0.f) + rs.get(4 * i4 + 2);
+            v[4 * i4 + 3] = fmaxf(fmaf(v[4 * i4 + 3], sc.w, sh.w), 0.f) + rs.get(4 * i4 + 3);
+          }
+        } else {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 sc = reinterpret_cast<const float4*>(s_scale + col)[i4];
+            const float4 sh = reinterpret_cast<const float4*>(s_shift + col)[i4];
+            v[4 * i4 + 0] = fmaf(v[4 * i4 + 0], sc.x, sh.x);
+            v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc.y, sh.y);
+            v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
+            v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
+          }
+          if (a.out_pre) st16_bf16(a.out_pre, off, v);
         }
         if (a.add_src) {
 #pragma unroll
@@ -549,7 +580,7 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   const int acc_stages = 4 * ncta <= 512 ? 2 : 1;
   int tmem_cols = 32;
   while (tmem_cols < 2 * ncta * acc_stages) tmem_cols *= 2;
-  const uint32_t fixed = 1024 + 8 * 64 + 64 + 2 * ncols * 4 + 16 * a.Cout + 64;
+  const uint32_t fixed = 1024 + 8 * 64 + 64 + 2 * ncols * 4 + 16 * a.Cout + 16 * ncta + 64;
   for (int kc = 64; kc >= 16; kc /= 2) {
     if (a.C0 % kc || a.C1 % kc) continue;
     const int nchunks = (a.C0 + a.C1) / kc;
@@ -579,7 +610,7 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
     g->a_tx = (uint32_t)ht * ht * kc * 2; g->b_tx = (uint32_t)ncta * kc * 2;
     g->layout = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
     g->b_resident = resident; g->acc_stages = acc_stages;
-    *smem_bytes = 1024 + na * a_bytes + nb * b_bytes + 8 * (2 * na + 2 * nb + 4) + 16 + 2 * ncols * 4 + 16 * a.Cout + 64;
+    *smem_bytes = 1024 + na * a_bytes + nb * b_bytes + 8 * (2 * na + 2 * nb + 4) + 16 + 2 * ncols * 4 + 16 * a.Cout + 16 * ncta + 64;
     return true;
   }
   return false;
@@ -621,6 +652,7 @@ bool conv_tc_supported(const ConvArgs& a) {
   if (a.C1 > 0 && !a.in1) return false;
   if (!a.w_tc) return false;
   if (a.head_w && (a.deconv || a.Cout > 256 || a.head_nc > 4)) return false;
+  if (a.film_g && a.deconv) return false;
   TcGeom g;
   uint32_t smem;
   return plan(a, &g, &smem);

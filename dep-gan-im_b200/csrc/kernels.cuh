@@ -15,7 +15,7 @@ int k_pack_conv_weights(const float* src, const float* scale, bf16* dst_tc, floa
 int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt, cudaStream_t st);
 // Conv2DTranspose k2 s2 'valid' + folded BN + ReLU (TG:307-312).  w: Keras (2,2,Cout,Cin) fp32.
 int k_deconv_fwd(const void* in, const float* w, const float* scale, const float* shift, void* out, int N, int H,
-                 int W, int Cin, int Cout, int dt, cudaStream_t st);
+                 int W, int Cin, int Cout, int dt, int relu, cudaStream_t st);
 // 1x1 conv (Cin -> nc_out<=4) + tanh / softmax, fp32 output (TG:494-495, TU:423-424). seg_out optional (pre-act)
 int k_head_fwd(const void* in, const float* w, const float* b, float* out, long long npix, int Cin, int nc_out,
                int head, int dt, cudaStream_t st);
@@ -95,3 +95,26 @@ int k_critic_loss_finalize(float* out4, float delta, cudaStream_t st);
 int k_scores_to_sums(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw, cudaStream_t st);
 int k_pack_deconv_dgrad(const float* src, const float* scale, float* dst_f32, bf16* dst_bf16, int Cin, int Cout,
                         cudaStream_t st);
+
+// ---- training-phase BatchNorm / Dropout / softmax-CCE / dense helpers (kernels_bn.cu) ----------------------
+int k_bn_stats(const void* x, long long rows, int C, double* sums_scratch, float* mean, float* inv_std, float* mov_mean,
+               float* mov_var, float momentum, int dt, cudaStream_t st);
+int k_bn_apply(const void* x, const float* mean, const float* inv_std, const float* gamma, const float* beta, void* out,
+               void* y_out, long long rows, int C, int relu, const float* fg, const float* fb, int fstride,
+               long long rows_per_sample, const void* res, const unsigned char* keep, float keep_scale, int dt,
+               cudaStream_t st);
+int k_bn_bwd(const void* dy, const void* x, const void* relu_out, const float* mean, const float* inv_std,
+             const float* gamma, float* red_scratch, void* dx, float* dgamma, float* dbeta, long long rows, int C,
+             int dt, cudaStream_t st);
+int k_dropout_bwd(const void* dy, const unsigned char* keep, float scale, void* dx, long long total, int dt,
+                  cudaStream_t st);
+int k_dense_fwd(const float* X, const float* W, const float* b, float* Y, int rows, int K, int C, cudaStream_t st);
+int k_dense_bwd_w(const float* X, const float* dY, float* G, float* db, int rows, int K, int C, cudaStream_t st);
+int k_dense_bwd_x(const float* dY, int ystride, int yoff, const float* W, float* dX, int rows, int K, int C,
+                  int accumulate, cudaStream_t st);
+int k_strided_copy(const float* src, int sstride, int soff, float* dst, int dstride, int doff, int rows, int C,
+                   cudaStream_t st);
+int k_softmax_cce(const float* prob, const float* target, float* dseg, float* loss, long long npix, int nc,
+                  float inv_total, cudaStream_t st);
+int k_head_bwd_multi(const float* dseg, const void* o, const float* w, void* d_o, float* d_w, float* d_b,
+                     long long npix, int C, int nc, int dt, cudaStream_t st);

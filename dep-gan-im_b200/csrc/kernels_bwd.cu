@@ -351,7 +351,7 @@ __global__ void s2d_mask_kernel(const T* d_up, int dstride, const T* up, T* out,
     const int w = p % W, h = (p / W) % H;
     const size_t n = p / ((size_t)W * H);
     const size_t op = (n * 2 * H + 2 * h + (ab >> 1)) * (2 * (size_t)W) + 2 * w + (ab & 1);
-    const float m = ldf(up + op * C + c);
+    const float m = up ? ldf(up + op * C + c) : 1.f;
     stf(out + i, m > 0.f ? ldf(d_up + op * dstride + c) : 0.f);
   }
 }

@@ -67,11 +67,36 @@ __global__ void maxpool_fwd_kernel(const T* in, T* out, int N, int H, int W, int
   }
 }
 
+// bf16 max-pool, 8 channels (128 bits) per thread: 4 vector loads, 1 vector store
+__global__ void maxpool_fwd_bf16x8_kernel(const uint4* in, uint4* out, int N, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C8;
+    const size_t p = i / C8;
+    const int wo = p % Wo, ho = (p / Wo) % Ho;
+    const size_t n = p / ((size_t)Wo * Ho);
+    const uint4* b = in + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C8 + c;
+    uint4 q[4] = {__ldg(b), __ldg(b + C8), __ldg(b + (size_t)W * C8), __ldg(b + (size_t)W * C8 + C8)};
+    uint4 r;
+    __nv_bfloat162* rr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat162 a0 = reinterpret_cast<const __nv_bfloat162*>(&q[0])[k];
+      const __nv_bfloat162 a1 = reinterpret_cast<const __nv_bfloat162*>(&q[1])[k];
+      const __nv_bfloat162 a2 = reinterpret_cast<const __nv_bfloat162*>(&q[2])[k];
+      const __nv_bfloat162 a3 = reinterpret_cast<const __nv_bfloat162*>(&q[3])[k];
+      rr[k] = __hmax2(__hmax2(a0, a1), __hmax2(a2, a3));
+    }
+    out[i] = r;
+  }
+}
+
 // Transposed conv k2 s2: one CTA = 16 input pixels; thread o -> output (a,b,co) index, 16 pixel accumulators.
 template <typename T>
 __global__ void __launch_bounds__(128) deconv_fwd_kernel(const T* in, const float* w, const float* scale,
                                                          const float* shift, T* out, int N, int H, int W, int Cin,
-                                                         int Cout) {
+                                                         int Cout, int relu) {
   extern __shared__ float s_x[];  // [16][Cin]
   const size_t npix = (size_t)N * H * W;
   const size_t p0 = (size_t)blockIdx.x * 16;
@@ -91,7 +116,7 @@ __global__ void __launch_bounds__(128) deconv_fwd_kernel(const T* in, const floa
 #pragma unroll
       for (int i = 0; i < 16; ++i) acc[i] = fmaf(s_x[i * Cin + ci], wv, acc[i]);
     }
-    const float s = scale[co], t = shift[co];
+    const float s = scale ? scale[co] : 1.f, t = shift ? shift[co] : 0.f;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
       size_t p = p0 + i;
@@ -100,7 +125,8 @@ __global__ void __launch_bounds__(128) deconv_fwd_kernel(const T* in, const floa
       int hi = (p / W) % H;
       size_t n = p / ((size_t)W * H);
       size_t op = ((n * 2 * H + 2 * hi + (ab >> 1)) * 2 * W + 2 * wi + (ab & 1));
-      stf(out + op * Cout + co, fmaxf(fmaf(acc[i], s, t), 0.f));
+      const float v = fmaf(acc[i], s, t);
+      stf(out + op * Cout + co, relu ? fmaxf(v, 0.f) : v);
     }
   }
 }
@@ -146,10 +172,11 @@ __global__ void film_stage_a_kernel(FilmMlpArgs a) {
 }
 
 // FiLM MLP stage B: out[n, off_h + c] = s_h[c] * sum_k h2[n,k] W_h[k,c] + t_h[c].
-// CTA = 32 columns x 8 samples; 128 threads = 32 columns x 4 k-slices.
-__global__ void __launch_bounds__(128) film_stage_b_kernel(FilmMlpArgs a) {
+// CTA = 32 columns x 8 samples; 512 threads = 32 columns x 16 k-slices.
+constexpr int FILM_KS = 16;
+__global__ void __launch_bounds__(32 * FILM_KS) film_stage_b_kernel(FilmMlpArgs a) {
   extern __shared__ float s_h2[];  // [8][K]
-  __shared__ float s_red[4][8][32];
+  __shared__ float s_red[FILM_KS][8][32];
   const int K = a.L * a.F;
   const int col0 = blockIdx.x * 32, n0 = blockIdx.y * 8;
   int h = 0;
@@ -166,7 +193,7 @@ __global__ void __launch_bounds__(128) film_stage_b_kernel(FilmMlpArgs a) {
   float acc[8];
 #pragma unroll
   for (int s = 0; s < 8; ++s) acc[s] = 0.f;
-  const int kpart = (K + 3) / 4;
+  const int kpart = (K + FILM_KS - 1) / FILM_KS;
   const int k_end = min(K, (kq + 1) * kpart);
   for (int k = kq * kpart; k < k_end; ++k) {
     const float wv = W[(size_t)k * C + cl0 + cx];
@@ -179,7 +206,9 @@ __global__ void __launch_bounds__(128) film_stage_b_kernel(FilmMlpArgs a) {
   for (int idx = threadIdx.x; idx < 8 * 32; idx += blockDim.x) {
     int s = idx >> 5, c = idx & 31;
     if (n0 + s >= a.N) continue;
-    float v = s_red[0][s][c] + s_red[1][s][c] + s_red[2][s][c] + s_red[3][s][c];
+    float v = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < FILM_KS; ++kk) v += s_red[kk][s][c];
     a.out[(size_t)(n0 + s) * a.total_c + col0 + c] = fmaf(v, a.head_s[h][cl0 + c], a.head_t[h][cl0 + c]);
   }
 }
@@ -336,6 +365,9 @@ int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt,
   if (total == 0) return 0;
   if (dt == DT_F32)
     maxpool_fwd_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)in, (float*)out, N, H, W, C);
+  else if (C % 8 == 0)
+    maxpool_fwd_bf16x8_kernel<<<grid_for(total / 8, 256, 148 * 32), 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W,
+                                                                                 C / 8);
   else
     maxpool_fwd_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)in, (bf16*)out, N, H, W, C);
   DG_LAUNCH_CHECK();
@@ -343,15 +375,17 @@ int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt,
 }
 
 int k_deconv_fwd(const void* in, const float* w, const float* scale, const float* shift, void* out, int N, int H,
-                 int W, int Cin, int Cout, int dt, cudaStream_t st) {
+                 int W, int Cin, int Cout, int dt, int relu, cudaStream_t st) {
   long long npix = (long long)N * H * W;
   if (npix == 0) return 0;
   int grid = (int)((npix + 15) / 16);
   size_t smem = 16 * Cin * sizeof(float);
   if (dt == DT_F32)
-    deconv_fwd_kernel<float><<<grid, 128, smem, st>>>((const float*)in, w, scale, shift, (float*)out, N, H, W, Cin, Cout);
+    deconv_fwd_kernel<float><<<grid, 128, smem, st>>>((const float*)in, w, scale, shift, (float*)out, N, H, W, Cin, Cout,
+                                                      relu);
   else
-    deconv_fwd_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)in, w, scale, shift, (bf16*)out, N, H, W, Cin, Cout);
+    deconv_fwd_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)in, w, scale, shift, (bf16*)out, N, H, W, Cin, Cout,
+                                                     relu);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -376,7 +410,7 @@ int k_film_mlp_fwd(const FilmMlpArgs& a, cudaStream_t st) {
   film_stage_a_kernel<<<a.N, a.L * a.F, a.L * a.F * sizeof(float), st>>>(a);
   DG_LAUNCH_CHECK();
   dim3 grid(a.total_c / 32, (a.N + 7) / 8);
-  film_stage_b_kernel<<<grid, 128, 8 * a.L * a.F * sizeof(float), st>>>(a);
+  film_stage_b_kernel<<<grid, 32 * FILM_KS, 8 * a.L * a.F * sizeof(float), st>>>(a);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -252,9 +252,12 @@ int fold_conv(depgan_net* h, ConvL& L, cudaStream_t st) {
                    L.inv_std, L.cout, st));
   if (L.deconv) {
     if (L.w_tc) DG_TRY(k_convert_in(h->P(L.k_off), L.w_tc, (long long)4 * L.cin * L.cout, DT_BF16, st));
-    DG_TRY(k_pack_deconv_dgrad(h->P(L.k_off), L.scale, L.w_dg, L.w_dg_tc, L.cin, L.cout, st));
+    DG_TRY(k_pack_deconv_dgrad(h->P(L.k_off), h->cfg.training == 2 ? nullptr : L.scale, L.w_dg, L.w_dg_tc, L.cin,
+                               L.cout, st));
   } else {
-    DG_TRY(k_pack_conv_weights(h->P(L.k_off), L.scale, L.w_tc, L.w_dg, L.w_dg_tc, L.ks * L.ks, L.cin, L.cout, st));
+    // training == 2 (Keras training phase): BN is applied after the raw convolution, so dgrad weights stay unscaled
+    DG_TRY(k_pack_conv_weights(h->P(L.k_off), h->cfg.training == 2 ? nullptr : L.scale, L.w_tc, L.w_dg, L.w_dg_tc,
+                               L.ks * L.ks, L.cin, L.cout, st));
   }
   return 0;
 }
@@ -338,7 +341,7 @@ static int net_deconv(depgan_net* h, const ConvL& L, const void* in, void* out, 
       return conv_fwd_tc(a, st);
     }
   }
-  return k_deconv_fwd(in, h->P(L.k_off), L.scale, L.shift, out, n, H, W, L.cin, L.cout, h->act_dt, st);
+  return k_deconv_fwd(in, h->P(L.k_off), L.scale, L.shift, out, n, H, W, L.cin, L.cout, h->act_dt, 1, st);
 }
 
 int gen_forward_impl(depgan_net* g, const float* x, const float* z, float* out, int n, bool keep, cudaStream_t st) {

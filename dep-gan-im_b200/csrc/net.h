@@ -119,6 +119,38 @@ static const char* const GEN_OUT[7] = {"gen_1", "gen_3", "gen_5", "gen_9", "gen_
 static const char* const GEN_SUF[7] = {"_m1", "_m2", "_m3", "", "_p3", "_p2", "_p1"};
 static const char* const GEN_DEC[3] = {"de_gen_9", "de_gen_11", "de_gen_15"};
 
+struct BnState { float* mean = nullptr; float* inv_std = nullptr; };  // batch statistics of one BN layer
+
+struct Train {
+  // shared scratch
+  float* sum_dy = nullptr;  // [2048]
+  float* g_raw = nullptr;   // raw weight gradient of a transposed conv [Cin][4*Cout]
+  // ---- critic ----
+  void* b[11] = {};   // pre-activation gradients of every conv, all rows
+  void* bp[4] = {};   // gradients at pooled resolution
+  void* v[11] = {};   // JVP activations (penalty rows only)
+  void* vp[4] = {};
+  float* go = nullptr;      // per-row output gradient
+  float* batch3 = nullptr;  // [real | fake | mixed] critic inputs, fp32 (3n,H,W,1)
+  float* g_in = nullptr;    // dD/dx, fp32 (rows,H,W,1)
+  float* u = nullptr;       // JVP input (penalty rows)
+  // ---- generator ----
+  void* d_o[7] = {};
+  void *d_r = nullptr, *d_y = nullptr, *b_in = nullptr, *d_in = nullptr, *s2d = nullptr;
+  float *d_film = nullptr, *d_h2 = nullptr, *sum_d = nullptr, *sum_d1 = nullptr, *sum_d0 = nullptr;
+  float** dev_dw_heads = nullptr;
+  float *fake2 = nullptr, *l1g = nullptr;
+  double* sums = nullptr;
+  bool heads_uploaded = false;
+  // ---- Keras training phase (cfg.training == 2, DEP-UResNet fit) ----
+  BnState bn_in[7], bn_no[7], bn_out[7], bn_dec[3], bn_f0, bn_f1, bn_head[14];
+  void *raw_a[7] = {}, *raw_y[7] = {}, *raw_o[7] = {}, *raw_up[7] = {}, *tmp_up = nullptr;
+  float *pre0 = nullptr, *pre1 = nullptr, *d_h1 = nullptr, *d_pre = nullptr, *raw_head[14] = {};
+  float *tmp_c1 = nullptr, *tmp_c2 = nullptr, *dseg = nullptr, *bn_red = nullptr;
+  double* bn_sums = nullptr;
+};
+
+
 // per-launch timing records (bench.py roofline leg; see depgan_profile_begin/end)
 struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; int ks, H, W, cin, cout, n; };
 struct ProfScope {

@@ -14,29 +14,6 @@
 // forward sweep of D_lin on u (a JVP).  Regular rows and penalty rows therefore share one wgrad per layer.
 #include "net.h"
 
-struct Train {
-  // shared scratch
-  float* sum_dy = nullptr;  // [2048]
-  float* g_raw = nullptr;   // raw weight gradient of a transposed conv [Cin][4*Cout]
-  // ---- critic ----
-  void* b[11] = {};   // pre-activation gradients of every conv, all rows
-  void* bp[4] = {};   // gradients at pooled resolution
-  void* v[11] = {};   // JVP activations (penalty rows only)
-  void* vp[4] = {};
-  float* go = nullptr;      // per-row output gradient
-  float* batch3 = nullptr;  // [real | fake | mixed] critic inputs, fp32 (3n,H,W,1)
-  float* g_in = nullptr;    // dD/dx, fp32 (rows,H,W,1)
-  float* u = nullptr;       // JVP input (penalty rows)
-  // ---- generator ----
-  void* d_o[7] = {};
-  void *d_r = nullptr, *d_y = nullptr, *b_in = nullptr, *d_in = nullptr, *s2d = nullptr;
-  float *d_film = nullptr, *d_h2 = nullptr, *sum_d = nullptr, *sum_d1 = nullptr, *sum_d0 = nullptr;
-  float** dev_dw_heads = nullptr;
-  float *fake2 = nullptr, *l1g = nullptr;
-  double* sums = nullptr;
-  bool heads_uploaded = false;
-};
-
 int train_alloc(depgan_net* h, Bump& bm) {
   Train* t = nullptr;
   if (bm.base) {
@@ -94,6 +71,35 @@ int train_alloc(depgan_net* h, Bump& bm) {
     T.fake2 = bm.arr<float>(NB * HW);
     T.l1g = bm.arr<float>(NB * HW);
     T.sums = bm.arr<double>(8);
+    if (c.training == 2) {  // Keras training phase (DEP-UResNet fit): pre-BN tensors and batch statistics
+      auto bn = [&](BnState& s, int C) { s.mean = bm.arr<float>(C); s.inv_std = bm.arr<float>(C); };
+      for (int bi = 0; bi < 7; ++bi) {
+        const int w = FIRST_FM * GEN_MULT[bi], lvl = GEN_LVL[bi];
+        const size_t px = NB * h->lvl_h(lvl) * h->lvl_w(lvl);
+        T.raw_a[bi] = bm.take(px * w * es);
+        T.raw_y[bi] = bm.take(px * w * es);
+        T.raw_o[bi] = bm.take(px * w * es);
+        bn(T.bn_in[bi], w); bn(T.bn_no[bi], w); bn(T.bn_out[bi], w);
+        if (bi >= 3 && bi < 6) { T.raw_up[bi] = bm.take(px * 4 * w * es); bn(T.bn_dec[bi - 3], w); }
+      }
+      T.tmp_up = bm.take(NB * HW * 64 * es);
+      const size_t LF = (size_t)c.noise_len * FIRST_FM;
+      T.pre0 = bm.arr<float>(NB * LF);
+      T.pre1 = bm.arr<float>(NB * LF);
+      T.d_h1 = bm.arr<float>(NB * LF);
+      T.d_pre = bm.arr<float>(NB * LF);
+      bn(T.bn_f0, FIRST_FM); bn(T.bn_f1, FIRST_FM);
+      for (int i = 0; i < 14; ++i) {
+        const int C = FIRST_FM * GEN_MULT[i / 2];
+        T.raw_head[i] = bm.arr<float>(NB * C);
+        bn(T.bn_head[i], C);
+      }
+      T.tmp_c1 = bm.arr<float>(NB * 256);
+      T.tmp_c2 = bm.arr<float>(NB * 256);
+      T.dseg = bm.arr<float>(NB * HW * 4);
+      T.bn_sums = bm.arr<double>(2 * 512);
+      T.bn_red = bm.arr<float>(2 * 512);
+    }
   }
   return 0;
 }

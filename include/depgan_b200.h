@@ -36,7 +36,8 @@ typedef struct depgan_cfg {
   int noise_len;  /* noiseSize TG:41 (32) */
   int max_batch;  /* workspace is sized for this many slices per call */
   int precision;  /* DEPGAN_PREC_* */
-  int training;   /* 1: also reserve backward / double-backward buffers */
+  int training;   /* 0: inference; 1: DEP-GAN train graphs (learning phase 0);
+                     2: Keras training phase (batch-statistic BN + Dropout) for the DEP-UResNet fit path */
 } depgan_cfg;
 
 typedef struct depgan_net depgan_net; /* opaque: one generator or one critic */
@@ -86,6 +87,19 @@ int depgan_gen_grads(depgan_net* g, depgan_net* dy2, depgan_net* ddem, const flo
                      void* stream);
 /* Final generator-loss terms from (possibly all-reduced) partial sums: out6 = combine(partials). */
 int depgan_gen_loss_finalize(float* out6_dev, const double* sums_dev, void* stream);
+
+/* ---- DEP-UResNet supervised step: my_network.fit(...) TU:602-606 on the model compiled at TU:427 ----
+ * Keras *training* phase: BatchNormalization uses (and back-propagates through) the statistics of the batch and
+ * refreshes moving_mean / moving_variance in the parameter buffer (momentum 0.99, Bessel-corrected variance);
+ * Dropout(0.25) `do_gen_1` after conv2d_gen_10 (TU:388) uses the caller's keep mask (n, H/4, W/4, 96) of 0/1 bytes;
+ * loss = mean categorical cross-entropy of the softmax output vs onehot (n,H,W,nc_out), written to loss_dev; the
+ * gradient of every trainable tensor is left in the gradient buffer (apply depgan_adam_step with Keras' defaults
+ * lr 1e-4, beta_1 0.9, beta_2 0.999, then depgan_net_prepare).  The handle must be created with cfg.training = 2.
+ * depgan_cce_loss: the same loss for a given softmax output (validation, TU:606); dseg_scratch: npix*nc floats. */
+int depgan_uresnet_grads(depgan_net* g, const float* x_dev, const float* z_dev, const float* onehot_dev,
+                         const unsigned char* drop_keep_dev, float* loss_dev, int n, void* stream);
+int depgan_cce_loss(const float* prob_dev, const float* onehot_dev, float* dseg_scratch_dev, float* loss_dev,
+                    long long npix, int nc, float inv_total, void* stream);
 
 /* Keras-form Adam (keras.optimizers.Adam.get_updates; call sites TG:549,568,594; TU:427):
  * lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m=b1*m+(1-b1)*g; v=b2*v+(1-b2)*g^2; p -= lr_t*m/(sqrt(v)+eps).

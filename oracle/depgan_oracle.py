@@ -432,3 +432,98 @@ def uresnet_labels(prob_mean_f64):
     lab = np.argmax(prob_mean_f64.reshape(-1, prob_mean_f64.shape[-1]), axis=1).astype(np.uint8)
     lab = lab.reshape(prob_mean_f64.shape[:-1])
     return lab, int(np.count_nonzero(lab > 0))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# DEP-UResNet supervised training step (TU:291-428 compile at TU:427, fit at TU:602-606): Keras *training* phase:
+# BatchNormalization normalises with the batch statistics (biased variance) and updates its moving statistics
+# (momentum 0.99, Bessel-corrected batch variance), Dropout(0.25) `do_gen_1` after conv2d_gen_10 (TU:388), loss =
+# keras.losses.categorical_crossentropy on the softmax output, optimizer Adam(lr=1e-4) with Keras defaults
+# beta_1=0.9, beta_2=0.999.  The Dropout mask is an explicit input (the reference draws it inside TF, unseeded).
+# ----------------------------------------------------------------------------------------------------------
+BN_MOMENTUM = 0.99
+DROP_RATE = 0.25
+
+
+def _bn_train(P, name, x, channel_dim, stats):
+    g, b = P[name + "/gamma"], P[name + "/beta"]
+    dims = [d for d in range(x.dim()) if d != channel_dim]
+    mean = x.mean(dim=dims)
+    var = x.var(dim=dims, unbiased=False)
+    m = x.numel() // x.shape[channel_dim]
+    stats[name] = (mean.detach(), (var * m / max(m - 1, 1)).detach())
+    shape = [1] * x.dim()
+    shape[channel_dim] = -1
+    return (x - mean.view(shape)) * torch.rsqrt(var.view(shape) + BN_EPS) * g.view(shape) + b.view(shape)
+
+
+def film_params_train(P, z, stats):
+    h = z @ P["dense_noise_1_add_f0/kernel"] + P["dense_noise_1_add_f0/bias"]
+    h = torch.relu(_bn_train(P, "dense_bn_noise_1_add_f0", h, 2, stats))
+    h = h @ P["dense_noise_1_add_f1/kernel"] + P["dense_noise_1_add_f1/bias"]
+    h = torch.relu(_bn_train(P, "dense_bn_noise_1_add_f1", h, 2, stats))
+    h = h.reshape(h.shape[0], -1)
+    out = {}
+    for suf, _ in FILM_HEADS:
+        r = []
+        for kind in ("mul", "add"):
+            n = "noise_2_%s%s" % (kind, suf)
+            v = h @ P["dense_" + n + "/kernel"] + P["dense_" + n + "/bias"]
+            r.append(_bn_train(P, "dense_bn_" + n, v, 1, stats))
+        out[suf] = (r[0], r[1])
+    return out
+
+
+def gen_forward_train(P, x_nhwc, z, drop_mask, head="softmax"):
+    """Gen_UNet2D (DEP-UResNet variant: a single Dropout, TU:388) in Keras training phase.
+    drop_mask: (N, H/4, W/4, 96) of {0,1} keep flags for `do_gen_1`; kept values are scaled by 1/(1-rate).
+    Returns (output NHWC, stats dict layer -> (batch mean, unbiased batch variance))."""
+    stats = {}
+    film = film_params_train(P, z, stats)
+    x = x_nhwc.permute(0, 3, 1, 2)
+    skips = []
+    for bi, (c_in, c_noise, c_out, suf, mult) in enumerate(GEN_BLOCKS):
+        a = torch.relu(_bn_train(P, "bn_" + c_in, _conv(P, "conv2d_" + c_in, x, 1), 1, stats))
+        if c_in == "gen_10":
+            a = a * drop_mask.permute(0, 3, 1, 2) / (1.0 - DROP_RATE)
+        y = _bn_train(P, "bn_" + c_noise, _conv(P, "conv2d_" + c_noise, a, 1), 1, stats)
+        gam, bet = film[suf]
+        r = torch.relu(y * gam[:, :, None, None] + bet[:, :, None, None]) + a
+        o = torch.relu(_bn_train(P, "bn_" + c_out, _conv(P, "conv2d_" + c_out, r, 1), 1, stats))
+        if bi < 3:
+            skips.append(o)
+            x = F.max_pool2d(o, 2)
+        elif bi < 6:
+            d = GEN_DECONVS[bi - 3]
+            u = torch.relu(_bn_train(P, "bn_" + d, _deconv(P, "deconv2d_" + d, o), 1, stats))
+            x = torch.cat([u, skips[5 - bi]], dim=1)
+        else:
+            x = o
+    seg = _conv(P, "gen_segmentation", x, 0)
+    out = torch.softmax(seg, dim=1) if head == "softmax" else seg
+    return out.permute(0, 2, 3, 1), stats
+
+
+def categorical_crossentropy(target, output, eps=1e-7):
+    """keras.backend.categorical_crossentropy (TF backend, from_logits=False), mean over N,H,W as Keras' fit reports."""
+    output = output / output.sum(dim=-1, keepdim=True)
+    output = output.clamp(eps, 1.0 - eps)
+    return (-(target * torch.log(output)).sum(dim=-1)).mean()
+
+
+def uresnet_train_step(P, x, z, onehot, drop_mask, opt=None):
+    """One Keras train_on_batch of the compiled DEP-UResNet (TU:427, 602).  P: torch leaves (requires_grad on
+    trainables).  Returns (loss, grads dict, stats); when `opt` (KerasAdam with beta_1=0.9, beta_2=0.999) is given
+    the parameters and the BN moving statistics are updated in place."""
+    out, stats = gen_forward_train(P, x, z, drop_mask)
+    loss = categorical_crossentropy(onehot, out)
+    keys = [k for k in P if P[k].requires_grad]
+    grads = torch.autograd.grad(loss, [P[k] for k in keys], allow_unused=True)
+    gd = {k: (g if g is not None else torch.zeros_like(P[k])) for k, g in zip(keys, grads)}
+    if opt is not None:
+        opt.step(P, gd)
+        with torch.no_grad():
+            for name, (mean, var_unb) in stats.items():
+                P[name + "/moving_mean"].mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * mean)
+                P[name + "/moving_variance"].mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * var_unb)
+    return float(loss.detach()), {k: v.detach() for k, v in gd.items()}, stats
