@@ -18,7 +18,7 @@ import numpy as np
 from . import _lib
 from . import synth
 
-__all__ = ["Gen_UNet2D", "Dis_C2D_FCN1", "conv2d_op", "wgrad_op", "launch_count"]
+__all__ = ["Gen_UNet2D", "Dis_C2D_FCN1", "InferencePipeline", "conv2d_op", "wgrad_op", "launch_count"]
 
 
 def _torch():
@@ -288,11 +288,79 @@ class Gen_UNet2D(_Net):
         n = x.shape[0]
         bs = max(1, min(int(batch_size), self.cfg.max_batch))
         out = np.empty((n, self.cfg.H, self.cfg.W, self.nc_out), np.float32)
+        if n > bs:  # several batches: overlap copies and kernels (results are identical, per-slice independent)
+            if getattr(self, "_pipe", None) is None:
+                self._pipe = InferencePipeline(self)
+            outs = []
+            for i in range(0, n, bs):
+                xh = torch.from_numpy(x[i:i + bs]).pin_memory()
+                zh = torch.from_numpy(z[i:i + bs]).pin_memory()
+                oh = torch.empty((xh.shape[0], self.cfg.H, self.cfg.W, self.nc_out), dtype=torch.float32).pin_memory()
+                self._pipe.submit(xh, zh, oh)
+                outs.append((i, oh))
+            self._pipe.flush()
+            for i, oh in outs:
+                out[i:i + oh.shape[0]] = oh.numpy()
+            return out
         for i in range(0, n, bs):
             xb = torch.from_numpy(x[i:i + bs]).to(self.device, non_blocking=False)
             zb = torch.from_numpy(z[i:i + bs]).to(self.device, non_blocking=False)
             out[i:i + bs] = self.forward_device(xb, zb).cpu().numpy()
         return out
+
+
+class InferencePipeline:
+    """Double-buffered host<->device pipeline around ``Gen_UNet2D.forward_device`` for streams of batches that
+    live in pinned host memory: the H2D copy of batch i+1 and the D2H copy of batch i-1 overlap the kernels of
+    batch i (three CUDA streams, events instead of host synchronisation).
+
+        pipe = InferencePipeline(netG)
+        for xh, zh, oh in batches:            # pinned host tensors; oh receives the prediction
+            pipe.submit(xh, zh, oh)
+        pipe.flush()                          # all outputs are complete in host memory
+    """
+
+    def __init__(self, net, depth=2):
+        torch = net._torch
+        self.net, self.torch, self.depth = net, torch, depth
+        dev, cfg = net.device, net.cfg
+        B = cfg.max_batch
+        with torch.cuda.device(dev):
+            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+            self.x = [torch.empty((B, cfg.H, cfg.W, cfg.nicg), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.z = [torch.empty((B, cfg.noise_len, 1), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.o = [torch.empty((B, cfg.H, cfg.W, net.nc_out), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.i = 0
+
+    def submit(self, xh, zh, oh):
+        torch = self.torch
+        k = self.i % self.depth
+        n = int(xh.shape[0])
+        with torch.cuda.device(self.net.device):
+            with torch.cuda.stream(self.s_in):
+                if self.i >= self.depth:
+                    self.s_in.wait_event(self.ev_run[k])   # the kernels that last read these input buffers
+                self.x[k][:n].copy_(xh, non_blocking=True)
+                self.z[k][:n].copy_(zh, non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[k])
+                if self.i >= self.depth:
+                    self.s_run.wait_event(self.ev_out[k])  # the D2H copy that last read this output buffer
+                self.net.forward_device(self.x[k][:n], self.z[k][:n], self.o[k][:n])
+                self.ev_run[k].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[k])
+                oh.copy_(self.o[k][:n], non_blocking=True)
+                self.ev_out[k].record(self.s_out)
+        self.i += 1
+
+    def flush(self):
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.synchronize()
 
 
 class Dis_C2D_FCN1(_Net):
