@@ -87,7 +87,9 @@ def lib():
     if _lib is not None:
         return _lib
     from . import build as _build
-    path = _build.build()
+    import os
+    # A/B benchmarking hook: an explicitly named build of this same library (never a fallback implementation)
+    path = os.environ.get("DEPGAN_B200_LIB") or _build.build()
     try:
         L = C.CDLL(str(path))
     except OSError as e:  # pragma: no cover

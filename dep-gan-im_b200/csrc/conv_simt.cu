@@ -128,86 +128,185 @@ int launch_fwd(const ConvArgs& a, cudaStream_t st) {
 
 
 // ------------------------------------------------------------------------------------------------------
-// First-layer direct convolution (conv2d_gen_0: nicg -> 32, conv2d_dis_0a: 1 -> 16).  K = ks*ks*Cin <= 25 is
-// far too small for tensor cores; the layer is HBM-bound (4*Cin B in, 2*Cout B out per pixel), so: one thread
-// per pixel, fp32 input halo tile and all weights in shared memory, Cout accumulators in registers, 128-bit
-// vectorised NHWC stores.
+// Edge layers (conv2d_gen_0: nicg -> 32 3x3, conv2d_dis_0a: 1 -> 16 5x5, and the 16 -> 1 data gradient of the
+// latter).  K = ks*ks*Cin <= 25 (or Cout = 1) is far too small for tensor cores and the layers are HBM-bound on
+// their wide side (2*Cout B per pixel), so they run on CUDA cores with everything that is reused held on chip:
+//   * CTA = 8 warps side by side over a band of EDGE_ROWS rows; the narrow operand's halo tile is staged in shared
+//     memory by the whole CTA (bulk coalesced loads, 2-3 CTAs per SM hide the fill).
+//   * G = COUT/CPT lanes share one pixel, each owning CPT channels; a warp covers 32/G horizontally adjacent
+//     pixels, so every wide-side access of a warp is ONE contiguous run of 32*CPT elements.
+//   * the warp walks down its column strip; the ks x ks image window slides vertically in registers (ks new
+//     shared-memory reads per pixel, rotation resolved at compile time by unrolling ks rows).
+//   * forward: the TAPS*CIN*CPT weights of the lane live in registers for the whole strip; weight gradient: the
+//     same number of accumulators does (the roles of weights and accumulators swap), reduced over the warp by
+//     shuffles, over the CTA in shared memory and over CTAs by one atomic per element.
 // ------------------------------------------------------------------------------------------------------
-template <typename TO, int KS, int CIN, int COUT>
-__global__ void __launch_bounds__(256) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
+constexpr int EDGE_ROWS = 32;  // rows per CTA band
+
+template <int N>
+struct VecIO;  // N consecutive channels of one pixel
+template <>
+struct VecIO<2> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[2]) {
+    const uint32_t q = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q));
+    v[0] = a.x; v[1] = a.y;
+  }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[2]) {
+    const float2 q = __ldg(reinterpret_cast<const float2*>(p));
+    v[0] = q.x; v[1] = q.y;
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[2]) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v[0], v[1]);
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[2]) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+  }
+};
+template <>
+struct VecIO<4> {
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[4]) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+    const float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[4]) {
+    uint2 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+    h[0] = __floats2bfloat162_rn(v[0], v[1]);
+    h[1] = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = q;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct VecIO<8> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
+    float lo[4], hi[4];
+    VecIO<4>::load(p, lo);
+    VecIO<4>::load(p + 4, hi);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[i] = lo[i]; v[4 + i] = hi[i]; }
+  }
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
+    uint4 q;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
+    float4* q = reinterpret_cast<float4*>(p);
+    q[0] = make_float4(v[0], v[1], v[2], v[3]);
+    q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+
+// fp32 image halo tile of a band: rows y0-PAD .. y0+EDGE_ROWS+PAD-1, columns x0-PAD .. x0+TILE_W+PAD-1 ('same' zeros)
+template <int KS, int CIN, int TILE_W>
+struct EdgeTile {
+  static constexpr int PAD = KS / 2, TR = EDGE_ROWS + KS - 1, TC = (TILE_W + KS - 1) * CIN;
+  float v[TR][TC];
+  __device__ __forceinline__ void fill(const float* __restrict__ x, int n, int y0, int x0, int H, int W) {
+    for (int i = threadIdx.x; i < TR * TC; i += blockDim.x) {
+      const int r = i / TC, cc = i - r * TC;
+      const int gy = y0 - PAD + r, gx = x0 - PAD + cc / CIN, ci = cc % CIN;
+      v[r][cc] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? __ldg(x + (((size_t)n * H + gy) * W + gx) * CIN + ci) : 0.f;
+    }
+  }
+  // the KS x CIN window row of output column `col` (tile-relative) at tile row r
+  __device__ __forceinline__ void row(int r, int col, float (&out)[KS * CIN]) const {
+#pragma unroll
+    for (int q = 0; q < KS * CIN; ++q) out[q] = v[r][col * CIN + q];
+  }
+};
+
+template <typename TO, int KS, int CIN, int COUT, int CPT>
+__global__ void __launch_bounds__(256, 2) conv_first_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ scale,
                                                          const float* __restrict__ shift, TO* __restrict__ out,
                                                          const TO* __restrict__ mask, int H, int W, int relu) {
-  constexpr int PAD = KS / 2, IT = 16 + KS - 1, TAPS = KS * KS;
-  __shared__ float s_in[IT][IT + 1][CIN];
-  __shared__ __align__(16) float s_w[TAPS * CIN][COUT];
-  __shared__ float s_sc[COUT], s_sh[COUT];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int tiles_w = W / 16;
-  const int w0 = (blockIdx.x % tiles_w) * 16, h0 = (blockIdx.x / tiles_w) * 16, n = blockIdx.y;
-  for (int i = tid; i < TAPS * CIN * COUT; i += 256) (&s_w[0][0])[i] = w[i];
-  for (int i = tid; i < COUT; i += 256) {
-    s_sc[i] = scale ? scale[i] : 1.f;
-    s_sh[i] = shift ? shift[i] : 0.f;
-  }
-  for (int i = tid; i < IT * IT * CIN; i += 256) {
-    const int ci = i % CIN, c = (i / CIN) % IT, r = i / (CIN * IT);
-    const int h = h0 + r - PAD, ww = w0 + c - PAD;
-    s_in[r][c][ci] = (h >= 0 && h < H && ww >= 0 && ww < W) ? x[(((size_t)n * H + h) * W + ww) * CIN + ci] : 0.f;
+  constexpr int TAPS = KS * KS, G = COUT / CPT, PXW = 32 / G, KW = KS * CIN, TILE_W = 8 * PXW;
+  __shared__ EdgeTile<KS, CIN, TILE_W> tile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cg = lane % G, px = lane / G;
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * EDGE_ROWS, n = blockIdx.z;
+  tile.fill(x, n, y0, x0, H, W);
+  const int col = warp * PXW + px, xc = x0 + col, c0 = cg * CPT;
+
+  float wr[TAPS * CIN][CPT], sc[CPT], sh[CPT];
+#pragma unroll
+  for (int t = 0; t < TAPS * CIN; ++t)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) wr[t][c] = __ldg(w + (size_t)t * COUT + c0 + c);
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    sc[c] = scale ? __ldg(scale + c0 + c) : 1.f;
+    sh[c] = shift ? __ldg(shift + c0 + c) : 0.f;
   }
   __syncthreads();
-  float acc[COUT];
+  if (xc >= W) return;
+  // window slot of tile row t: t % KS; tile rows 0 .. KS-2 are preloaded
+  float win[KS][KW];
 #pragma unroll
-  for (int i = 0; i < COUT; ++i) acc[i] = 0.f;
+  for (int d = 0; d < KS - 1; ++d) tile.row(d, col, win[d]);
+  const int rows = min(EDGE_ROWS, H - y0);
+  for (int r0 = 0; r0 < rows; r0 += KS) {
 #pragma unroll
-  for (int tap = 0; tap < TAPS; ++tap) {
+    for (int k = 0; k < KS; ++k) {
+      const int r = r0 + k;
+      if (r < rows) {
+        tile.row(r + KS - 1, col, win[(k + KS - 1) % KS]);
+        float acc[CPT];
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) {
-      const float v = s_in[ty + tap / KS][tx + tap % KS][ci];
-      const float4* wp = reinterpret_cast<const float4*>(&s_w[tap * CIN + ci][0]);
+        for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
 #pragma unroll
-      for (int q = 0; q < COUT / 4; ++q) {
-        const float4 w4 = wp[q];
-        acc[4 * q + 0] = fmaf(v, w4.x, acc[4 * q + 0]);
-        acc[4 * q + 1] = fmaf(v, w4.y, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(v, w4.z, acc[4 * q + 2]);
-        acc[4 * q + 3] = fmaf(v, w4.w, acc[4 * q + 3]);
+        for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+          for (int q = 0; q < KW; ++q) {
+            const float v = win[(k + dy) % KS][q];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) acc[c] = fmaf(v, wr[dy * KW + q][c], acc[c]);
+          }
+        const size_t o = (((size_t)n * H + y0 + r) * W + xc) * COUT + c0;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          acc[c] = fmaf(acc[c], sc[c], sh[c]);
+          if (relu) acc[c] = fmaxf(acc[c], 0.f);
+        }
+        if (mask) {  // activation-pattern mask of the JVP pass (TG:543: the critic linearised at the mixed sample)
+          float m[CPT];
+          VecIO<CPT>::load(mask + o, m);
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) acc[c] = m[c] > 0.f ? acc[c] : 0.f;
+        }
+        VecIO<CPT>::store(out + o, acc);
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < COUT; ++i) {
-    acc[i] = fmaf(acc[i], s_sc[i], s_sh[i]);
-    if (relu) acc[i] = fmaxf(acc[i], 0.f);
-  }
-  const size_t obase = (((size_t)n * H + h0 + ty) * W + w0 + tx) * COUT;
-  if (mask) {  // activation-pattern mask of the JVP pass (TG:543: the critic linearised at the mixed sample)
-#pragma unroll
-    for (int i = 0; i < COUT; ++i) acc[i] = ldf(mask + obase + i) > 0.f ? acc[i] : 0.f;
-  }
-  TO* o = out + obase;
-  if constexpr (sizeof(TO) == 2) {
-    uint4* o4 = reinterpret_cast<uint4*>(o);
-#pragma unroll
-    for (int q = 0; q < COUT / 8; ++q) {
-      uint4 pk;
-      __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) hp[k] = __floats2bfloat162_rn(acc[8 * q + 2 * k], acc[8 * q + 2 * k + 1]);
-      o4[q] = pk;
-    }
-  } else {
-    float4* o4 = reinterpret_cast<float4*>(o);
-#pragma unroll
-    for (int q = 0; q < COUT / 4; ++q) o4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-  }
 }
 
-template <typename TO, int KS, int CIN, int COUT>
+template <typename TO, int KS, int CIN, int COUT, int CPT>
 int launch_first(const ConvArgs& a, cudaStream_t st) {
-  dim3 grid((a.W / 16) * (a.H / 16), a.N);
-  conv_first_kernel<TO, KS, CIN, COUT><<<grid, 256, 0, st>>>((const float*)a.in0, a.w, a.scale, a.shift, (TO*)a.out,
-                                                              (const TO*)a.mask_src, a.H, a.W, a.relu);
+  constexpr int TILE_W = 8 * (32 / (COUT / CPT));
+  dim3 grid((a.W + TILE_W - 1) / TILE_W, (a.H + EDGE_ROWS - 1) / EDGE_ROWS, a.N);
+  conv_first_kernel<TO, KS, CIN, COUT, CPT><<<grid, 256, 0, st>>>((const float*)a.in0, a.w, a.scale, a.shift,
+                                                                   (TO*)a.out, (const TO*)a.mask_src, a.H, a.W, a.relu);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -216,121 +315,208 @@ int launch_first(const ConvArgs& a, cudaStream_t st) {
 template <typename TO>
 int try_first(const ConvArgs& a, cudaStream_t st) {
   if (a.in_dt != DT_F32 || a.C1 != 0 || a.out_pre || a.film_g || a.add_src || !a.out) return 0;
-  if (a.H % 16 || a.W % 16) return 0;
+  if (a.W % 8) return 0;
   int r = 1;
-  if (a.ks == 3 && a.C0 == 1 && a.Cout == 32) r = launch_first<TO, 3, 1, 32>(a, st);
-  else if (a.ks == 3 && a.C0 == 2 && a.Cout == 32) r = launch_first<TO, 3, 2, 32>(a, st);
-  else if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) r = launch_first<TO, 5, 1, 16>(a, st);
+  if (a.ks == 3 && a.C0 == 1 && a.Cout == 32) r = launch_first<TO, 3, 1, 32, 8>(a, st);
+  else if (a.ks == 3 && a.C0 == 2 && a.Cout == 32) r = launch_first<TO, 3, 2, 32, 4>(a, st);
+  else if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) r = launch_first<TO, 5, 1, 16, 2>(a, st);
   else return 0;
   return r < 0 ? r : 1;
 }
 
-
 // ------------------------------------------------------------------------------------------------------
 // Single-output-channel convolution (the data gradient of conv2d_dis_0a: 16 -> 1, 5x5): dD/dx for the gradient
-// penalty and for the generator's adversarial terms.  HBM-bound (2*Cin B in, 4 B out per pixel): one thread per
-// pixel, the input halo tile in shared memory as fp32, weights broadcast from shared memory, fp32 output.
+// penalty and for the generator's adversarial terms.  CTA = 32 columns x LAST_ROWS rows; the input halo tile is
+// staged in shared memory as channel pairs; G = CIN/2 lanes share a pixel (2 input channels each, their 25*2 weights in
+// registers).  The thread walks down its column one INPUT row at a time: the row's 5 x 2 values feed the 5 output
+// rows it touches (accumulator ring, rotation unrolled), so each output costs 5 shared-memory reads instead of 25;
+// a finished output row is reduced over the G lanes with shuffles.  fp32 output.
 // ------------------------------------------------------------------------------------------------------
+template <typename T> struct LastPair;  // two adjacent input channels as staged in shared memory
+template <> struct LastPair<bf16> {
+  typedef uint32_t type;
+  static constexpr int ROWS = 32;
+  static __device__ __forceinline__ uint32_t load(const bf16* p) { return __ldg(reinterpret_cast<const uint32_t*>(p)); }
+  static __device__ __forceinline__ float2 get(uint32_t q) {
+    return make_float2(__uint_as_float(q << 16), __uint_as_float(q & 0xFFFF0000u));
+  }
+};
+template <> struct LastPair<float> {
+  typedef float2 type;
+  static constexpr int ROWS = 12;
+  static __device__ __forceinline__ float2 load(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ float2 get(float2 q) { return q; }
+};
+
 template <typename TI, int KS, int CIN>
 __global__ void __launch_bounds__(256) conv_last_kernel(const TI* __restrict__ in, const float* __restrict__ w,
                                                         float* __restrict__ out, int H, int W) {
-  constexpr int PAD = KS / 2, IT = 16 + KS - 1, TAPS = KS * KS;
-  __shared__ float s_in[IT * IT][CIN + 1];
-  __shared__ float s_w[TAPS * CIN];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int tiles_w = W / 16;
-  const int w0 = (blockIdx.x % tiles_w) * 16, h0 = (blockIdx.x / tiles_w) * 16, n = blockIdx.y;
-  for (int i = tid; i < TAPS * CIN; i += 256) s_w[i] = w[i];  // [tap][ci][0]
-  for (int i = tid; i < IT * IT * CIN; i += 256) {
-    const int ci = i % CIN, p = i / CIN, c = p % IT, r = p / IT;
-    const int h = h0 + r - PAD, ww = w0 + c - PAD;
-    s_in[p][ci] = (h >= 0 && h < H && ww >= 0 && ww < W) ? ldf(in + (((size_t)n * H + h) * W + ww) * CIN + ci) : 0.f;
+  typedef LastPair<TI> LP;
+  constexpr int LAST_ROWS = LP::ROWS;
+  constexpr int PAD = KS / 2, TAPS = KS * KS, CPT = 2, G = CIN / CPT, PXW = 32 / G, TILE_W = 8 * PXW;
+  constexpr int TR = LAST_ROWS + KS - 1, TCOLS = TILE_W + KS - 1;
+  // [row][col][channel pair] (+1: lanes of one pixel hit distinct banks)
+  __shared__ typename LP::type s_in[TR][TCOLS][G + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cg = lane % G, px = lane / G;
+  const int x0 = blockIdx.x * TILE_W, y0 = blockIdx.y * LAST_ROWS, n = blockIdx.z;
+  for (int i = threadIdx.x; i < TR * TCOLS * G; i += 256) {
+    const int g = i % G, c = (i / G) % TCOLS, r = i / (G * TCOLS);
+    const int gy = y0 - PAD + r, gx = x0 - PAD + c;
+    typename LP::type v{};
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = LP::load(in + (((size_t)n * H + gy) * W + gx) * CIN + 2 * g);
+    s_in[r][c][g] = v;
   }
+  float wr[TAPS][CPT];
+#pragma unroll
+  for (int tp = 0; tp < TAPS; ++tp)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) wr[tp][c] = __ldg(w + tp * CIN + cg * CPT + c);  // [tap][ci][0]
   __syncthreads();
-  float acc = 0.f;
+  const int col = warp * PXW + px, xc = x0 + col;
+  const int rows = min(LAST_ROWS, H - y0);
+  // accumulator of output row o (tile-relative) lives in slot o % KS; input tile row t feeds outputs t-KS+1 .. t
+  float acc[KS];
 #pragma unroll
-  for (int tap = 0; tap < TAPS; ++tap) {
-    const float* xp = s_in[(ty + tap / KS) * IT + tx + tap % KS];
+  for (int s = 0; s < KS; ++s) acc[s] = 0.f;
+  for (int t0 = 0; t0 < rows + KS - 1; t0 += KS) {
 #pragma unroll
-    for (int ci = 0; ci < CIN; ++ci) acc = fmaf(xp[ci], s_w[tap * CIN + ci], acc);
+    for (int k = 0; k < KS; ++k) {
+      const int t = t0 + k;  // input tile row; t % KS == k
+      if (t < rows + KS - 1) {
+        float2 v[KS];
+#pragma unroll
+        for (int c = 0; c < KS; ++c) v[c] = LP::get(s_in[t][col + c][cg]);
+#pragma unroll
+        for (int dy = 0; dy < KS; ++dy) {  // output row o = t - dy, slot (k - dy) mod KS
+          float a = acc[(k - dy + KS) % KS];
+#pragma unroll
+          for (int c = 0; c < KS; ++c) {
+            a = fmaf(v[c].x, wr[dy * KS + c][0], a);
+            a = fmaf(v[c].y, wr[dy * KS + c][1], a);
+          }
+          acc[(k - dy + KS) % KS] = a;
+        }
+        // output row o = t - (KS-1) is complete (its slot is (k+1) % KS); emit it and recycle the slot
+        const int o = t - (KS - 1);
+        float done = acc[(k + 1) % KS];
+        acc[(k + 1) % KS] = 0.f;
+#pragma unroll
+        for (int m = 1; m < G; m <<= 1) done += __shfl_xor_sync(0xffffffffu, done, m);
+        if (o >= 0 && o < rows && cg == 0 && xc < W) out[((size_t)n * H + y0 + o) * W + xc] = done;
+      }
+    }
   }
-  out[((size_t)n * H + h0 + ty) * W + w0 + tx] = acc;
 }
 
 template <typename TI>
 int try_last(const ConvArgs& a, cudaStream_t st) {
   if (a.out_dt != DT_F32 || a.Cout != 1 || a.C1 != 0 || a.scale || a.shift || a.out_pre || a.film_g || a.add_src ||
-      a.mask_src || a.relu || !a.out || a.H % 16 || a.W % 16)
+      a.mask_src || a.relu || !a.out)
     return 0;
-  dim3 grid((a.W / 16) * (a.H / 16), a.N);
-  if (a.ks == 5 && a.C0 == 16)
+  if (a.ks == 5 && a.C0 == 16) {
+    constexpr int TILE_W = 8 * (32 / 8);
+    constexpr int LAST_ROWS = LastPair<TI>::ROWS;
+    dim3 grid((a.W + TILE_W - 1) / TILE_W, (a.H + LAST_ROWS - 1) / LAST_ROWS, a.N);
     conv_last_kernel<TI, 5, 16><<<grid, 256, 0, st>>>((const TI*)a.in0, a.w, (float*)a.out, a.H, a.W);
-  else
+  } else {
     return 0;
+  }
   DG_LAUNCH_CHECK();
   return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Weight gradient of a first layer (fp32 input with CIN <= 2 channels): dw[tap][ci][co] += sum_p x[p+off] dy[p][co].
-// The result is tiny (<= 25*2*32 floats) and the pass is HBM-bound on dy: CTA = one 16x16 tile, thread =
-// (tap, ci, co) item looping the tile's pixels out of shared memory, one atomic per item per CTA.
+// Same CTA / lane mapping as conv_first_kernel with the roles of weights and accumulators swapped: per pixel one
+// coalesced CPT-channel read of dy (fetched KS rows ahead into a register ring), ks new image values from the
+// shared-memory tile, TAPS*CIN*CPT FMAs into register accumulators.  Persistent CTAs; reduction = shuffles over the
+// warp's pixels, shared-memory atomics over the CTA's warps, one global atomic per element per CTA.
 // ------------------------------------------------------------------------------------------------------
-template <typename TD, int KS, int CIN, int COUT>
-__global__ void __launch_bounds__(256) wgrad_first_kernel(const float* __restrict__ x, const TD* __restrict__ dy,
-                                                          float* __restrict__ dw, int H, int W, int tiles, float alpha) {
-  constexpr int PAD = KS / 2, IT = 16 + KS - 1, TAPS = KS * KS, ITEMS = TAPS * CIN * COUT;
-  __shared__ float s_x[IT][IT + 1][CIN];
-  __shared__ float s_d[256][COUT + 1];
-  const int tid = threadIdx.x;
-  const int tiles_w = W / 16, tiles_per_img = tiles_w * (H / 16);
-  float acc[(ITEMS + 255) / 256];
+template <typename TD, int KS, int CIN, int COUT, int CPT>
+__global__ void __launch_bounds__(256, 2) wgrad_first_kernel(const float* __restrict__ x, const TD* __restrict__ dy,
+                                                          float* __restrict__ dw, int N, int H, int W, float alpha) {
+  constexpr int TAPS = KS * KS, G = COUT / CPT, PXW = 32 / G, KW = KS * CIN, ITEMS = TAPS * CIN * COUT;
+  constexpr int TILE_W = 8 * PXW;
+  __shared__ EdgeTile<KS, CIN, TILE_W> tile;
+  __shared__ float s_acc[ITEMS];
+  for (int i = threadIdx.x; i < ITEMS; i += 256) s_acc[i] = 0.f;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cg = lane % G, px = lane / G, c0 = cg * CPT;
+  const int col = warp * PXW + px;
+  const int tiles_w = (W + TILE_W - 1) / TILE_W, bands = (H + EDGE_ROWS - 1) / EDGE_ROWS;
+  const int n_tiles = N * bands * tiles_w;
+  float acc[TAPS * CIN][CPT];
 #pragma unroll
-  for (int k = 0; k < (ITEMS + 255) / 256; ++k) acc[k] = 0.f;
-  for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const int n = t / tiles_per_img, tt = t % tiles_per_img;
-    const int w0 = (tt % tiles_w) * 16, h0 = (tt / tiles_w) * 16;
-    __syncthreads();
-    for (int i = tid; i < IT * IT * CIN; i += 256) {
-      const int ci = i % CIN, c = (i / CIN) % IT, r = i / (CIN * IT);
-      const int h = h0 + r - PAD, ww = w0 + c - PAD;
-      s_x[r][c][ci] = (h >= 0 && h < H && ww >= 0 && ww < W) ? x[(((size_t)n * H + h) * W + ww) * CIN + ci] : 0.f;
-    }
-    for (int i = tid; i < 256 * COUT; i += 256) {
-      const int co = i % COUT, p = i / COUT;
-      s_d[p][co] = ldf(dy + (((size_t)n * H + h0 + p / 16) * W + w0 + p % 16) * COUT + co);
-    }
-    __syncthreads();
+  for (int t = 0; t < TAPS * CIN; ++t)
 #pragma unroll
-    for (int k = 0; k < (ITEMS + 255) / 256; ++k) {
-      const int item = tid + 256 * k;
-      if (item < ITEMS) {
-        const int co = item % COUT, ci = (item / COUT) % CIN, tap = item / (COUT * CIN);
-        const int dy_ = tap / KS, dx_ = tap % KS;
-        float a = 0.f;
-        for (int p = 0; p < 256; ++p) a = fmaf(s_x[(p >> 4) + dy_][(p & 15) + dx_][ci], s_d[p][co], a);
-        acc[k] += a;
+    for (int c = 0; c < CPT; ++c) acc[t][c] = 0.f;
+  for (int tid = blockIdx.x; tid < n_tiles; tid += gridDim.x) {
+    const int x0 = (tid % tiles_w) * TILE_W, y0 = ((tid / tiles_w) % bands) * EDGE_ROWS, n = tid / (tiles_w * bands);
+    __syncthreads();  // everybody is done with the previous tile
+    tile.fill(x, n, y0, x0, H, W);
+    const int xc = x0 + col;
+    const int rows = xc < W ? min(EDGE_ROWS, H - y0) : 0;
+    const TD* dyp = dy + (((size_t)n * H + y0) * W + xc) * COUT + c0;
+    const size_t dy_row = (size_t)W * COUT;
+    float dring[KS][CPT];  // dy of rows r .. r+KS-1, fetched KS rows ahead of use
+#pragma unroll
+    for (int k = 0; k < KS; ++k)
+      if (k < rows) VecIO<CPT>::load(dyp + k * dy_row, dring[k]);
+    __syncthreads();
+    if (rows > 0) {
+      float win[KS][KW];
+#pragma unroll
+      for (int d = 0; d < KS - 1; ++d) tile.row(d, col, win[d]);
+      for (int r0 = 0; r0 < rows; r0 += KS) {
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const int r = r0 + k;
+          if (r < rows) {
+            tile.row(r + KS - 1, col, win[(k + KS - 1) % KS]);
+            float d[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) d[c] = dring[k][c];
+            if (r + KS < rows) VecIO<CPT>::load(dyp + (size_t)(r + KS) * dy_row, dring[k]);
+#pragma unroll
+            for (int ty = 0; ty < KS; ++ty)
+#pragma unroll
+              for (int q = 0; q < KW; ++q) {
+                const float v = win[(k + ty) % KS][q];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) acc[ty * KW + q][c] = fmaf(v, d[c], acc[ty * KW + q][c]);
+              }
+          }
+        }
       }
     }
   }
+  // lanes with equal cg hold partial sums of the same (tap, ci, co) elements
 #pragma unroll
-  for (int k = 0; k < (ITEMS + 255) / 256; ++k) {
-    const int item = tid + 256 * k;
-    if (item < ITEMS) atomicAdd(dw + item, alpha * acc[k]);
-  }
+  for (int t = 0; t < TAPS * CIN; ++t)
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      float v = acc[t][c];
+#pragma unroll
+      for (int m = G; m < 32; m <<= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+      if (px == 0) atomicAdd(&s_acc[t * COUT + c0 + c], v);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < ITEMS; i += 256) atomicAdd(dw + i, alpha * s_acc[i]);
 }
 
 template <typename TD>
 int try_wgrad_first(const WgradArgs& a, cudaStream_t st) {
-  if (a.x_dt != DT_F32 || a.C1 != 0 || a.H % 16 || a.W % 16) return 0;
-  const int tiles = (a.W / 16) * (a.H / 16) * a.N;
-  const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
-#define DG_WF(KS_, CI_, CO_)                                                                                   \
-  wgrad_first_kernel<TD, KS_, CI_, CO_><<<grid, 256, 0, st>>>((const float*)a.x0, (const TD*)a.dy, a.dw, a.H, a.W, \
-                                                              tiles, a.alpha)
-  if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) DG_WF(5, 1, 16);
-  else if (a.ks == 3 && a.C0 == 1 && a.Cout == 32) DG_WF(3, 1, 32);
-  else if (a.ks == 3 && a.C0 == 2 && a.Cout == 32) DG_WF(3, 2, 32);
+  if (a.x_dt != DT_F32 || a.C1 != 0 || a.W % 8) return 0;
+#define DG_WF(KS_, CI_, CO_, CPT_)                                                                             \
+  do {                                                                                                         \
+    constexpr int TILE_W_ = 8 * (32 / (CO_ / CPT_));                                                           \
+    long long grid = (long long)a.N * ((a.H + EDGE_ROWS - 1) / EDGE_ROWS) * ((a.W + TILE_W_ - 1) / TILE_W_);   \
+    if (grid > 148 * 2) grid = 148 * 2;                                                                        \
+    wgrad_first_kernel<TD, KS_, CI_, CO_, CPT_><<<(unsigned)grid, 256, 0, st>>>(                               \
+        (const float*)a.x0, (const TD*)a.dy, a.dw, a.N, a.H, a.W, a.alpha);                                    \
+  } while (0)
+  if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) DG_WF(5, 1, 16, 2);
+  else if (a.ks == 3 && a.C0 == 1 && a.Cout == 32) DG_WF(3, 1, 32, 4);
+  else if (a.ks == 3 && a.C0 == 2 && a.Cout == 32) DG_WF(3, 2, 32, 4);
   else return 0;
 #undef DG_WF
   DG_LAUNCH_CHECK();

@@ -1,31 +1,8 @@
-// tcgen05 / TMEM implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate in tensor memory).
-//
-// Replaces Keras Conv2D 'same' stride-1 (+BatchNormalization +Activation, TG:285-304), the k2s2 Conv2DTranspose
-// (TG:307-312, as a 1x1 GEMM with 4*Cout columns scattered to the 2x2 output parities), and -- with flipped /
-// transposed weights -- the data-gradient and JVP passes of the same layers (TG:543-549).
-//
-// GEMM view: M = pixels, N = output channels, K = taps x input channels.
-//   * One CTA = one 16x16 pixel tile of one slice = two M=128 accumulators ("strips" of 8 columns x 16 rows),
-//     N = ncta <= 256 output columns each, living in TMEM (2*ncta columns).
-//   * K loop = channel chunks (kc = 16/32/64 channels = one 32/64/128-byte swizzle span) x taps.  Per chunk ONE
-//     TMA box load brings the (16+ks-1)^2 halo tile [rows][cols][kc] into shared memory ('same' zero padding
-//     comes from TMA out-of-bound fill); every tap then reads its A operand as a *shifted view* of that halo
-//     tile: rows of the canonical K-major layout are consecutive pixels (pitch = swizzle span), 8-row groups
-//     are tile rows (SBO = halo row pitch), so a tap is just a different descriptor start address.  The
-//     hardware swizzle is a function of the shared-memory address, so views starting at any pixel are valid
-//     as long as the TMA destination is pattern (1024 B) aligned.  Activations are read from L2/HBM once per
-//     tile (x1.27 halo overhead) instead of once per tap.
-//   * B (weights, [tap][n][k] bf16) streams through its own TMA ring, one (tap, chunk) tile per stage.
-//     When every (chunk, tap) tile of the layer fits next to the activation ring (32->32 ... 96->96 3x3 layers)
-//     the weights are loaded ONCE per CTA and stay resident.
-//   * Persistent: grid = min(#work items, #SMs), one CTA per SM looping over (tile, n-split) items.
-//     warp 0 lane 0 = TMA producer, warp 1 lane 0 = MMA issuer (tcgen05.mma.cta_group::1.kind::f16), warps 2..9 =
-//     fused epilogue straight out of TMEM (tcgen05.ld 32x32b.x16).  Two TMEM accumulator stages (when
-//     4*ncta <= 512 columns) overlap the epilogue of item i with the MMA stream of item i+1; the producer runs
-//     ahead across items, so prologue latency is paid once per CTA, not once per tile.
-#include <cuda.h>
+// Host side of the tcgen05 implicit-GEMM convolution: shape planning (shared-memory rings, TMEM columns), TMA tensor
+// maps and dispatch to the kernel instantiations of conv_tc_k{1,3,5}.cu.  The kernel itself is conv_tc_kernel.cuh.
+#include "conv_tc_kernel.cuh"
 
-#include "common.cuh"
+using namespace convtc;
 
 namespace {
 
@@ -35,502 +12,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 148;
 
-struct TcGeom {
-  int tiles_w, tiles_h;
-  int nchunk0, nchunk1;  // channel chunks taken from in0 / in1
-  int kc;                // channels per chunk
-  int ncols_total;       // weight rows per tap (Cout, or 4*Cout for the transposed conv)
-  int ncta;              // output columns per CTA
-  int tmem_cols;         // power of two >= 2*ncta
-  int na, nb;            // ring depths
-  uint32_t a_bytes, b_bytes;  // stage strides (1024-aligned)
-  uint32_t a_tx, b_tx;        // TMA transaction bytes per stage
-  uint32_t layout;            // UMMA smem layout type (2 = SW128, 4 = SW64, 6 = SW32)
-  int b_resident;             // 1: all (chunk, tap) weight tiles live in smem for the CTA's lifetime
-  int acc_stages;             // TMEM accumulator stages (2 when 4*ncta <= 512)
-};
-
-// ---------------------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok;
-}
-// Bounded wait: a protocol bug traps (surfacing as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
-      "[%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// K-major shared-memory matrix descriptor (SM100 version 1): rows at one swizzle-span pitch, 8-row groups at SBO.
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
-  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-__device__ __forceinline__ void ld16_bf16(const void* base, size_t elem_off, float (&v)[16]) {
-  const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem_off);
-  uint4 q[2] = {__ldg(p), __ldg(p + 1)};
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(q);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float2 f = __bfloat1622float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
-  }
-}
-struct Packed16 {  // 16 bf16 values as loaded (two 128-bit words)
-  uint4 q[2];
-  __device__ __forceinline__ void load(const void* base, size_t elem_off) {
-    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem_off);
-    q[0] = __ldg(p);
-    q[1] = __ldg(p + 1);
-  }
-  __device__ __forceinline__ float get(int i) const {
-    const uint32_t w = reinterpret_cast<const uint32_t*>(q)[i >> 1];
-    return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
-  }
-};
-__device__ __forceinline__ void st16_bf16(void* base, size_t elem_off, const float (&v)[16]) {
-  uint4 q[2];
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + elem_off);
-  p[0] = q[0];
-  p[1] = q[1];
-}
-__device__ __forceinline__ void ld16_f32(const float* p, float (&v)[16]) {
-  const float4* q = reinterpret_cast<const float4*>(p);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float4 t = __ldg(q + i);
-    v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// kernel: persistent, warp-specialised.  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..9 = epilogue (warp w reads TMEM lane quarter w%4 of strip (w-2)/4).  Two TMEM accumulator stages let
-// the epilogue of work item i overlap the MMA stream of item i+1.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int TC_THREADS = 320;
-
-struct Ring {
-  int idx = 0;
-  uint32_t phase = 0;
-  __device__ __forceinline__ void advance(int n) {
-    if (++idx == n) { idx = 0; phase ^= 1u; }
-  }
-};
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-
-template <int KS, int KSTEPS, bool RES>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                                const __grid_constant__ CUtensorMap tmA1,
-                                                                const __grid_constant__ CUtensorMap tmB,
-                                                                const ConvArgs a, const TcGeom g) {
-  constexpr int PAD = KS / 2, HT = 16 + KS - 1, TAPS = KS * KS;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  const uint32_t a_base = base;
-  const uint32_t b_base = a_base + g.na * g.a_bytes;
-  const uint32_t bar_base = b_base + g.nb * g.b_bytes;
-  const uint32_t fullA = bar_base, emptyA = fullA + 8 * g.na;
-  const uint32_t fullB = emptyA + 8 * g.na, emptyB = fullB + 8 * g.nb;
-  const uint32_t accFull = emptyB + 8 * g.nb, accEmpty = accFull + 16;
-  const uint32_t tmem_slot = accEmpty + 16;
-  const uint32_t ss_off = tmem_slot + 16;  // scale / shift staging: 2 * ncols_total floats, then head weights
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
-  float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_off - raw));
-  float* s_shift = s_scale + g.ncols_total;
-  float4* s_head = reinterpret_cast<float4*>(s_shift + g.ncols_total);  // [Cout] x (up to 4 head outputs)
-  // FiLM folded with BN per (sample, channel): [2 slots][2][ncta] floats, rebuilt per work item by the epilogue warps
-  float* s_film = reinterpret_cast<float*>(s_head + a.Cout);
-
-  // warp index made provably warp-uniform so the role loops run on the uniform datapath
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  constexpr int rowb = KSTEPS * 32;  // bytes per pixel row of a chunk = one swizzle span (kc = 16*KSTEPS)
-  const int nchunks = g.nchunk0 + g.nchunk1;
-  const int nsplit = g.ncols_total / g.ncta;
-  const int tiles_per_img = g.tiles_w * g.tiles_h;
-  const int n_items = tiles_per_img * a.N * nsplit;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < g.na; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
-    for (int i = 0; i < g.nb; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(g.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  {  // BN scale / shift (or bias) once per CTA
-    const int cmod = a.Cout;
-    for (int i = threadIdx.x; i < g.ncols_total; i += TC_THREADS) {
-      s_scale[i] = a.scale ? a.scale[i % cmod] : 1.f;
-      s_shift[i] = a.shift ? a.shift[i % cmod] : 0.f;
-    }
-    if (a.head_w) {
-      for (int i = threadIdx.x; i < a.Cout; i += TC_THREADS) {
-        float hv[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int k = 0; k < a.head_nc; ++k) hv[k] = a.head_w[(size_t)i * a.head_nc + k];
-        s_head[i] = make_float4(hv[0], hv[1], hv[2], hv[3]);
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
-  const int acc_stride = g.acc_stages == 2 ? g.tmem_cols / 2 : 0;
-
-  if (warp == 0) {
-    // ===== TMA producer (whole warp runs the loops; one elected lane issues) =====
-    if (RES) {  // all weights of the layer stay in shared memory for the CTA's lifetime
-      if (elect_one()) {
-        mbar_expect_tx(fullB, g.b_tx * TAPS * nchunks);
-        for (int c = 0; c < nchunks; ++c) {
-          const int kglob = c < g.nchunk0 ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
-          for (int tap = 0; tap < TAPS; ++tap)
-            tma_load_2d(b_base + (c * TAPS + tap) * g.b_bytes, &tmB, fullB, kglob, tap * g.ncols_total);
-        }
-      }
-      __syncwarp();
-    }
-    Ring ra, rb;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-      const int ns = it % nsplit, t = it / nsplit;
-      const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
-      const int w0 = tw * 16, h0 = th * 16, n0 = ns * g.ncta;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(emptyA + 8 * ra.idx, ra.phase ^ 1u);
-        const bool first = c < g.nchunk0;
-        if (elect_one()) {
-          mbar_expect_tx(fullA + 8 * ra.idx, g.a_tx);
-          tma_load_4d(a_base + ra.idx * g.a_bytes, first ? &tmA0 : &tmA1, fullA + 8 * ra.idx,
-                      (first ? c : c - g.nchunk0) * g.kc, w0 - PAD, h0 - PAD, n);
-        }
-        __syncwarp();
-        ra.advance(g.na);
-        if (!RES) {
-          const int kglob = first ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
-          for (int tap = 0; tap < TAPS; ++tap) {
-            mbar_wait(emptyB + 8 * rb.idx, rb.phase ^ 1u);
-            if (elect_one()) {
-              mbar_expect_tx(fullB + 8 * rb.idx, g.b_tx);
-              tma_load_2d(b_base + rb.idx * g.b_bytes, &tmB, fullB + 8 * rb.idx, kglob, tap * g.ncols_total + n0);
-            }
-            __syncwarp();
-            rb.advance(g.nb);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (whole warp converged, one elected lane issues tcgen05.mma / commit) =====
-    // Descriptors: the high word (SBO, version, swizzle mode) is constant; per MMA only the 14-bit start
-    // address field of the low word moves, in 16-byte units.
-    const uint32_t idesc = make_idesc(g.ncta);
-    const uint32_t hiA = ((uint32_t)(HT * rowb) >> 4) | (1u << 14) | (g.layout << 29);
-    const uint32_t hiB = ((uint32_t)(8 * rowb) >> 4) | (1u << 14) | (g.layout << 29);
-    constexpr uint32_t LBO1 = 1u << 16;
-    constexpr uint32_t ROW16 = rowb / 16;  // one pixel row in descriptor units
-    Ring ra, rb;
-    int k_it = 0;
-    if (RES) mbar_wait(fullB, 0);
-    const uint32_t b_step = g.b_bytes >> 4;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_it) {
-      const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
-      const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
-      mbar_wait(accEmpty + 8 * as, (use & 1u) ^ 1u);
-      tc_fence_after();
-      const uint32_t d0 = tmem_base + as * acc_stride, d1 = d0 + g.ncta;
-      for (int c = 0; c < nchunks; ++c) {
-        mbar_wait(fullA + 8 * ra.idx, ra.phase);
-        tc_fence_after();
-        const uint32_t a_lo = (((a_base + ra.idx * g.a_bytes) & 0x3FFFFu) >> 4) | LBO1;
-        const uint32_t accc = (uint32_t)(c != 0);
-        if (RES) {
-          // weights resident: the whole chunk (TAPS x 2 strips x KSTEPS MMAs) is issued back to back
-          const uint32_t b_lo0 = (((b_base + c * TAPS * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
-          if (elect_one()) {
-#pragma unroll
-            for (int tap = 0; tap < TAPS; ++tap) {
-              const uint32_t at = a_lo + (uint32_t)(((tap / KS) * HT + (tap % KS)) * ROW16);
-              const uint32_t b_lo = b_lo0 + tap * b_step;
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                const uint32_t acc = (tap | k) != 0 ? 1u : accc;
-                tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
-                tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
-                       idesc, acc);
-              }
-            }
-            tc_commit(emptyA + 8 * ra.idx);
-          }
-          __syncwarp();
-        } else {
-#pragma unroll 1
-          for (int tap = 0; tap < TAPS; ++tap) {
-            mbar_wait(fullB + 8 * rb.idx, rb.phase);
-            tc_fence_after();
-            const uint32_t b_lo = (((b_base + rb.idx * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
-            const int dy = tap / KS, dx = tap - dy * KS;
-            const uint32_t at = a_lo + (uint32_t)((dy * HT + dx) * ROW16);
-            if (elect_one()) {
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                const uint32_t acc = k != 0 ? 1u : (tap != 0 ? 1u : accc);
-                tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
-                tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
-                       idesc, acc);
-              }
-              tc_commit(emptyB + 8 * rb.idx);
-              if (tap == TAPS - 1) tc_commit(emptyA + 8 * ra.idx);
-            }
-            __syncwarp();
-            rb.advance(g.nb);
-          }
-        }
-        ra.advance(g.na);
-      }
-      if (elect_one()) tc_commit(accFull + 8 * as);
-      __syncwarp();
-    }
-  } else {
-    // ===== epilogue warps: TMEM -> registers -> global =====
-    const int ew = warp - 2;
-    const int strip = ew >> 2;
-    const int q = warp & 3;          // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;     // accumulator row
-    const int ty = r >> 3, tx = strip * 8 + (r & 7);
-    const int Cout = a.Cout;
-    int k_it = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_it) {
-      const int ns = it % nsplit, t = it / nsplit;
-      const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
-      const int h = th * 16 + ty, w = tw * 16 + tx, n0 = ns * g.ncta;
-      const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
-      const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
-      // ---- everything that does not need the accumulator is issued BEFORE waiting for it ----
-      const size_t pix0 = ((size_t)n * a.H + h) * a.W + w;
-      float* sF = s_film + (k_it & 1) * 2 * g.ncta;
-      Packed16 rs_next;
-      if (a.film_g) {
-        // FiLM folded into the BN affine for this item's sample: v = relu(acc*(s*g) + (t*g + b)) + res
-        for (int c = ew * 32 + lane; c < g.ncta; c += 256) {
-          const float fgv = __ldg(a.film_g + (size_t)n * a.film_stride + n0 + c);
-          const float fbv = __ldg(a.film_b + (size_t)n * a.film_stride + n0 + c);
-          sF[c] = s_scale[n0 + c] * fgv;
-          sF[g.ncta + c] = fmaf(s_shift[n0 + c], fgv, fbv);
-        }
-        rs_next.load(a.res, pix0 * Cout + n0);
-        // all 8 epilogue warps: the slot is complete (and nobody still reads the other use of it)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-      }
-      mbar_wait(accFull + 8 * as, use & 1u);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + as * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(strip * g.ncta);
-      float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
-      const int nj = g.ncta / 16;
-#pragma unroll 1
-      for (int j = 0; j < nj; ++j) {
-        const int col = n0 + j * 16;
-        int c0 = col;
-        size_t opix = pix0;
-        if (a.deconv) {
-          const int ab = col / Cout;
-          c0 = col - ab * Cout;
-          opix = ((size_t)n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1);
-        }
-        const size_t off = opix * Cout + c0;
-        // issue the global reads of this chunk before waiting on tensor memory
-        Packed16 rs, ad, mk;  // bf16 x 16, unpacked at use (keeps the prefetch cheap in registers)
-        if (a.film_g) {
-          rs = rs_next;
-          if (j + 1 < nj) rs_next.load(a.res, off + 16);  // next chunk's residual while this one is processed
-        }
-        if (a.add_src) ad.load(a.add_src, off);
-        if (a.mask_src) mk.load(a.mask_src, off);
-        float v[16];
-        tc_ld16(t_row + (uint32_t)(j * 16), v);
-        if (a.film_g) {
-          if (a.out_pre) {
-            float vp[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) vp[i] = fmaf(v[i], s_scale[col + i], s_shift[col + i]);
-            st16_bf16(a.out_pre, off, vp);
-          }
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 sc = reinterpret_cast<const float4*>(sF + j * 16)[i4];
-            const float4 sh = reinterpret_cast<const float4*>(sF + g.ncta + j * 16)[i4];
-            v[4 * i4 + 0] = fmaxf(fmaf(v[4 * i4 + 0], sc.x, sh.x), 0.f) + rs.get(4 * i4 + 0);
-            v[4 * i4 + 1] = fmaxf(fmaf(v[4 * i4 + 1], sc.y, sh.y), 0.f) + rs.get(4 * i4 + 1);
-            v[4 * i4 + 2] = fmaxf(fmaf(v[4 * i4 + 2], sc.z, sh.z), 0.f) + rs.get(4 * i4 + 2);
-            v[4 * i4 + 3] = fmaxf(fmaf(v[4 * i4 + 3], sc.w, sh.w), 0.f) + rs.get(4 * i4 + 3);
-          }
-        } else {
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 sc = reinterpret_cast<const float4*>(s_scale + col)[i4];
-            const float4 sh = reinterpret_cast<const float4*>(s_shift + col)[i4];
-            v[4 * i4 + 0] = fmaf(v[4 * i4 + 0], sc.x, sh.x);
-            v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc.y, sh.y);
-            v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
-            v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
-          }
-          if (a.out_pre) st16_bf16(a.out_pre, off, v);
-        }
-        if (a.add_src) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += ad.get(i);
-        }
-        if (a.mask_src) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = mk.get(i) > 0.f ? v[i] : 0.f;
-        }
-        if (a.relu) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-        }
-        if (a.out) st16_bf16(a.out, off, v);
-        if (a.head_w) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float4 hw = s_head[c0 + i];
-            head_acc[0] = fmaf(v[i], hw.x, head_acc[0]);
-            head_acc[1] = fmaf(v[i], hw.y, head_acc[1]);
-            head_acc[2] = fmaf(v[i], hw.z, head_acc[2]);
-            head_acc[3] = fmaf(v[i], hw.w, head_acc[3]);
-          }
-        }
-      }
-      // this warp is done with the accumulator stage: hand it back to the MMA issuer
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(accEmpty + 8 * as);
-      if (a.head_w) {
-        const size_t pix = ((size_t)n * a.H + h) * a.W + w;
-        const int nc = a.head_nc;
-        float o0 = head_acc[0] + __ldg(a.head_b), o1 = 0.f, o2 = 0.f, o3 = 0.f;
-        if (nc > 1) o1 = head_acc[1] + __ldg(a.head_b + 1);
-        if (nc > 2) o2 = head_acc[2] + __ldg(a.head_b + 2);
-        if (nc > 3) o3 = head_acc[3] + __ldg(a.head_b + 3);
-        if (a.head_act == 0) {
-          o0 = tanhf(o0); o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3);
-        } else if (a.head_act == 1) {
-          float m = o0;
-          if (nc > 1) m = fmaxf(m, o1);
-          if (nc > 2) m = fmaxf(m, o2);
-          if (nc > 3) m = fmaxf(m, o3);
-          o0 = expf(o0 - m);
-          o1 = nc > 1 ? expf(o1 - m) : 0.f;
-          o2 = nc > 2 ? expf(o2 - m) : 0.f;
-          o3 = nc > 3 ? expf(o3 - m) : 0.f;
-          const float inv = 1.0f / (o0 + o1 + o2 + o3);
-          o0 *= inv; o1 *= inv; o2 *= inv; o3 *= inv;
-        }
-        if (nc == 4) {
-          *reinterpret_cast<float4*>(a.head_out + pix * 4) = make_float4(o0, o1, o2, o3);
-        } else {
-          float* op = a.head_out + pix * nc;
-          op[0] = o0;
-          if (nc > 1) op[1] = o1;
-          if (nc > 2) op[2] = o2;
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// host side
-// ---------------------------------------------------------------------------------------------------------
 CUtensorMapSwizzle swizzle_for(int kc) {
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
@@ -572,11 +53,11 @@ constexpr uint32_t SMEM_BUDGET = 220 * 1024;  // one persistent CTA per SM
 bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   const int ks = a.ks, ht = 16 + ks - 1, taps = ks * ks;
   const int ncols = a.deconv ? 4 * a.Cout : a.Cout;
-  const int nsplit = (ncols + 255) / 256;
+  // the transposed conv's epilogue is long (4*Cout columns): 128-column items keep two accumulator stages
+  const int nsplit = (a.deconv && ncols % 128 == 0) ? ncols / 128 : (ncols + 255) / 256;
   if (ncols % nsplit) return false;
   const int ncta = ncols / nsplit;
   if (ncta % 16 || ncta < 16 || ncta > 256) return false;
-  if (a.deconv && (ncta % a.Cout)) return false;
   const int acc_stages = 4 * ncta <= 512 ? 2 : 1;
   int tmem_cols = 32;
   while (tmem_cols < 2 * ncta * acc_stages) tmem_cols *= 2;
@@ -631,15 +112,9 @@ int conv_tc_init() {
   int dev = 0;
   DG_CHECK_CUDA(cudaGetDevice(&dev));
   DG_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-#define DG_TC_ATTR(KS_, K_)                                                                                        \
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS_, K_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                     227 * 1024));                                                                 \
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS_, K_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                     227 * 1024))
-  DG_TC_ATTR(1, 1); DG_TC_ATTR(1, 2); DG_TC_ATTR(1, 4);
-  DG_TC_ATTR(3, 1); DG_TC_ATTR(3, 2); DG_TC_ATTR(3, 4);
-  DG_TC_ATTR(5, 1); DG_TC_ATTR(5, 2); DG_TC_ATTR(5, 4);
-#undef DG_TC_ATTR
+  DG_TRY(set_attrs_ks1());
+  DG_TRY(set_attrs_ks3());
+  DG_TRY(set_attrs_ks5());
   return 0;
 }
 
@@ -652,7 +127,7 @@ bool conv_tc_supported(const ConvArgs& a) {
   if (a.C1 > 0 && !a.in1) return false;
   if (!a.w_tc) return false;
   if (a.head_w && (a.deconv || a.Cout > 256 || a.head_nc > 4)) return false;
-  if (a.film_g && a.deconv) return false;
+  if (a.deconv && (a.film_g || a.add_src || a.mask_src)) return false;  // side inputs index the conv layout
   TcGeom g;
   uint32_t smem;
   return plan(a, &g, &smem);
@@ -672,25 +147,12 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   DG_TRY(make_w_map(&tmB, a.w_tc, a.C0 + a.C1, a.ks * a.ks * g.ncols_total, g.kc, g.ncta));
   const int n_items = g.tiles_w * g.tiles_h * a.N * (g.ncols_total / g.ncta);
   const int grid = n_items < g_num_sms ? n_items : g_num_sms;
-#define DG_TC_LAUNCH(KS_, K_)                                                                  \
-  do {                                                                                         \
-    if (g.b_resident) conv_tc_kernel<KS_, K_, true><<<grid, TC_THREADS, smem, st>>>(tmA0, tmA1, tmB, a, g);  \
-    else conv_tc_kernel<KS_, K_, false><<<grid, TC_THREADS, smem, st>>>(tmA0, tmA1, tmB, a, g);              \
-  } while (0)
-  const int key = a.ks * 10 + g.kc / 16;
-  switch (key) {
-    case 11: DG_TC_LAUNCH(1, 1); break;
-    case 12: DG_TC_LAUNCH(1, 2); break;
-    case 14: DG_TC_LAUNCH(1, 4); break;
-    case 31: DG_TC_LAUNCH(3, 1); break;
-    case 32: DG_TC_LAUNCH(3, 2); break;
-    case 34: DG_TC_LAUNCH(3, 4); break;
-    case 51: DG_TC_LAUNCH(5, 1); break;
-    case 52: DG_TC_LAUNCH(5, 2); break;
-    case 54: DG_TC_LAUNCH(5, 4); break;
-    default: depgan_set_error("conv_fwd_tc: no kernel for this (ks, kc)"); return -2;
+  // side inputs the epilogue has to stream (selects the EPI instantiation): bit 0 FiLM residual, bit 1 add / mask
+  const int need = (a.film_g ? 1 : 0) | ((a.add_src || a.mask_src) ? 2 : 0);
+  switch (a.ks) {
+    case 1: return launch_ks1(grid, smem, st, tmA0, tmA1, tmB, a, g, need);
+    case 3: return launch_ks3(grid, smem, st, tmA0, tmA1, tmB, a, g, need);
+    case 5: return launch_ks5(grid, smem, st, tmA0, tmA1, tmB, a, g, need);
+    default: depgan_set_error("conv_fwd_tc: no kernel for this kernel size"); return -2;
   }
-#undef DG_TC_LAUNCH
-  DG_LAUNCH_CHECK();
-  return 0;
 }

@@ -652,8 +652,9 @@ int depgan_op_wgrad(const void* x0, const void* x1, int C0, int C1, const void* 
   WgradArgs a{};
   a.x0 = x0; a.x1 = x1; a.C0 = C0; a.C1 = C1; a.dy = dy; a.dw = dw; a.N = N; a.H = H; a.W = W; a.Cout = Cout;
   a.ks = ks; a.alpha = 1.f;
-  a.x_dt = a.dy_dt = use_tc ? DT_BF16 : DT_F32;
-  if (use_tc) {
+  a.x_dt = a.dy_dt = use_tc == 1 ? DT_BF16 : DT_F32;
+  if (use_tc == 2) a.dy_dt = DT_BF16;  // first-layer case of the bf16 networks: fp32 image, bf16 gradient
+  if (use_tc == 1) {
     DG_REQUIRE(wgrad_tc_supported(a), "op_wgrad: shape not supported by the tcgen05 path");
     return conv_wgrad_tc(a, (cudaStream_t)stream);
   }

@@ -161,7 +161,8 @@ typedef struct depgan_conv_desc {
 } depgan_conv_desc;
 int depgan_op_conv2d(const depgan_conv_desc* d, void* stream);
 /* Weight gradient of one convolution: dw[tap][Cin][Cout] (fp32, Keras HWIO order) += sum_p x[p+off(tap)] (x) dy[p].
- * use_tc=1: tcgen05 path (x, dy bf16); use_tc=0: fp32 CUDA-core path (x, dy float32).  The caller zeroes dw. */
+ * use_tc=1: tcgen05 path (x, dy bf16); use_tc=0: fp32 CUDA-core path (x, dy float32); use_tc=2: CUDA-core path with
+ * x float32 and dy bf16 (the first layer of a bf16 network).  The caller zeroes dw. */
 int depgan_op_wgrad(const void* x0, const void* x1, int C0, int C1, const void* dy, float* dw, int N, int H, int W,
                     int Cout, int ks, int use_tc, void* stream);
 int depgan_op_pack_weights(const float* w_f32_dev, void* w_bf16_dev, int taps, int cin, int cout, void* stream);

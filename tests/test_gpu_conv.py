@@ -195,3 +195,68 @@ def test_simt_wgrad_matches_reference(ks, c0, cout):
     got = wgrad_op(x.cuda(), dy.cuda(), ks, use_tc=False).cpu()
     want = ref_wgrad(x, dy, ks)
     assert float((got - want).abs().max()) <= 1e-3 * float(want.abs().max())
+
+
+# ---- persistent-loop coverage: more work items than SMs, so the epilogue's side-input ring crosses item boundaries ----
+@pytest.mark.parametrize("c,H,W,N", [(32, 128, 128, 3), (96, 64, 64, 11), (64, 64, 48, 13)])
+def test_tcgen05_film_residual_many_items(c, H, W, N):
+    from depgan_b200 import conv2d_op
+    x, w = _bf(_rand((N, H, W, c), 1)), _bf(_rand((3, 3, c, c), 2, 0.06))
+    g, b, res = 1 + 0.3 * _rand((N, c), 3), 0.2 * _rand((N, c), 4), _bf(_rand((N, H, W, c), 5))
+    got, ex = conv2d_op(x.cuda(), w.cuda(), film=(g, b), res=res.cuda(), use_tc=True, want_pre=True)
+    want, pre = ref_conv(x, w, film=(g, b), res=res)
+    assert float((got.cpu() - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
+    assert float((ex["pre"].cpu() - pre).abs().max()) <= 2e-2 * max(1.0, float(pre.abs().max()))
+
+
+@pytest.mark.parametrize("ks,cin,cout,H,W,N,use_add", [(3, 32, 32, 128, 128, 3, True), (5, 32, 16, 64, 64, 12, False),
+                                                        (3, 128, 96, 32, 32, 40, True), (1, 64, 256, 32, 32, 40, True),
+                                                        (3, 256, 128, 16, 16, 160, False)])
+def test_tcgen05_add_mask_many_items(ks, cin, cout, H, W, N, use_add):
+    """The dgrad / JVP epilogue (add_src, ReLU-pattern mask) over a persistent loop with 1..16 chunks per item."""
+    from depgan_b200 import conv2d_op
+    x = _bf(_rand((N, H, W, cin), 1))
+    w = _bf(_rand((ks, ks, cin, cout), 2, 1.0 / np.sqrt(ks * ks * cin)))
+    mask = _bf(_rand((N, H, W, cout), 6))
+    add = _bf(_rand((N, H, W, cout), 7)) if use_add else None
+    got = conv2d_op(x.cuda(), w.cuda(), add=None if add is None else add.cuda(), mask=mask.cuda(), use_tc=True).cpu()
+    want, _ = ref_conv(x, w, add=add, mask=mask)
+    assert float((got - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
+
+
+def test_tcgen05_plain_many_items_and_deconv_split():
+    from depgan_b200 import conv2d_op
+    N, H, W, c = 5, 64, 64, 64
+    x, w = _bf(_rand((N, H, W, c), 1)), _bf(_rand((3, 3, c, c), 2, 0.05))
+    sc, sh = 1 + 0.1 * _rand((c,), 4), 0.1 * _rand((c,), 5)
+    got = conv2d_op(x.cuda(), w.cuda(), scale=sc, shift=sh, relu=True, use_tc=True).cpu()
+    want, _ = ref_conv(x, w, None, sc, sh, relu=True)
+    assert float((got - want).abs().max()) <= 1e-2 * max(1.0, float(want.abs().max()))
+    wd = _bf(_rand((2, 2, c, c), 6, 1.0 / np.sqrt(c)))
+    got = conv2d_op(x.cuda(), wd.cuda(), scale=sc, shift=sh, relu=True, deconv=True, use_tc=True).cpu()
+    want = ref_deconv(x, wd, sc, sh)
+    assert float((got - want).abs().max()) <= 1e-2 * max(1.0, float(want.abs().max()))
+
+
+# ---- edge-layer kernels: ragged strips (H not a multiple of the 32-row strip, odd H for the row pairs) ----
+@pytest.mark.parametrize("ks,c0,cout,H,W", [(3, 1, 32, 80, 64), (3, 2, 32, 48, 40), (5, 1, 16, 35, 24)])
+def test_first_layer_ragged(ks, c0, cout, H, W):
+    from depgan_b200 import conv2d_op, wgrad_op
+    N = 3
+    x, w = _rand((N, H, W, c0), 1), _rand((ks, ks, c0, cout), 3, 0.2)
+    sc, sh = 1 + 0.1 * _rand((cout,), 4), 0.1 * _rand((cout,), 5)
+    got = conv2d_op(x.cuda(), w.cuda(), scale=sc, shift=sh, relu=True, use_tc=False).cpu()
+    want, _ = ref_conv(x, w, None, sc, sh, relu=True)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4), float((got - want).abs().max())
+    dy = _rand((N, H, W, cout), 2)
+    got = wgrad_op(x.cuda(), dy.cuda(), ks, use_tc=False).cpu()
+    want = ref_wgrad(x, dy, ks)
+    assert float((got - want).abs().max()) <= 1e-3 * float(want.abs().max())
+
+
+def test_last_layer_ragged():
+    from depgan_b200 import conv2d_op
+    b, wd = _rand((3, 35, 24, 16), 4), _rand((5, 5, 16, 1), 5, 0.2)
+    got = conv2d_op(b.cuda(), wd.cuda(), use_tc=False).cpu()
+    want, _ = ref_conv(b, wd)
+    assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
