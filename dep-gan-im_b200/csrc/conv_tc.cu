@@ -12,20 +12,43 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode = nullptr;
 int g_num_sms = 148;
 
-CUtensorMapSwizzle swizzle_for(int kc) {
+CUtensorMapSwizzle swizzle_for(int kc) {  // kc bf16 channels = one swizzle span
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
-int make_act_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int kc, int ht) {
+int make_nhwc_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int box_c, int box_w, int box_h,
+                  const char* what) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)ht, (cuuint32_t)ht, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(box_c), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    depgan_set_error("cuTensorMapEncodeTiled(activation) failed: " + std::to_string((int)r));
+    depgan_set_error(std::string("cuTensorMapEncodeTiled(") + what + ") failed: " + std::to_string((int)r));
+    return -1;
+  }
+  return 0;
+}
+
+int make_act_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int kc, int ht) {
+  return make_nhwc_map(tm, p, C, W, H, N, kc, ht, ht, "activation");
+}
+
+// Output of the k2 s2 transposed convolution, (N, 2H, 2W, C), seen from the input grid as (c, b, w, a, n*H + h):
+// element ((n*2H + 2h + a) * 2W + 2w + b) * C + c.  One box = the [16 h][16 w] tile of one output parity (a, b).
+int make_deconv_out_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int ch) {
+  cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)W, 2, (cuuint64_t)N * H};
+  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * W * C * 2,
+                           (cuuint64_t)4 * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)ch, 1, 16, 1, 16};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(ch), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    depgan_set_error("cuTensorMapEncodeTiled(deconv output) failed: " + std::to_string((int)r));
     return -1;
   }
   return 0;
@@ -48,7 +71,9 @@ int make_w_map(CUtensorMap* tm, const void* p, int Cin, int rows, int kc, int nc
 
 uint32_t round1024(uint32_t x) { return (x + 1023u) & ~1023u; }
 
-constexpr uint32_t SMEM_BUDGET = 220 * 1024;  // one persistent CTA per SM
+constexpr uint32_t SMEM_BUDGET = 226 * 1024 - DG_TRACE_SMEM;  // one persistent CTA per SM (227 KB opt-in limit)
+
+uint32_t bar_bytes(int na, int nb) { return 8u * (2 * na + 2 * nb + 8) + 32u; }
 
 bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   const int ks = a.ks, ht = 16 + ks - 1, taps = ks * ks;
@@ -61,29 +86,38 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   const int acc_stages = 4 * ncta <= 512 ? 2 : 1;
   int tmem_cols = 32;
   while (tmem_cols < 2 * ncta * acc_stages) tmem_cols *= 2;
-  const uint32_t fixed = 1024 + 8 * 64 + 64 + 2 * ncols * 4 + 16 * a.Cout + 16 * ncta + 64;
+  // epilogue staging: ch-channel chunks of the item's [16][16] tile (a transposed-conv chunk stays inside one parity)
+  int ch = ncta % 32 == 0 ? 32 : 16;
+  if (a.deconv) ch = (a.Cout % 64 == 0 && ncta % 64 == 0) ? 64 : (a.Cout % 32 == 0 && ncta % 32 == 0) ? 32 : 16;
+  const int n_side = a.film_g ? 1 : (a.add_src ? 1 : 0) + (a.mask_src ? 1 : 0);
+  const int stage_out = a.out ? 1 : 0;
+  const uint32_t slot = 256u * ch * 2u;
+  const uint32_t staging = (stage_out ? 2u : 0u) * slot + 2u * n_side * slot;
+  const uint32_t floats = 2u * ncols * 4 + (a.head_w ? 16u * a.Cout : 0u) + (a.film_g ? 24u * ncta : 0u) + 64u;
   for (int kc = 64; kc >= 16; kc /= 2) {
     if (a.C0 % kc || a.C1 % kc) continue;
     const int nchunks = (a.C0 + a.C1) / kc;
     const uint32_t a_bytes = round1024((uint32_t)ht * ht * kc * 2), b_bytes = round1024((uint32_t)ncta * kc * 2);
-    int na, nb, resident = 0;
-    const uint32_t w_all = (uint32_t)taps * nchunks * b_bytes;
-    if (nsplit == 1 && fixed + w_all + 2 * a_bytes <= SMEM_BUDGET) {
+    int na = 0, nb = 0, resident = 0;
+    const int nb_all = taps * nchunks;
+    const uint32_t w_all = (uint32_t)nb_all * b_bytes;
+    const uint32_t fixed_res = 1024 + bar_bytes(6, nb_all) + floats + staging;
+    if (nsplit == 1 && nb_all <= 56 && fixed_res + w_all + 2 * a_bytes <= SMEM_BUDGET) {
       resident = 1;
-      nb = taps * nchunks;
-      na = (int)((SMEM_BUDGET - fixed - w_all) / a_bytes);
+      nb = nb_all;
+      na = (int)((SMEM_BUDGET - fixed_res - w_all) / a_bytes);
       if (na > 6) na = 6;
     } else {
+      const uint32_t fixed_str = 1024 + bar_bytes(3, 12) + floats + staging;
       na = 3;
-      if (fixed + na * a_bytes + 4 * b_bytes > SMEM_BUDGET) na = 2;
-      if (fixed + na * a_bytes + 3 * b_bytes > SMEM_BUDGET) {
+      if (fixed_str + na * a_bytes + 4 * b_bytes > SMEM_BUDGET) na = 2;
+      if (fixed_str + na * a_bytes + 3 * b_bytes > SMEM_BUDGET) {
         if (kc > 16) continue;
         return false;
       }
-      nb = (int)((SMEM_BUDGET - fixed - na * a_bytes) / b_bytes);
+      nb = (int)((SMEM_BUDGET - fixed_str - na * a_bytes) / b_bytes);
       if (nb > 12) nb = 12;
     }
-    if (resident && nb > 56) continue;  // barrier area holds 64 slots
     g->tiles_w = a.W / 16; g->tiles_h = a.H / 16;
     g->nchunk0 = a.C0 / kc; g->nchunk1 = a.C1 / kc;
     g->kc = kc; g->ncols_total = ncols; g->ncta = ncta; g->tmem_cols = tmem_cols;
@@ -91,7 +125,10 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
     g->a_tx = (uint32_t)ht * ht * kc * 2; g->b_tx = (uint32_t)ncta * kc * 2;
     g->layout = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
     g->b_resident = resident; g->acc_stages = acc_stages;
-    *smem_bytes = 1024 + na * a_bytes + nb * b_bytes + 8 * (2 * na + 2 * nb + 4) + 16 + 2 * ncols * 4 + 16 * a.Cout + 16 * ncta + 64;
+    // two issuers share the A ring by parity waits: safe only while the ring holds a whole item (see the kernel)
+    g->n_issuers = (resident && acc_stages == 2 && na >= nchunks) ? 2 : 1;
+    g->ch = ch; g->n_side = n_side; g->stage_out = stage_out; g->slot_bytes = slot;
+    *smem_bytes = 1024 + na * a_bytes + nb * b_bytes + staging + bar_bytes(na, nb) + floats;
     return true;
   }
   return false;
@@ -128,6 +165,8 @@ bool conv_tc_supported(const ConvArgs& a) {
   if (!a.w_tc) return false;
   if (a.head_w && (a.deconv || a.Cout > 256 || a.head_nc > 4)) return false;
   if (a.deconv && (a.film_g || a.add_src || a.mask_src)) return false;  // side inputs index the conv layout
+  if (a.film_g && (a.add_src || a.mask_src || !a.out || !a.res)) return false;
+  if (a.deconv && (a.out_pre || !a.out)) return false;
   TcGeom g;
   uint32_t smem;
   return plan(a, &g, &smem);
@@ -140,19 +179,34 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   uint32_t smem;
   DG_REQUIRE(conv_tc_supported(a) && plan(a, &g, &smem), "conv_fwd_tc: unsupported shape");
   const int ht = 16 + a.ks - 1;
-  CUtensorMap tmA0, tmA1, tmB;
-  DG_TRY(make_act_map(&tmA0, a.in0, a.C0, a.W, a.H, a.N, g.kc, ht));
-  if (a.C1 > 0) DG_TRY(make_act_map(&tmA1, a.in1, a.C1, a.W, a.H, a.N, g.kc, ht));
-  else tmA1 = tmA0;
-  DG_TRY(make_w_map(&tmB, a.w_tc, a.C0 + a.C1, a.ks * a.ks * g.ncols_total, g.kc, g.ncta));
+  TcMaps tm;
+  DG_TRY(make_act_map(&tm.a0, a.in0, a.C0, a.W, a.H, a.N, g.kc, ht));
+  if (a.C1 > 0) DG_TRY(make_act_map(&tm.a1, a.in1, a.C1, a.W, a.H, a.N, g.kc, ht));
+  else tm.a1 = tm.a0;
+  DG_TRY(make_w_map(&tm.b, a.w_tc, a.C0 + a.C1, a.ks * a.ks * g.ncols_total, g.kc, g.ncta));
+  tm.out = tm.s0 = tm.s1 = tm.a0;  // placeholders for the maps this launch does not use
+  if (a.out) {
+    if (a.deconv) DG_TRY(make_deconv_out_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch));
+    else DG_TRY(make_nhwc_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "output"));
+  }
+  // side inputs of the epilogue: the FiLM residual, or the add source followed by the mask source
+  const void* side[2] = {nullptr, nullptr};
+  if (a.film_g) side[0] = a.res;
+  else {
+    int k = 0;
+    if (a.add_src) side[k++] = a.add_src;
+    if (a.mask_src) side[k++] = a.mask_src;
+  }
+  if (side[0]) DG_TRY(make_nhwc_map(&tm.s0, side[0], a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "side input"));
+  if (side[1]) DG_TRY(make_nhwc_map(&tm.s1, side[1], a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "side input"));
   const int n_items = g.tiles_w * g.tiles_h * a.N * (g.ncols_total / g.ncta);
   const int grid = n_items < g_num_sms ? n_items : g_num_sms;
-  // side inputs the epilogue has to stream (selects the EPI instantiation): bit 0 FiLM residual, bit 1 add / mask
-  const int need = (a.film_g ? 1 : 0) | ((a.add_src || a.mask_src) ? 2 : 0);
+  // side inputs the epilogue has to stream (selects the EPI instantiation): 1 FiLM residual, 2 add / mask
+  const int need = a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : 0);
   switch (a.ks) {
-    case 1: return launch_ks1(grid, smem, st, tmA0, tmA1, tmB, a, g, need);
-    case 3: return launch_ks3(grid, smem, st, tmA0, tmA1, tmB, a, g, need);
-    case 5: return launch_ks5(grid, smem, st, tmA0, tmA1, tmB, a, g, need);
+    case 1: return launch_ks1(grid, smem, st, tm, a, g, need);
+    case 3: return launch_ks3(grid, smem, st, tm, a, g, need);
+    case 5: return launch_ks5(grid, smem, st, tm, a, g, need);
     default: depgan_set_error("conv_fwd_tc: no kernel for this kernel size"); return -2;
   }
 }

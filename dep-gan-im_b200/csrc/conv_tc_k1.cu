@@ -3,56 +3,18 @@
 
 namespace convtc {
 
-// EPI variants built for this kernel size; a call is routed to the smallest superset of its side inputs
-static int pick_epi(int need) {
-  return need == 0 ? 0 : (need == 2 ? 2 : 3);
-}
-
-int launch_ks1(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
-               const CUtensorMap& tmB, const ConvArgs& a, const TcGeom& g, int need) {
-  const int key = pick_epi(need) * 100 + (g.kc / 16) * 10 + (g.b_resident ? 1 : 0);
-  switch (key) {
-    case 10: return launch_one<1, 1, false, 0>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 11: return launch_one<1, 1, true, 0>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 20: return launch_one<1, 2, false, 0>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 21: return launch_one<1, 2, true, 0>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 40: return launch_one<1, 4, false, 0>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 41: return launch_one<1, 4, true, 0>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 210: return launch_one<1, 1, false, 2>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 211: return launch_one<1, 1, true, 2>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 220: return launch_one<1, 2, false, 2>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 221: return launch_one<1, 2, true, 2>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 240: return launch_one<1, 4, false, 2>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 241: return launch_one<1, 4, true, 2>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 310: return launch_one<1, 1, false, 3>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 311: return launch_one<1, 1, true, 3>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 320: return launch_one<1, 2, false, 3>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 321: return launch_one<1, 2, true, 3>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 340: return launch_one<1, 4, false, 3>(grid, smem, st, tmA0, tmA1, tmB, a, g);
-    case 341: return launch_one<1, 4, true, 3>(grid, smem, st, tmA0, tmA1, tmB, a, g);
+// epi = side inputs of the call: 0 none, 1 FiLM residual, 2 add / mask sources
+int launch_ks1(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi) {
+  switch (epi * 100 + (g.kc / 16) * 10 + (g.b_resident ? 1 : 0)) {
+    DG_TC_CASES(1, 0)
+    DG_TC_CASES(1, 2)
     default: depgan_set_error("conv_fwd_tc: no kernel for this (ks, kc, epi)"); return -2;
   }
 }
 
 int set_attrs_ks1() {
-  DG_TRY((set_attr_one<1, 1, false, 0>()));
-  DG_TRY((set_attr_one<1, 1, true, 0>()));
-  DG_TRY((set_attr_one<1, 2, false, 0>()));
-  DG_TRY((set_attr_one<1, 2, true, 0>()));
-  DG_TRY((set_attr_one<1, 4, false, 0>()));
-  DG_TRY((set_attr_one<1, 4, true, 0>()));
-  DG_TRY((set_attr_one<1, 1, false, 2>()));
-  DG_TRY((set_attr_one<1, 1, true, 2>()));
-  DG_TRY((set_attr_one<1, 2, false, 2>()));
-  DG_TRY((set_attr_one<1, 2, true, 2>()));
-  DG_TRY((set_attr_one<1, 4, false, 2>()));
-  DG_TRY((set_attr_one<1, 4, true, 2>()));
-  DG_TRY((set_attr_one<1, 1, false, 3>()));
-  DG_TRY((set_attr_one<1, 1, true, 3>()));
-  DG_TRY((set_attr_one<1, 2, false, 3>()));
-  DG_TRY((set_attr_one<1, 2, true, 3>()));
-  DG_TRY((set_attr_one<1, 4, false, 3>()));
-  DG_TRY((set_attr_one<1, 4, true, 3>()));
+  DG_TC_ATTRS(1, 0)
+  DG_TC_ATTRS(1, 2)
   return 0;
 }
 

@@ -21,13 +21,14 @@
 //     When every (chunk, tap) tile of the layer fits next to the activation ring (32->32 ... 96->96 3x3 layers)
 //     the weights are loaded ONCE per CTA and stay resident (template RES).
 //   * Persistent: grid = min(#work items, #SMs), one CTA per SM looping over (tile, n-split) items.
-//     warp 0 = TMA producer, warp 1 = MMA issuer (tcgen05.mma.cta_group::1.kind::f16), warps 4..11 = fused epilogue
-//     straight out of TMEM.  Two TMEM accumulator stages (when 4*ncta <= 512 columns) overlap the epilogue of
-//     item i with the MMA stream of item i+1; the producer runs ahead across items.
-//   * Epilogue (template EPI = which global side inputs exist: bit 0 FiLM residual, bit 1 add / mask sources):
-//     the side inputs of the next PF 16-channel chunks -- across item boundaries -- are always in flight in a
-//     register ring, and the tcgen05.ld of chunk j+1 is issued before chunk j is processed, so neither the L2/HBM
-//     nor the TMEM read latency is paid per chunk.
+//     Control warps: TMA producer of the A/B rings, TMA producer of the epilogue side inputs, and two MMA issuers
+//     (tcgen05.mma.cta_group::1.kind::f16), one per TMEM accumulator stage (4*ncta <= 512 columns), so the barrier
+//     round trips between two items of one issuer are covered by the other issuer's MMA stream.
+//   * Epilogue (8 warps, thread = one pixel = one TMEM lane; template EPI = which side inputs exist: 1 FiLM residual,
+//     2 add / mask sources) never touches global memory with per-thread accesses: side inputs arrive as TMA tiles
+//     [16][16][ch] in a 2-stage ring, results are packed to bf16 into a swizzled staging tile and leave by one TMA
+//     store per ch-channel chunk (5-D map for the transposed conv's 2x2 scatter), double-buffered with bulk-group
+//     waits.  The TMEM stage is handed back to the issuer as soon as its last column is in registers.
 #pragma once
 #include <cuda.h>
 
@@ -48,15 +49,22 @@ struct TcGeom {
   uint32_t layout;            // UMMA smem layout type (2 = SW128, 4 = SW64, 6 = SW32)
   int b_resident;             // 1: all (chunk, tap) weight tiles live in smem for the CTA's lifetime
   int acc_stages;             // TMEM accumulator stages (2 when 4*ncta <= 512)
+  int n_issuers;              // MMA issuer warps (2: one per accumulator stage)
+  int ch;                     // channels per epilogue staging chunk (16 / 32 / 64 = one 32/64/128-byte swizzle span)
+  int n_side;                 // side-input tensors TMA-loaded per chunk (FiLM residual; add and/or mask sources)
+  int stage_out;              // 1: `out` is written tile-wise from shared memory by TMA stores
+  uint32_t slot_bytes;        // one staging tile: 256 pixels x ch x 2 bytes
+};
+
+// tensor maps of one launch: activations (two concatenated sources), weights, output, epilogue side inputs
+struct TcMaps {
+  CUtensorMap a0, a1, b, out, s0, s1;
 };
 
 // one launcher per kernel size, defined in conv_tc_k{1,3,5}.cu; epi = bit mask of the side inputs the call uses
-int launch_ks1(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
-               const CUtensorMap& tmB, const ConvArgs& a, const TcGeom& g, int epi);
-int launch_ks3(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
-               const CUtensorMap& tmB, const ConvArgs& a, const TcGeom& g, int epi);
-int launch_ks5(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
-               const CUtensorMap& tmB, const ConvArgs& a, const TcGeom& g, int epi);
+int launch_ks1(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi);
+int launch_ks3(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi);
+int launch_ks5(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi);
 int set_attrs_ks1();
 int set_attrs_ks3();
 int set_attrs_ks5();
@@ -108,12 +116,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+#ifdef DG_DBG_NOMMA  // timing experiment only (scripts/build_variant.sh): results are garbage
+  return;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -158,6 +180,10 @@ struct Packed16 {  // 16 bf16 values as loaded (two 128-bit words)
   }
 };
 __device__ __forceinline__ void st16_bf16(void* base, size_t elem_off, const float (&v)[16]) {
+#ifdef DG_DBG_NOSTORE  // timing experiment only: keeps the values alive without a global store
+  if (v[0] == 1.2345e-30f && v[7] == 5.4321e-30f) reinterpret_cast<float*>(base)[0] = v[3];
+  return;
+#endif
   uint4 q[2];
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
 #pragma unroll
@@ -167,14 +193,42 @@ __device__ __forceinline__ void st16_bf16(void* base, size_t elem_off, const flo
   p[1] = q[1];
 }
 
-constexpr int TC_THREADS = 384;  // warpgroup 0: producer, MMA issuer, 2 idle warps; warpgroups 1-2: epilogue
-constexpr int EPI_PF = 4;  // side-input lookahead of the epilogue, in 16-channel chunks
+#ifdef DG_DBG_TRACE  // timing experiment only (scripts/build_variant.sh): per-role event clocks of CTA 0
+__device__ long long* g_dbg_trace = nullptr;  // [role 0..2][item 0..39][event 0..7], dumped from shared memory at exit
+#define DG_TRACE_DECL __shared__ uint32_t s_trace[3 * 40 * 8];
+#define DG_TRACE_SMEM 4096
+#define DG_TRACE(role_, item_, ev_)                                                                       \
+  do {                                                                                                    \
+    if (blockIdx.x == 0 && (item_) < 40 && (threadIdx.x & 31) == 0)                                       \
+      s_trace[((role_) * 40 + (item_)) * 8 + (ev_)] = (uint32_t)clock64();                                \
+  } while (0)
+#define DG_TRACE_DUMP                                                                                     \
+  do {                                                                                                    \
+    if (blockIdx.x == 0 && g_dbg_trace)                                                                   \
+      for (int i_ = threadIdx.x; i_ < 3 * 40 * 8; i_ += blockDim.x) g_dbg_trace[i_] = s_trace[i_];        \
+  } while (0)
+#else
+#define DG_TRACE_DECL
+#define DG_TRACE_SMEM 0
+#define DG_TRACE(role_, item_, ev_) do {} while (0)
+#define DG_TRACE_DUMP do {} while (0)
+#endif
+
+constexpr int TC_THREADS = 384;  // two epilogue warpgroups (warps 0..7) + one control warpgroup (warps 8..11)
+// The warp scheduler favours the highest warp id of a sub-partition, so the latency-critical single-warp roles sit in
+// the LAST warpgroup and the instruction-heavy epilogue in warps 0..7.
+constexpr int CTRL_W0 = 8;  // first control warp
+constexpr int EPI_W0 = 0;   // first epilogue warp
 
 struct Ring {
   int idx = 0;
   uint32_t phase = 0;
   __device__ __forceinline__ void advance(int n) {
     if (++idx == n) { idx = 0; phase ^= 1u; }
+  }
+  __device__ __forceinline__ void skip(int k, int n) {  // k stages ahead
+    idx += k;
+    while (idx >= n) { idx -= n; phase ^= 1u; }
   }
 };
 
@@ -189,33 +243,37 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// kernel: persistent, warp-specialised.  warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-3 idle
-// (they only complete warpgroup 0 so it can hand its registers over with setmaxnreg), warps 4..11 = epilogue
-// (warp w reads TMEM lane quarter w%4 of strip (w-4)/4) running with the registers warpgroup 0 gave up.
+// kernel: persistent, warp-specialised, 12 warps.
+//   control warpgroup (warps 8..11): 8 = TMA producer of the A / B rings, 9 = MMA issuer 0 + TMEM owner,
+//     10 = TMA producer of the epilogue's side-input tiles, 11 = MMA issuer 1.
+//   epilogue warps 0..7 (warp w reads TMEM lane quarter w%4 of strip w/4), running with the registers the control
+//     warpgroup gave up.
 // ---------------------------------------------------------------------------------------------------------
 template <int KS, int KSTEPS, bool RES, int EPI>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                                const __grid_constant__ CUtensorMap tmA1,
-                                                                const __grid_constant__ CUtensorMap tmB,
-                                                                const ConvArgs a, const TcGeom g) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps tm, const ConvArgs a,
+                                                                const TcGeom g) {
   constexpr int PAD = KS / 2, HT = 16 + KS - 1, TAPS = KS * KS;
   extern __shared__ uint8_t smem_raw[];
+  DG_TRACE_DECL
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + g.na * g.a_bytes;
-  const uint32_t bar_base = b_base + g.nb * g.b_bytes;
+  const uint32_t o_base = b_base + g.nb * g.b_bytes;                       // 2 output staging slots
+  const uint32_t s_base = o_base + (g.stage_out ? 2u * g.slot_bytes : 0u);  // 2 side stages x n_side slots
+  const uint32_t bar_base = s_base + 2u * g.n_side * g.slot_bytes;
   const uint32_t fullA = bar_base, emptyA = fullA + 8 * g.na;
   const uint32_t fullB = emptyA + 8 * g.na, emptyB = fullB + 8 * g.nb;
   const uint32_t accFull = emptyB + 8 * g.nb, accEmpty = accFull + 16;
-  const uint32_t tmem_slot = accEmpty + 16;
+  const uint32_t sideFull = accEmpty + 16, sideEmpty = sideFull + 16;
+  const uint32_t tmem_slot = sideEmpty + 16;
   const uint32_t ss_off = tmem_slot + 16;  // scale / shift staging: 2 * ncols_total floats, then head weights
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* s_scale = reinterpret_cast<float*>(smem_raw + (ss_off - raw));
   float* s_shift = s_scale + g.ncols_total;
   float4* s_head = reinterpret_cast<float4*>(s_shift + g.ncols_total);  // [Cout] x (up to 4 head outputs)
-  // FiLM folded with BN per (sample, channel): [2 slots][2][ncta] floats, rebuilt per work item by the epilogue warps
-  float* s_film = reinterpret_cast<float*>(s_head + a.Cout);
+  // FiLM folded with BN per (sample, channel): [3 slots][2][ncta] floats, slot k%3 belongs to the CTA's k-th item
+  float* s_film = reinterpret_cast<float*>(s_head + (a.head_w ? a.Cout : 0));
 
   // warp index made provably warp-uniform so the role loops run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -224,14 +282,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int nsplit = g.ncols_total / g.ncta;
   const int tiles_per_img = g.tiles_w * g.tiles_h;
   const int n_items = tiles_per_img * a.N * nsplit;
+  const int nco = g.ncta / g.ch;  // staging chunks per item
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < g.na; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
     for (int i = 0; i < g.nb; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(accFull + 8 * i, 1); mbar_init(accEmpty + 8 * i, 8);
+      mbar_init(sideFull + 8 * i, 1); mbar_init(sideEmpty + 8 * i, 8);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == CTRL_W0 + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(g.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -256,32 +318,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int acc_stride = g.acc_stages == 2 ? g.tmem_cols / 2 : 0;
 
-  if (warp < 4) {
+  if (warp >= CTRL_W0) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-  if (warp == 0) {
-    // ===== TMA producer (whole warp runs the loops; one elected lane issues) =====
+  if (warp == CTRL_W0) {
+    // ===== TMA producer of the operand rings (whole warp runs the loops; one elected lane issues) =====
     if (RES) {  // all weights of the layer stay in shared memory for the CTA's lifetime
       if (elect_one()) {
         mbar_expect_tx(fullB, g.b_tx * TAPS * nchunks);
         for (int c = 0; c < nchunks; ++c) {
           const int kglob = c < g.nchunk0 ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
           for (int tap = 0; tap < TAPS; ++tap)
-            tma_load_2d(b_base + (c * TAPS + tap) * g.b_bytes, &tmB, fullB, kglob, tap * g.ncols_total);
+            tma_load_2d(b_base + (c * TAPS + tap) * g.b_bytes, &tm.b, fullB, kglob, tap * g.ncols_total);
         }
       }
       __syncwarp();
     }
     Ring ra, rb;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+    int p_it = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++p_it) {
       const int ns = it % nsplit, t = it / nsplit;
       const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
       const int w0 = tw * 16, h0 = th * 16, n0 = ns * g.ncta;
+      DG_TRACE(0, p_it, 0);
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(emptyA + 8 * ra.idx, ra.phase ^ 1u);
+        if (c == 0) DG_TRACE(0, p_it, 1);
         const bool first = c < g.nchunk0;
         if (elect_one()) {
           mbar_expect_tx(fullA + 8 * ra.idx, g.a_tx);
-          tma_load_4d(a_base + ra.idx * g.a_bytes, first ? &tmA0 : &tmA1, fullA + 8 * ra.idx,
+          tma_load_4d(a_base + ra.idx * g.a_bytes, first ? &tm.a0 : &tm.a1, fullA + 8 * ra.idx,
                       (first ? c : c - g.nchunk0) * g.kc, w0 - PAD, h0 - PAD, n);
         }
         __syncwarp();
@@ -292,36 +357,69 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             mbar_wait(emptyB + 8 * rb.idx, rb.phase ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(fullB + 8 * rb.idx, g.b_tx);
-              tma_load_2d(b_base + rb.idx * g.b_bytes, &tmB, fullB + 8 * rb.idx, kglob, tap * g.ncols_total + n0);
+              tma_load_2d(b_base + rb.idx * g.b_bytes, &tm.b, fullB + 8 * rb.idx, kglob, tap * g.ncols_total + n0);
             }
             __syncwarp();
             rb.advance(g.nb);
           }
         }
       }
+      DG_TRACE(0, p_it, 2);
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer (whole warp converged, one elected lane issues tcgen05.mma / commit) =====
+  } else if (warp == CTRL_W0 + 2) {
+    // ===== TMA producer of the epilogue's side-input tiles (FiLM residual, or add / mask sources) =====
+    if (EPI != 0 && g.n_side > 0) {
+      Ring rs;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int ns = it % nsplit, t = it / nsplit;
+        const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
+        for (int cc = 0; cc < nco; ++cc) {
+          mbar_wait(sideEmpty + 8 * rs.idx, rs.phase ^ 1u);
+          if (elect_one()) {
+            const uint32_t dst = s_base + (uint32_t)(rs.idx * g.n_side) * g.slot_bytes;
+            mbar_expect_tx(sideFull + 8 * rs.idx, (uint32_t)g.n_side * g.slot_bytes);
+            tma_load_4d(dst, &tm.s0, sideFull + 8 * rs.idx, ns * g.ncta + cc * g.ch, tw * 16, th * 16, n);
+            if (g.n_side == 2)
+              tma_load_4d(dst + g.slot_bytes, &tm.s1, sideFull + 8 * rs.idx, ns * g.ncta + cc * g.ch, tw * 16, th * 16, n);
+          }
+          __syncwarp();
+          rs.advance(2);
+        }
+      }
+    }
+  } else {
+    // ===== MMA issuers (whole warp converged, one elected lane issues tcgen05.mma / commit) =====
+    // Issuer m takes the CTA's items m, m + n_issuers, ... and owns accumulator stage m, so while one issuer sits in
+    // the barrier waits between two of its items the other keeps the tensor pipe fed.
     // Descriptors: the high word (SBO, version, swizzle mode) is constant; per MMA only the 14-bit start
     // address field of the low word moves, in 16-byte units.
+    const int m = warp == CTRL_W0 + 1 ? 0 : 1;
+    const int nI = g.n_issuers;
+    if (m < nI) {
     const uint32_t idesc = make_idesc(g.ncta);
     const uint32_t hiA = ((uint32_t)(HT * rowb) >> 4) | (1u << 14) | (g.layout << 29);
     const uint32_t hiB = ((uint32_t)(8 * rowb) >> 4) | (1u << 14) | (g.layout << 29);
     constexpr uint32_t LBO1 = 1u << 16;
     constexpr uint32_t ROW16 = rowb / 16;  // one pixel row in descriptor units
     Ring ra, rb;
-    int k_it = 0;
+    ra.skip(m * nchunks, g.na);
     if (RES) mbar_wait(fullB, 0);
     const uint32_t b_step = g.b_bytes >> 4;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++k_it) {
-      const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
-      const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
-      mbar_wait(accEmpty + 8 * as, (use & 1u) ^ 1u);
+    const int as = g.acc_stages == 2 ? (nI == 2 ? m : 0) : 0;
+    int k_it = 0;  // this issuer's item counter
+    for (int it = blockIdx.x + m * gridDim.x; it < n_items; it += nI * gridDim.x, ++k_it) {
+      // single issuer with two stages alternates them; otherwise the stage is fixed
+      const int st = (g.acc_stages == 2 && nI == 1) ? (k_it & 1) : as;
+      const uint32_t use = (g.acc_stages == 2 && nI == 1) ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
+      if (m == 0) DG_TRACE(1, k_it, 0);
+      mbar_wait(accEmpty + 8 * st, (use & 1u) ^ 1u);
       tc_fence_after();
-      const uint32_t d0 = tmem_base + as * acc_stride, d1 = d0 + g.ncta;
+      if (m == 0) DG_TRACE(1, k_it, 1);
+      const uint32_t d0 = tmem_base + st * acc_stride, d1 = d0 + g.ncta;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(fullA + 8 * ra.idx, ra.phase);
         tc_fence_after();
+        if (c == 0 && m == 0) DG_TRACE(1, k_it, 2);
         const uint32_t a_lo = (((a_base + ra.idx * g.a_bytes) & 0x3FFFFu) >> 4) | LBO1;
         const uint32_t accc = (uint32_t)(c != 0);
         if (RES) {
@@ -368,57 +466,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         ra.advance(g.na);
       }
-      if (elect_one()) tc_commit(accFull + 8 * as);
+      if (elect_one()) tc_commit(accFull + 8 * st);
       __syncwarp();
+      if (m == 0) DG_TRACE(1, k_it, 3);
+      if (nI == 2) ra.skip(nchunks, g.na);  // the other issuer's item
+    }
     }
   }
   } else {
-    // ===== epilogue warps: TMEM -> registers -> global =====
+    // ===== epilogue warps: TMEM -> registers -> (staging tile in shared memory -> TMA store) =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     constexpr bool E_RES = (EPI & 1) != 0, E_AM = (EPI & 2) != 0;
-    const int ew = warp - 4;
+    const int ew = warp - EPI_W0;
     const int strip = ew >> 2;
     const int q = warp & 3;          // TMEM lane quarter this warp may read
     const int r = q * 32 + lane;     // accumulator row
     const int ty = r >> 3, tx = strip * 8 + (r & 7);
     const int Cout = a.Cout;
-    const int nj = g.ncta / 16;
+    const int ng = g.ncta / 16;       // 16-column groups per item
+    const int gpc = g.ch / 16;        // groups per staging chunk
     const bool has_film = E_RES && a.film_g != nullptr;
     const bool has_add = E_AM && a.add_src != nullptr;
     const bool has_mask = E_AM && a.mask_src != nullptr;
+    const bool side = EPI != 0 && g.n_side > 0;
+    const bool stage_out = g.stage_out != 0;
+    const bool t0 = threadIdx.x == EPI_W0 * 32;  // issues the TMA stores
     const int step = (int)gridDim.x;
+    // this thread's pixel in a staging tile [16 rows][16 cols][ch] whose 16-byte units are XOR-swizzled like the TMA
+    // (unit j of the pixel at byte offset o lives at o + ((j ^ ((o >> 7) & (units-1))) << 4)): conflict-free 128-bit
+    // accesses for 8 neighbouring pixels
+    const uint32_t p_off = (uint32_t)(ty * 16 + tx) * (uint32_t)(g.ch * 2);
+    const uint32_t p_xor = (p_off >> 7) & (uint32_t)(g.ch / 8 - 1);
+    const uint32_t add_slot = 0, mask_slot = has_add ? g.slot_bytes : 0u;
 
-    // element offset of (item, this thread's pixel, first column of the item); side inputs never come with deconv
-    auto item_base = [&](int it_) -> size_t {
-      const int ns_ = it_ % nsplit, t_ = it_ / nsplit;
-      const int tw_ = t_ % g.tiles_w, th_ = (t_ / g.tiles_w) % g.tiles_h, n_ = t_ / tiles_per_img;
-      return (((size_t)n_ * a.H + th_ * 16 + ty) * a.W + tw_ * 16 + tx) * Cout + ns_ * g.ncta;
-    };
-
-    // ---- side-input ring: chunks (it_pf, j_pf) .. are in flight, EPI_PF ahead of the chunk being processed ----
-    Packed16 ring_res[EPI_PF], ring_add[EPI_PF], ring_mk[EPI_PF];
-    int it_pf = blockIdx.x, j_pf = 0;
-    size_t base_pf = 0;
-    if (EPI != 0 && it_pf < n_items) base_pf = item_base(it_pf);
-#define DG_EPI_ISSUE(S_)                                                        \
-  do {                                                                          \
-    if (EPI != 0 && it_pf < n_items) {                                          \
-      const size_t off_ = base_pf + (size_t)j_pf * 16;                          \
-      if (has_film) ring_res[S_].load(a.res, off_);                             \
-      if (has_add) ring_add[S_].load(a.add_src, off_);                          \
-      if (has_mask) ring_mk[S_].load(a.mask_src, off_);                         \
-      if (++j_pf == nj) {                                                       \
-        j_pf = 0;                                                               \
-        it_pf += step;                                                          \
-        if (it_pf < n_items) base_pf = item_base(it_pf);                        \
-      }                                                                         \
-    }                                                                           \
-  } while (0)
-#pragma unroll
-    for (int s = 0; s < EPI_PF; ++s) DG_EPI_ISSUE(s);
-
-    // FiLM (gamma, beta) of the NEXT item's sample for this thread's table column, fetched one item ahead
-    const int fc = ew * 32 + lane;  // column of the per-item FiLM table this thread fills (ncta <= 256)
+    // FiLM (gamma, beta) for this thread's column of the per-item table, fetched two items ahead
+    const int fc = ew * 32 + lane;  // table column this thread fills (ncta <= 256)
     float fg_next = 0.f, fb_next = 0.f;
     auto film_fetch = [&](int it_) {
       if (has_film && it_ < n_items && fc < g.ncta) {
@@ -427,186 +509,236 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         fb_next = __ldg(a.film_b + (size_t)n_ * a.film_stride + ns_ * g.ncta + fc);
       }
     };
-    film_fetch(blockIdx.x);
+    auto film_fill = [&](int it_, int slot_) {  // v = relu(acc*(s*g) + (t*g + b)) + res
+      if (has_film && it_ < n_items && fc < g.ncta) {
+        const int n0_ = (it_ % nsplit) * g.ncta;
+        float* sF_ = s_film + slot_ * 2 * g.ncta;
+        sF_[fc] = s_scale[n0_ + fc] * fg_next;
+        sF_[g.ncta + fc] = fmaf(s_shift[n0_ + fc], fg_next, fb_next);
+      }
+    };
+    if (has_film) {
+      film_fetch(blockIdx.x);
+      film_fill(blockIdx.x, 0);
+      film_fetch(blockIdx.x + step);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
 
-    // ---- per-item state ----
-    int it = blockIdx.x, j = 0, k_it = 0;
-    int n = 0, h = 0, w = 0, n0 = 0, as = 0;
-    size_t pix0 = 0;
-    uint32_t t_row = 0;
-    float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float* sF = s_film;
+    Ring rs;             // side-input stages
+    uint32_t oslot = 0;  // output staging slot of the next chunk
+    int k_it = 0;
     uint32_t vn[16];
-
-    while (it < n_items) {
+    for (int it = blockIdx.x; it < n_items; it += step, ++k_it) {
+      const int ns = it % nsplit, t = it / nsplit;
+      const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h;
+      const int n = t / tiles_per_img;
+      const int h = th * 16 + ty, w = tw * 16 + tx, n0 = ns * g.ncta;
+      const size_t pix0 = ((size_t)n * a.H + h) * a.W + w;
+      const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
+      const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
+      const float* sF = s_film + (k_it % 3) * 2 * g.ncta;
+      if (has_film) {
+        // table of the NEXT item: its slot was last read two items ago, and every thread passes one of this item's
+        // chunk barriers between this write and the reads
+        film_fill(it + step, (k_it + 1) % 3);
+        film_fetch(it + 2 * step);
+      }
+      float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
+      if (ew == 0) DG_TRACE(2, k_it, 0);
+      mbar_wait(accFull + 8 * as, use & 1u);
+      tc_fence_after();
+      if (ew == 0) DG_TRACE(2, k_it, 1);
+      const uint32_t t_row = tmem_base + as * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(strip * g.ncta);
+      tc_ld16_issue(t_row, vn);
+      int gg = 0, cc = 0;
+      for (int gi = 0; gi < ng; ++gi) {
+        if (gg == 0 && side) mbar_wait(sideFull + 8 * rs.idx, rs.phase);
+        // accumulator group gi has landed; start group gi+1's TMEM read before working on gi
+        tc_ld_wait(vn);
+        if (ew == 0 && gi == 0) DG_TRACE(2, k_it, 3);
+        float v[16];
 #pragma unroll
-      for (int s = 0; s < EPI_PF; ++s) {
-        if (it < n_items) {
-          if (j == 0) {
-            // ---- item start ----
-            const int ns = it % nsplit, t = it / nsplit;
-            const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h;
-            n = t / tiles_per_img;
-            h = th * 16 + ty; w = tw * 16 + tx; n0 = ns * g.ncta;
-            pix0 = ((size_t)n * a.H + h) * a.W + w;
-            as = g.acc_stages == 2 ? (k_it & 1) : 0;
-            const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
-            if (has_film) {
-              // FiLM folded into the BN affine for this item's sample: v = relu(acc*(s*g) + (t*g + b)) + res
-              sF = s_film + (k_it & 1) * 2 * g.ncta;
-              if (fc < g.ncta) {
-                sF[fc] = s_scale[n0 + fc] * fg_next;
-                sF[g.ncta + fc] = fmaf(s_shift[n0 + fc], fg_next, fb_next);
-              }
-              // all 8 epilogue warps: the slot is complete, and every warp has left the item that last used it
-              asm volatile("bar.sync 1, 256;" ::: "memory");
-              film_fetch(it + step);
-            }
-            head_acc[0] = head_acc[1] = head_acc[2] = head_acc[3] = 0.f;
-            mbar_wait(accFull + 8 * as, use & 1u);
-            tc_fence_after();
-            t_row = tmem_base + as * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(strip * g.ncta);
-            tc_ld16_issue(t_row, vn);
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vn[i]);
+        if (gi + 1 < ng) {
+          tc_ld16_issue(t_row + (uint32_t)((gi + 1) * 16), vn);
+        } else {
+          // all of this item's accumulator is in registers: hand the TMEM stage back before the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accEmpty + 8 * as);
+        }
+        const int col = n0 + gi * 16;
+        // the two 16-byte units of this group inside the thread's staging pixel
+        const uint32_t u0 = p_off + ((((uint32_t)(2 * gg)) ^ p_xor) << 4), u1 = p_off + ((((uint32_t)(2 * gg + 1)) ^ p_xor) << 4);
+        const uint8_t* sgen = smem_raw + (s_base + (uint32_t)(rs.idx * g.n_side) * g.slot_bytes - raw);
+        if (has_film) {
+          if (a.out_pre) {
+            float vp[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) vp[i] = fmaf(v[i], s_scale[col + i], s_shift[col + i]);
+            st16_bf16(a.out_pre, pix0 * Cout + col, vp);
           }
-          // this chunk's side inputs leave the ring; the slot is refilled EPI_PF chunks ahead
-          Packed16 rs, ad, mk;
-          if (has_film) rs = ring_res[s];
-          if (has_add) ad = ring_add[s];
-          if (has_mask) mk = ring_mk[s];
-          DG_EPI_ISSUE(s);
-          // accumulator chunk j has landed; start chunk j+1's TMEM read before working on j
-          tc_ld_wait(vn);
-          float v[16];
+          Packed16 rs16;
+          rs16.q[0] = *reinterpret_cast<const uint4*>(sgen + u0);
+          rs16.q[1] = *reinterpret_cast<const uint4*>(sgen + u1);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vn[i]);
-          if (j + 1 < nj) tc_ld16_issue(t_row + (uint32_t)((j + 1) * 16), vn);
-
-          const int col = n0 + j * 16;
-          int c0 = col;
-          size_t opix = pix0;
-          if (a.deconv) {
-            const int ab = col / Cout;
-            c0 = col - ab * Cout;
-            opix = ((size_t)n * 2 * a.H + 2 * h + (ab >> 1)) * (2 * a.W) + 2 * w + (ab & 1);
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 sc = reinterpret_cast<const float4*>(sF + gi * 16)[i4];
+            const float4 sh = reinterpret_cast<const float4*>(sF + g.ncta + gi * 16)[i4];
+            v[4 * i4 + 0] = fmaxf(fmaf(v[4 * i4 + 0], sc.x, sh.x), 0.f) + rs16.get(4 * i4 + 0);
+            v[4 * i4 + 1] = fmaxf(fmaf(v[4 * i4 + 1], sc.y, sh.y), 0.f) + rs16.get(4 * i4 + 1);
+            v[4 * i4 + 2] = fmaxf(fmaf(v[4 * i4 + 2], sc.z, sh.z), 0.f) + rs16.get(4 * i4 + 2);
+            v[4 * i4 + 3] = fmaxf(fmaf(v[4 * i4 + 3], sc.w, sh.w), 0.f) + rs16.get(4 * i4 + 3);
           }
-          const size_t off = opix * Cout + c0;
-          if (has_film) {
-            if (a.out_pre) {
-              float vp[16];
+        } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) vp[i] = fmaf(v[i], s_scale[col + i], s_shift[col + i]);
-              st16_bf16(a.out_pre, off, vp);
-            }
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 sc = reinterpret_cast<const float4*>(sF + j * 16)[i4];
-              const float4 sh = reinterpret_cast<const float4*>(sF + g.ncta + j * 16)[i4];
-              v[4 * i4 + 0] = fmaxf(fmaf(v[4 * i4 + 0], sc.x, sh.x), 0.f) + rs.get(4 * i4 + 0);
-              v[4 * i4 + 1] = fmaxf(fmaf(v[4 * i4 + 1], sc.y, sh.y), 0.f) + rs.get(4 * i4 + 1);
-              v[4 * i4 + 2] = fmaxf(fmaf(v[4 * i4 + 2], sc.z, sh.z), 0.f) + rs.get(4 * i4 + 2);
-              v[4 * i4 + 3] = fmaxf(fmaf(v[4 * i4 + 3], sc.w, sh.w), 0.f) + rs.get(4 * i4 + 3);
-            }
-          } else {
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 sc = reinterpret_cast<const float4*>(s_scale + col)[i4];
-              const float4 sh = reinterpret_cast<const float4*>(s_shift + col)[i4];
-              v[4 * i4 + 0] = fmaf(v[4 * i4 + 0], sc.x, sh.x);
-              v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc.y, sh.y);
-              v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
-              v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
-            }
-            if (a.out_pre) st16_bf16(a.out_pre, off, v);
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 sc = reinterpret_cast<const float4*>(s_scale + col)[i4];
+            const float4 sh = reinterpret_cast<const float4*>(s_shift + col)[i4];
+            v[4 * i4 + 0] = fmaf(v[4 * i4 + 0], sc.x, sh.x);
+            v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc.y, sh.y);
+            v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
+            v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
           }
-          if (has_add) {
+          if (a.out_pre) st16_bf16(a.out_pre, pix0 * Cout + col, v);
+        }
+        if (has_add) {
+          Packed16 ad;
+          ad.q[0] = *reinterpret_cast<const uint4*>(sgen + add_slot + u0);
+          ad.q[1] = *reinterpret_cast<const uint4*>(sgen + add_slot + u1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += ad.get(i);
-          }
-          if (has_mask) {
+          for (int i = 0; i < 16; ++i) v[i] += ad.get(i);
+        }
+        if (has_mask) {
+          Packed16 mk;
+          mk.q[0] = *reinterpret_cast<const uint4*>(sgen + mask_slot + u0);
+          mk.q[1] = *reinterpret_cast<const uint4*>(sgen + mask_slot + u1);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = mk.get(i) > 0.f ? v[i] : 0.f;
-          }
-          if (a.relu) {
+          for (int i = 0; i < 16; ++i) v[i] = mk.get(i) > 0.f ? v[i] : 0.f;
+        }
+        if (a.relu) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (a.out) st16_bf16(a.out, off, v);
-          if (a.head_w) {
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (stage_out) {
+          uint4 pk[2];
+          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float4 hw = s_head[c0 + i];
-              head_acc[0] = fmaf(v[i], hw.x, head_acc[0]);
-              head_acc[1] = fmaf(v[i], hw.y, head_acc[1]);
-              head_acc[2] = fmaf(v[i], hw.z, head_acc[2]);
-              head_acc[3] = fmaf(v[i], hw.w, head_acc[3]);
-            }
+          for (int i = 0; i < 8; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          uint8_t* ogen = smem_raw + (o_base + oslot * g.slot_bytes - raw);
+          *reinterpret_cast<uint4*>(ogen + u0) = pk[0];
+          *reinterpret_cast<uint4*>(ogen + u1) = pk[1];
+        }
+        if (a.head_w) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float4 hw = s_head[col + i];
+            head_acc[0] = fmaf(v[i], hw.x, head_acc[0]);
+            head_acc[1] = fmaf(v[i], hw.y, head_acc[1]);
+            head_acc[2] = fmaf(v[i], hw.z, head_acc[2]);
+            head_acc[3] = fmaf(v[i], hw.w, head_acc[3]);
           }
-
-          if (++j == nj) {
-            // ---- item end: hand the accumulator stage back to the MMA issuer, write the fused head ----
-            tc_fence_before();
+        }
+        if (++gg == gpc) {
+          // ---- staging chunk cc complete ----
+          if (side) {
             __syncwarp();
-            if (lane == 0) mbar_arrive(accEmpty + 8 * as);
-            if (a.head_w) {
-              const int nc = a.head_nc;
-              float o0 = head_acc[0] + __ldg(a.head_b), o1 = 0.f, o2 = 0.f, o3 = 0.f;
-              if (nc > 1) o1 = head_acc[1] + __ldg(a.head_b + 1);
-              if (nc > 2) o2 = head_acc[2] + __ldg(a.head_b + 2);
-              if (nc > 3) o3 = head_acc[3] + __ldg(a.head_b + 3);
-              if (a.head_act == 0) {
-                o0 = tanhf(o0); o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3);
-              } else if (a.head_act == 1) {
-                float m = o0;
-                if (nc > 1) m = fmaxf(m, o1);
-                if (nc > 2) m = fmaxf(m, o2);
-                if (nc > 3) m = fmaxf(m, o3);
-                o0 = expf(o0 - m);
-                o1 = nc > 1 ? expf(o1 - m) : 0.f;
-                o2 = nc > 2 ? expf(o2 - m) : 0.f;
-                o3 = nc > 3 ? expf(o3 - m) : 0.f;
-                const float inv = 1.0f / (o0 + o1 + o2 + o3);
-                o0 *= inv; o1 *= inv; o2 *= inv; o3 *= inv;
-              }
-              if (nc == 4) {
-                *reinterpret_cast<float4*>(a.head_out + pix0 * 4) = make_float4(o0, o1, o2, o3);
-              } else {
-                float* op = a.head_out + pix0 * nc;
-                op[0] = o0;
-                if (nc > 1) op[1] = o1;
-                if (nc > 2) op[2] = o2;
-              }
-            }
-            j = 0;
-            it += step;
-            ++k_it;
+            if (lane == 0) mbar_arrive(sideEmpty + 8 * rs.idx);
+            rs.advance(2);
           }
+          if (stage_out) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            // the previous chunk's store has drained its slot before anyone passes the barrier and refills it
+            if (t0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (t0) {
+              const uint32_t src = o_base + oslot * g.slot_bytes;
+              const int c0 = n0 + cc * g.ch;
+              if (a.deconv) {
+                const int ab = c0 / Cout;
+                tma_store_5d(&tm.out, src, c0 - ab * Cout, ab & 1, tw * 16, ab >> 1, n * a.H + th * 16);
+              } else {
+                tma_store_4d(&tm.out, src, c0, tw * 16, th * 16, n);
+              }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            oslot ^= 1u;
+          }
+          gg = 0;
+          ++cc;
+        }
+      }
+      if (ew == 0) DG_TRACE(2, k_it, 2);
+      if (a.head_w) {
+        const int nc = a.head_nc;
+        float o0 = head_acc[0] + __ldg(a.head_b), o1 = 0.f, o2 = 0.f, o3 = 0.f;
+        if (nc > 1) o1 = head_acc[1] + __ldg(a.head_b + 1);
+        if (nc > 2) o2 = head_acc[2] + __ldg(a.head_b + 2);
+        if (nc > 3) o3 = head_acc[3] + __ldg(a.head_b + 3);
+        if (a.head_act == 0) {
+          o0 = tanhf(o0); o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3);
+        } else if (a.head_act == 1) {
+          float mx = o0;
+          if (nc > 1) mx = fmaxf(mx, o1);
+          if (nc > 2) mx = fmaxf(mx, o2);
+          if (nc > 3) mx = fmaxf(mx, o3);
+          o0 = expf(o0 - mx);
+          o1 = nc > 1 ? expf(o1 - mx) : 0.f;
+          o2 = nc > 2 ? expf(o2 - mx) : 0.f;
+          o3 = nc > 3 ? expf(o3 - mx) : 0.f;
+          const float inv = 1.0f / (o0 + o1 + o2 + o3);
+          o0 *= inv; o1 *= inv; o2 *= inv; o3 *= inv;
+        }
+        if (nc == 4) {
+          *reinterpret_cast<float4*>(a.head_out + pix0 * 4) = make_float4(o0, o1, o2, o3);
+        } else {
+          float* op = a.head_out + pix0 * nc;
+          op[0] = o0;
+          if (nc > 1) op[1] = o1;
+          if (nc > 2) op[2] = o2;
         }
       }
     }
-#undef DG_EPI_ISSUE
+    if (t0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output tiles written
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  DG_TRACE_DUMP;
+  if (warp == CTRL_W0 + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(g.tmem_cols) : "memory");
   }
 }
 
 // ---- instantiation helpers used by conv_tc_k{1,3,5}.cu ----
 template <int KS, int KSTEPS, bool RES, int EPI>
-int launch_one(int grid, uint32_t smem, cudaStream_t st, const CUtensorMap& tmA0, const CUtensorMap& tmA1,
-               const CUtensorMap& tmB, const ConvArgs& a, const TcGeom& g) {
-  conv_tc_kernel<KS, KSTEPS, RES, EPI><<<grid, TC_THREADS, smem, st>>>(tmA0, tmA1, tmB, a, g);
+int launch_one(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g) {
+  conv_tc_kernel<KS, KSTEPS, RES, EPI><<<grid, TC_THREADS, smem, st>>>(tm, a, g);
   DG_LAUNCH_CHECK();
   return 0;
 }
 template <int KS, int KSTEPS, bool RES, int EPI>
 int set_attr_one() {
   DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, KSTEPS, RES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     227 * 1024));
+                                     227 * 1024 - DG_TRACE_SMEM));
   return 0;
 }
+
+// One (kernel size, EPI) family = the six (KSTEPS, RES) instantiations; key = (kc/16)*10 + resident
+#define DG_TC_CASES(KS_, EPI_)                                                            \
+  case EPI_ * 100 + 10: return launch_one<KS_, 1, false, EPI_>(grid, smem, st, tm, a, g); \
+  case EPI_ * 100 + 11: return launch_one<KS_, 1, true, EPI_>(grid, smem, st, tm, a, g);  \
+  case EPI_ * 100 + 20: return launch_one<KS_, 2, false, EPI_>(grid, smem, st, tm, a, g); \
+  case EPI_ * 100 + 21: return launch_one<KS_, 2, true, EPI_>(grid, smem, st, tm, a, g);  \
+  case EPI_ * 100 + 40: return launch_one<KS_, 4, false, EPI_>(grid, smem, st, tm, a, g); \
+  case EPI_ * 100 + 41: return launch_one<KS_, 4, true, EPI_>(grid, smem, st, tm, a, g);
+#define DG_TC_ATTRS(KS_, EPI_)                        \
+  DG_TRY((set_attr_one<KS_, 1, false, EPI_>()));      \
+  DG_TRY((set_attr_one<KS_, 1, true, EPI_>()));       \
+  DG_TRY((set_attr_one<KS_, 2, false, EPI_>()));      \
+  DG_TRY((set_attr_one<KS_, 2, true, EPI_>()));       \
+  DG_TRY((set_attr_one<KS_, 4, false, EPI_>()));      \
+  DG_TRY((set_attr_one<KS_, 4, true, EPI_>()));
 #endif  // __CUDACC__
 
 }  // namespace convtc
