@@ -162,6 +162,20 @@ __device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[16]) {
                : "memory");
 }
 
+// waits for every tcgen05.ld in flight; names all four register groups so no use can be scheduled above it
+__device__ __forceinline__ void tc_ld_wait4(uint32_t (&r)[4][16]) {
+  tc_ld_wait(r[0]);
+  asm volatile("" : "+r"(r[1][0]), "+r"(r[1][1]), "+r"(r[1][2]), "+r"(r[1][3]), "+r"(r[1][4]), "+r"(r[1][5]),
+                    "+r"(r[1][6]), "+r"(r[1][7]), "+r"(r[1][8]), "+r"(r[1][9]), "+r"(r[1][10]), "+r"(r[1][11]),
+                    "+r"(r[1][12]), "+r"(r[1][13]), "+r"(r[1][14]), "+r"(r[1][15]) :: "memory");
+  asm volatile("" : "+r"(r[2][0]), "+r"(r[2][1]), "+r"(r[2][2]), "+r"(r[2][3]), "+r"(r[2][4]), "+r"(r[2][5]),
+                    "+r"(r[2][6]), "+r"(r[2][7]), "+r"(r[2][8]), "+r"(r[2][9]), "+r"(r[2][10]), "+r"(r[2][11]),
+                    "+r"(r[2][12]), "+r"(r[2][13]), "+r"(r[2][14]), "+r"(r[2][15]) :: "memory");
+  asm volatile("" : "+r"(r[3][0]), "+r"(r[3][1]), "+r"(r[3][2]), "+r"(r[3][3]), "+r"(r[3][4]), "+r"(r[3][5]),
+                    "+r"(r[3][6]), "+r"(r[3][7]), "+r"(r[3][8]), "+r"(r[3][9]), "+r"(r[3][10]), "+r"(r[3][11]),
+                    "+r"(r[3][12]), "+r"(r[3][13]), "+r"(r[3][14]), "+r"(r[3][15]) :: "memory");
+}
+
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128.
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -219,6 +233,37 @@ constexpr int TC_THREADS = 384;  // two epilogue warpgroups (warps 0..7) + one c
 // the LAST warpgroup and the instruction-heavy epilogue in warps 0..7.
 constexpr int CTRL_W0 = 8;  // first control warp
 constexpr int EPI_W0 = 0;   // first epilogue warp
+
+// Work item index -> (n-split, tile column, tile row, slice), stepped by the grid size with mixed-radix carries so the
+// per-item path has no integer division.
+struct ItemIter {
+  int it, ns, tw, th, n;
+  int d_it, d_ns, d_tw, d_th, d_n;
+  int r_ns, r_tw, r_th;
+  __device__ __forceinline__ void init(int it0, int step, int nsplit, int tiles_w, int tiles_h) {
+    r_ns = nsplit; r_tw = tiles_w; r_th = tiles_h;
+    it = it0; d_it = step;
+    ns = it0 % nsplit; int t = it0 / nsplit;
+    tw = t % tiles_w; t /= tiles_w;
+    th = t % tiles_h; n = t / tiles_h;
+    d_ns = step % nsplit; t = step / nsplit;
+    d_tw = t % tiles_w; t /= tiles_w;
+    d_th = t % tiles_h; d_n = t / tiles_h;
+  }
+  __device__ __forceinline__ void advance() {
+    it += d_it;
+    ns += d_ns;
+    int c = ns >= r_ns ? 1 : 0;
+    ns -= c ? r_ns : 0;
+    tw += d_tw + c;
+    c = tw >= r_tw ? 1 : 0;
+    tw -= c ? r_tw : 0;
+    th += d_th + c;
+    c = th >= r_th ? 1 : 0;
+    th -= c ? r_th : 0;
+    n += d_n + c;
+  }
+};
 
 struct Ring {
   int idx = 0;
@@ -335,10 +380,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     Ring ra, rb;
     int p_it = 0;
-    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++p_it) {
-      const int ns = it % nsplit, t = it / nsplit;
-      const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
-      const int w0 = tw * 16, h0 = th * 16, n0 = ns * g.ncta;
+    ItemIter ii;
+    ii.init(blockIdx.x, (int)gridDim.x, nsplit, g.tiles_w, g.tiles_h);
+    for (; ii.it < n_items; ii.advance(), ++p_it) {
+      const int n = ii.n;
+      const int w0 = ii.tw * 16, h0 = ii.th * 16, n0 = ii.ns * g.ncta;
       DG_TRACE(0, p_it, 0);
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(emptyA + 8 * ra.idx, ra.phase ^ 1u);
@@ -370,9 +416,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ===== TMA producer of the epilogue's side-input tiles (FiLM residual, or add / mask sources) =====
     if (EPI != 0 && g.n_side > 0) {
       Ring rs;
-      for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int ns = it % nsplit, t = it / nsplit;
-        const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h, n = t / tiles_per_img;
+      ItemIter ii;
+      ii.init(blockIdx.x, (int)gridDim.x, nsplit, g.tiles_w, g.tiles_h);
+      for (; ii.it < n_items; ii.advance()) {
+        const int ns = ii.ns, tw = ii.tw, th = ii.th, n = ii.n;
         for (int cc = 0; cc < nco; ++cc) {
           mbar_wait(sideEmpty + 8 * rs.idx, rs.phase ^ 1u);
           if (elect_one()) {
@@ -491,57 +538,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const bool side = EPI != 0 && g.n_side > 0;
     const bool stage_out = g.stage_out != 0;
     const bool t0 = threadIdx.x == EPI_W0 * 32;  // issues the TMA stores
-    const int step = (int)gridDim.x;
     // this thread's pixel in a staging tile [16 rows][16 cols][ch] whose 16-byte units are XOR-swizzled like the TMA
     // (unit j of the pixel at byte offset o lives at o + ((j ^ ((o >> 7) & (units-1))) << 4)): conflict-free 128-bit
     // accesses for 8 neighbouring pixels
     const uint32_t p_off = (uint32_t)(ty * 16 + tx) * (uint32_t)(g.ch * 2);
     const uint32_t p_xor = (p_off >> 7) & (uint32_t)(g.ch / 8 - 1);
     const uint32_t add_slot = 0, mask_slot = has_add ? g.slot_bytes : 0u;
+    const int head_nc = a.head_w ? a.head_nc : 0;
+
+    ItemIter cur, nx1, nx2;  // this item, the next one and the one after (FiLM tables are built ahead)
+    cur.init(blockIdx.x, (int)gridDim.x, nsplit, g.tiles_w, g.tiles_h);
+    nx1 = cur; nx1.advance();
+    nx2 = nx1; nx2.advance();
 
     // FiLM (gamma, beta) for this thread's column of the per-item table, fetched two items ahead
     const int fc = ew * 32 + lane;  // table column this thread fills (ncta <= 256)
     float fg_next = 0.f, fb_next = 0.f;
-    auto film_fetch = [&](int it_) {
-      if (has_film && it_ < n_items && fc < g.ncta) {
-        const int ns_ = it_ % nsplit, n_ = (it_ / nsplit) / tiles_per_img;
-        fg_next = __ldg(a.film_g + (size_t)n_ * a.film_stride + ns_ * g.ncta + fc);
-        fb_next = __ldg(a.film_b + (size_t)n_ * a.film_stride + ns_ * g.ncta + fc);
+    auto film_fetch = [&](const ItemIter& i_) {
+      if (has_film && i_.it < n_items && fc < g.ncta) {
+        fg_next = __ldg(a.film_g + (size_t)i_.n * a.film_stride + i_.ns * g.ncta + fc);
+        fb_next = __ldg(a.film_b + (size_t)i_.n * a.film_stride + i_.ns * g.ncta + fc);
       }
     };
-    auto film_fill = [&](int it_, int slot_) {  // v = relu(acc*(s*g) + (t*g + b)) + res
-      if (has_film && it_ < n_items && fc < g.ncta) {
-        const int n0_ = (it_ % nsplit) * g.ncta;
+    auto film_fill = [&](const ItemIter& i_, int slot_) {  // v = relu(acc*(s*g) + (t*g + b)) + res
+      if (has_film && i_.it < n_items && fc < g.ncta) {
+        const int n0_ = i_.ns * g.ncta;
         float* sF_ = s_film + slot_ * 2 * g.ncta;
         sF_[fc] = s_scale[n0_ + fc] * fg_next;
         sF_[g.ncta + fc] = fmaf(s_shift[n0_ + fc], fg_next, fb_next);
       }
     };
     if (has_film) {
-      film_fetch(blockIdx.x);
-      film_fill(blockIdx.x, 0);
-      film_fetch(blockIdx.x + step);
+      film_fetch(cur);
+      film_fill(cur, 0);
+      film_fetch(nx1);
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
 
     Ring rs;             // side-input stages
     uint32_t oslot = 0;  // output staging slot of the next chunk
-    int k_it = 0;
-    uint32_t vn[16];
-    for (int it = blockIdx.x; it < n_items; it += step, ++k_it) {
-      const int ns = it % nsplit, t = it / nsplit;
-      const int tw = t % g.tiles_w, th = (t / g.tiles_w) % g.tiles_h;
-      const int n = t / tiles_per_img;
-      const int h = th * 16 + ty, w = tw * 16 + tx, n0 = ns * g.ncta;
-      const size_t pix0 = ((size_t)n * a.H + h) * a.W + w;
+    int k_it = 0, fslot = 0;
+    uint32_t vb[4][16];  // up to 64 accumulator columns in flight
+    for (; cur.it < n_items; ++k_it) {
+      const int h = cur.th * 16 + ty, w = cur.tw * 16 + tx, n0 = cur.ns * g.ncta;
+      const size_t pix0 = ((size_t)cur.n * a.H + h) * a.W + w;
       const int as = g.acc_stages == 2 ? (k_it & 1) : 0;
       const uint32_t use = g.acc_stages == 2 ? (uint32_t)(k_it >> 1) : (uint32_t)k_it;
-      const float* sF = s_film + (k_it % 3) * 2 * g.ncta;
+      const float* sF = s_film + fslot * 2 * g.ncta;
+      const int fnext = fslot == 2 ? 0 : fslot + 1;
       if (has_film) {
         // table of the NEXT item: its slot was last read two items ago, and every thread passes one of this item's
         // chunk barriers between this write and the reads
-        film_fill(it + step, (k_it + 1) % 3);
-        film_fetch(it + 2 * step);
+        film_fill(nx1, fnext);
+        film_fetch(nx2);
       }
       float head_acc[4] = {0.f, 0.f, 0.f, 0.f};
       if (ew == 0) DG_TRACE(2, k_it, 0);
@@ -549,27 +598,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       tc_fence_after();
       if (ew == 0) DG_TRACE(2, k_it, 1);
       const uint32_t t_row = tmem_base + as * acc_stride + ((uint32_t)(q * 32) << 16) + (uint32_t)(strip * g.ncta);
-      tc_ld16_issue(t_row, vn);
       int gg = 0, cc = 0;
-      for (int gi = 0; gi < ng; ++gi) {
+      // one 16-column group: BN / FiLM / add / mask / ReLU, pack to bf16 into the staging tile, fused head; the last
+      // group of a staging chunk hands the chunk to the TMA store
+      auto do_group = [&](const uint32_t (&vr)[16], const int gi) {
         if (gg == 0 && side) mbar_wait(sideFull + 8 * rs.idx, rs.phase);
-        // accumulator group gi has landed; start group gi+1's TMEM read before working on gi
-        tc_ld_wait(vn);
-        if (ew == 0 && gi == 0) DG_TRACE(2, k_it, 3);
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vn[i]);
-        if (gi + 1 < ng) {
-          tc_ld16_issue(t_row + (uint32_t)((gi + 1) * 16), vn);
-        } else {
-          // all of this item's accumulator is in registers: hand the TMEM stage back before the stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(accEmpty + 8 * as);
-        }
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
         const int col = n0 + gi * 16;
         // the two 16-byte units of this group inside the thread's staging pixel
-        const uint32_t u0 = p_off + ((((uint32_t)(2 * gg)) ^ p_xor) << 4), u1 = p_off + ((((uint32_t)(2 * gg + 1)) ^ p_xor) << 4);
+        const uint32_t u0 = p_off + ((((uint32_t)(2 * gg)) ^ p_xor) << 4);
+        const uint32_t u1 = p_off + ((((uint32_t)(2 * gg + 1)) ^ p_xor) << 4);
         const uint8_t* sgen = smem_raw + (s_base + (uint32_t)(rs.idx * g.n_side) * g.slot_bytes - raw);
         if (has_film) {
           if (a.out_pre) {
@@ -629,7 +669,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           *reinterpret_cast<uint4*>(ogen + u0) = pk[0];
           *reinterpret_cast<uint4*>(ogen + u1) = pk[1];
         }
-        if (a.head_w) {
+        if (head_nc == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) head_acc[0] = fmaf(v[i], s_head[col + i].x, head_acc[0]);
+        } else if (head_nc > 1) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const float4 hw = s_head[col + i];
@@ -639,6 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             head_acc[3] = fmaf(v[i], hw.w, head_acc[3]);
           }
         }
+        if (ew == 0 && gi == ng - 1) DG_TRACE(2, k_it, 4);
         if (++gg == gpc) {
           // ---- staging chunk cc complete ----
           if (side) {
@@ -648,35 +692,73 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
           if (stage_out) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            // the previous chunk's store has drained its slot before anyone passes the barrier and refills it
-            if (t0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // store coordinates; the previous chunk's store has drained its slot before anyone passes the barrier
+            // and refills it
+            int c0 = n0 + cc * g.ch, c1 = 0, c3 = 0;
             if (t0) {
-              const uint32_t src = o_base + oslot * g.slot_bytes;
-              const int c0 = n0 + cc * g.ch;
               if (a.deconv) {
                 const int ab = c0 / Cout;
-                tma_store_5d(&tm.out, src, c0 - ab * Cout, ab & 1, tw * 16, ab >> 1, n * a.H + th * 16);
-              } else {
-                tma_store_4d(&tm.out, src, c0, tw * 16, th * 16, n);
+                c0 -= ab * Cout; c1 = ab & 1; c3 = ab >> 1;
               }
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            }
+            if (ew == 0 && gi == ng - 1) DG_TRACE(2, k_it, 5);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (ew == 0 && gi == ng - 1) DG_TRACE(2, k_it, 6);
+            if (t0) {
+              const uint32_t src = o_base + oslot * g.slot_bytes;
+              if (a.deconv) tma_store_5d(&tm.out, src, c0, c1, cur.tw * 16, c3, cur.n * a.H + cur.th * 16);
+              else tma_store_4d(&tm.out, src, c0, cur.tw * 16, cur.th * 16, cur.n);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
+            if (ew == 0 && gi == ng - 1) DG_TRACE(2, k_it, 7);
             oslot ^= 1u;
           }
           gg = 0;
           ++cc;
         }
+      };
+      // TMEM reads run one 32-column batch ahead of the math (ping-pong register buffers)
+      tc_ld16_issue(t_row, vb[0]);
+      if (ng > 1) tc_ld16_issue(t_row + 16u, vb[1]);
+      for (int gb = 0; gb < ng; gb += 4) {
+        tc_ld_wait4(vb);
+        if (ew == 0 && gb == 0) DG_TRACE(2, k_it, 3);
+        if (gb + 2 < ng) {
+          tc_ld16_issue(t_row + (uint32_t)((gb + 2) * 16), vb[2]);
+          if (gb + 3 < ng) tc_ld16_issue(t_row + (uint32_t)((gb + 3) * 16), vb[3]);
+        } else {
+          // all of this item's accumulator is in registers: hand the TMEM stage back before the math and the stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(accEmpty + 8 * as);
+        }
+        do_group(vb[0], gb);
+        if (gb + 1 < ng) do_group(vb[1], gb + 1);
+        if (gb + 2 < ng) {
+          tc_ld_wait4(vb);
+          if (gb + 4 < ng) {
+            tc_ld16_issue(t_row + (uint32_t)((gb + 4) * 16), vb[0]);
+            if (gb + 5 < ng) tc_ld16_issue(t_row + (uint32_t)((gb + 5) * 16), vb[1]);
+          } else {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(accEmpty + 8 * as);
+          }
+          do_group(vb[2], gb + 2);
+          if (gb + 3 < ng) do_group(vb[3], gb + 3);
+        }
       }
       if (ew == 0) DG_TRACE(2, k_it, 2);
-      if (a.head_w) {
-        const int nc = a.head_nc;
+      if (head_nc) {
+        const int nc = head_nc;
         float o0 = head_acc[0] + __ldg(a.head_b), o1 = 0.f, o2 = 0.f, o3 = 0.f;
         if (nc > 1) o1 = head_acc[1] + __ldg(a.head_b + 1);
         if (nc > 2) o2 = head_acc[2] + __ldg(a.head_b + 2);
         if (nc > 3) o3 = head_acc[3] + __ldg(a.head_b + 3);
         if (a.head_act == 0) {
-          o0 = tanhf(o0); o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3);
+          o0 = tanhf(o0);
+          if (nc > 1) { o1 = tanhf(o1); o2 = tanhf(o2); o3 = tanhf(o3); }
         } else if (a.head_act == 1) {
           float mx = o0;
           if (nc > 1) mx = fmaxf(mx, o1);
@@ -698,6 +780,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (nc > 2) op[2] = o2;
         }
       }
+      cur = nx1; nx1 = nx2; nx2.advance();
+      fslot = fnext;
     }
     if (t0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output tiles written
   }

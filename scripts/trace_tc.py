@@ -27,9 +27,9 @@ for mk in kbench.CASES:
     t = buf.cpu().view(3, 40, 8)
     t0 = int(t[0, 0, 0])
     print("== %s (clocks relative to the producer's first item; P: top, emptyA ok, issued | M: top, accEmpty ok, "
-          "fullA ok, committed | E: start, accFull ok, released, first chunk landed)" % name)
+          "fullA ok, committed | E: start, accFull ok, item end, first group landed, last group staged, store drained, barrier passed, store issued)" % name)
     for i in range(0, 40):
         if int(t[0, i, 0]) == 0:
             break
         f = lambda r, n: " ".join("%7d" % ((int(v) - t0) & 0xFFFFFFFF) for v in t[r, i, :n])
-        print("%3d  P %s | M %s | E %s" % (i, f(0, 3), f(1, 4), f(2, 4)))
+        print("%3d  P %s | M %s | E %s" % (i, f(0, 3), f(1, 4), f(2, 8)))
