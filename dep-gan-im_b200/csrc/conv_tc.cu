@@ -1,5 +1,8 @@
 // Host side of the tcgen05 implicit-GEMM convolution: shape planning (shared-memory rings, TMEM columns), TMA tensor
 // maps and dispatch to the kernel instantiations of conv_tc_k{1,3,5}.cu.  The kernel itself is conv_tc_kernel.cuh.
+#include <cstdio>
+#include <cstdlib>
+
 #include "conv_tc_kernel.cuh"
 
 using namespace convtc;
@@ -98,7 +101,7 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
     if (a.C0 % kc || a.C1 % kc) continue;
     const int nchunks = (a.C0 + a.C1) / kc;
     const uint32_t a_bytes = round1024((uint32_t)ht * ht * kc * 2), b_bytes = round1024((uint32_t)ncta * kc * 2);
-    int na = 0, nb = 0, resident = 0;
+    int na = 0, nb = 0, resident = 0, tps = 1;
     const int nb_all = taps * nchunks;
     const uint32_t w_all = (uint32_t)nb_all * b_bytes;
     const uint32_t fixed_res = 1024 + bar_bytes(6, nb_all) + floats + staging;
@@ -108,27 +111,42 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
       na = (int)((SMEM_BUDGET - fixed_res - w_all) / a_bytes);
       if (na > 6) na = 6;
     } else {
+      // streamed weights: ring stages of all taps of a chunk, else one kernel row, else single taps
       const uint32_t fixed_str = 1024 + bar_bytes(3, 12) + floats + staging;
-      na = 3;
-      if (fixed_str + na * a_bytes + 4 * b_bytes > SMEM_BUDGET) na = 2;
-      if (fixed_str + na * a_bytes + 3 * b_bytes > SMEM_BUDGET) {
+      bool ok = false;
+      const int tps_opts[3] = {taps, ks, 1};
+      for (int oi = 0; oi < 3 && !ok; ++oi) {
+        tps = tps_opts[oi];
+        if (oi > 0 && tps == tps_opts[oi - 1]) continue;
+        const uint32_t stage = (uint32_t)tps * b_bytes;
+        const int want = tps == 1 ? 4 : (tps == taps ? 2 : 3);  // stages needed to keep the issuer fed
+        for (na = 3; na >= 2 && !ok; --na) {
+          if (fixed_str + na * a_bytes + want * stage > SMEM_BUDGET) continue;
+          nb = (int)((SMEM_BUDGET - fixed_str - na * a_bytes) / stage);
+          const int cap = tps == 1 ? 12 : (tps == taps ? 3 : 6);
+          if (nb > cap) nb = cap;
+          ok = true;
+          break;
+        }
+      }
+      if (!ok) {
         if (kc > 16) continue;
         return false;
       }
-      nb = (int)((SMEM_BUDGET - fixed_str - na * a_bytes) / b_bytes);
-      if (nb > 12) nb = 12;
     }
     g->tiles_w = a.W / 16; g->tiles_h = a.H / 16;
     g->nchunk0 = a.C0 / kc; g->nchunk1 = a.C1 / kc;
     g->kc = kc; g->ncols_total = ncols; g->ncta = ncta; g->tmem_cols = tmem_cols;
-    g->na = na; g->nb = nb; g->a_bytes = a_bytes; g->b_bytes = b_bytes;
+    g->na = na; g->nb = nb; g->b_tps = tps; g->a_bytes = a_bytes; g->b_bytes = b_bytes;
     g->a_tx = (uint32_t)ht * ht * kc * 2; g->b_tx = (uint32_t)ncta * kc * 2;
     g->layout = kc == 64 ? 2u : kc == 32 ? 4u : 6u;
     g->b_resident = resident; g->acc_stages = acc_stages;
-    // two issuers share the A ring by parity waits: safe only while the ring holds a whole item (see the kernel)
-    g->n_issuers = (resident && acc_stages == 2 && na >= nchunks) ? 2 : 1;
+    // Two issuers share the A ring through parity waits.  A parity wait for fill f of a stage is only meaningful once
+    // fill f-1 has landed; an issuer knows that for its own previous item (two items back), so a stage must not be
+    // refilled more than once within two consecutive items: na >= 2 * nchunks.
+    g->n_issuers = (resident && acc_stages == 2 && na >= 2 * nchunks) ? 2 : 1;
     g->ch = ch; g->n_side = n_side; g->stage_out = stage_out; g->slot_bytes = slot;
-    *smem_bytes = 1024 + na * a_bytes + nb * b_bytes + staging + bar_bytes(na, nb) + floats;
+    *smem_bytes = 1024 + na * a_bytes + nb * (resident ? 1 : tps) * b_bytes + staging + bar_bytes(na, nb) + floats;
     return true;
   }
   return false;
@@ -203,10 +221,27 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   const int grid = n_items < g_num_sms ? n_items : g_num_sms;
   // side inputs the epilogue has to stream (selects the EPI instantiation): 1 FiLM residual, 2 add / mask
   const int need = a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : 0);
+  int rc;
   switch (a.ks) {
-    case 1: return launch_ks1(grid, smem, st, tm, a, g, need);
-    case 3: return launch_ks3(grid, smem, st, tm, a, g, need);
-    case 5: return launch_ks5(grid, smem, st, tm, a, g, need);
+    case 1: rc = launch_ks1(grid, smem, st, tm, a, g, need); break;
+    case 3: rc = launch_ks3(grid, smem, st, tm, a, g, need); break;
+    case 5: rc = launch_ks5(grid, smem, st, tm, a, g, need); break;
     default: depgan_set_error("conv_fwd_tc: no kernel for this kernel size"); return -2;
   }
+  static const bool dbg_sync = getenv("DEPGAN_DEBUG_SYNC") != nullptr;  // debugging aid: fail at the faulting launch
+  if (rc == 0 && dbg_sync) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+      char buf[512];
+      snprintf(buf, sizeof buf,
+               "conv_tc_kernel failed (%s): N=%d H=%d W=%d C0=%d C1=%d Cout=%d ks=%d deconv=%d film=%d add=%d mask=%d "
+               "pre=%d out=%d head=%d relu=%d | kc=%d ncta=%d na=%d nb=%d tps=%d res=%d acc=%d iss=%d ch=%d side=%d smem=%u",
+               cudaGetErrorString(e), a.N, a.H, a.W, a.C0, a.C1, a.Cout, a.ks, a.deconv, a.film_g != nullptr,
+               a.add_src != nullptr, a.mask_src != nullptr, a.out_pre != nullptr, a.out != nullptr, a.head_w != nullptr,
+               a.relu, g.kc, g.ncta, g.na, g.nb, g.b_tps, g.b_resident, g.acc_stages, g.n_issuers, g.ch, g.n_side, smem);
+      depgan_set_error(buf);
+      return -1;
+    }
+  }
+  return rc;
 }

@@ -43,7 +43,8 @@ struct TcGeom {
   int ncols_total;       // weight rows per tap (Cout, or 4*Cout for the transposed conv)
   int ncta;              // output columns per CTA
   int tmem_cols;         // power of two >= 2*ncta*acc_stages
-  int na, nb;            // ring depths
+  int na, nb;            // ring depths (weights: stages of b_tps taps)
+  int b_tps;             // taps per weight-ring stage when the weights stream: TAPS, KS or 1
   uint32_t a_bytes, b_bytes;  // stage strides (1024-aligned)
   uint32_t a_tx, b_tx;        // TMA transaction bytes per stage
   uint32_t layout;            // UMMA smem layout type (2 = SW128, 4 = SW64, 6 = SW32)
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t base = (raw + 1023u) & ~1023u;
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + g.na * g.a_bytes;
-  const uint32_t o_base = b_base + g.nb * g.b_bytes;                       // 2 output staging slots
+  const uint32_t o_base = b_base + g.nb * g.b_tps * g.b_bytes;             // 2 output staging slots
   const uint32_t s_base = o_base + (g.stage_out ? 2u * g.slot_bytes : 0u);  // 2 side stages x n_side slots
   const uint32_t bar_base = s_base + 2u * g.n_side * g.slot_bytes;
   const uint32_t fullA = bar_base, emptyA = fullA + 8 * g.na;
@@ -398,12 +399,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         __syncwarp();
         ra.advance(g.na);
         if (!RES) {
+          // weight ring: one stage = b_tps consecutive taps of this channel chunk (all taps, one kernel row, or one tap)
           const int kglob = first ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
-          for (int tap = 0; tap < TAPS; ++tap) {
+          for (int tap = 0; tap < TAPS; tap += g.b_tps) {
             mbar_wait(emptyB + 8 * rb.idx, rb.phase ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(fullB + 8 * rb.idx, g.b_tx);
-              tma_load_2d(b_base + rb.idx * g.b_bytes, &tm.b, fullB + 8 * rb.idx, kglob, tap * g.ncols_total + n0);
+              mbar_expect_tx(fullB + 8 * rb.idx, g.b_tx * g.b_tps);
+              for (int t2 = 0; t2 < g.b_tps; ++t2)
+                tma_load_2d(b_base + (rb.idx * g.b_tps + t2) * g.b_bytes, &tm.b, fullB + 8 * rb.idx, kglob,
+                            (tap + t2) * g.ncols_total + n0);
             }
             __syncwarp();
             rb.advance(g.nb);
@@ -437,7 +441,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else {
     // ===== MMA issuers (whole warp converged, one elected lane issues tcgen05.mma / commit) =====
     // Issuer m takes the CTA's items m, m + n_issuers, ... and owns accumulator stage m, so while one issuer sits in
-    // the barrier waits between two of its items the other keeps the tensor pipe fed.
+    // the barrier waits between two of its items the other keeps the tensor pipe fed.  (Two issuers need
+    // na >= 2 * nchunks, see plan(): the parity wait of one issuer must never race the other issuer's fill.)
     // Descriptors: the high word (SBO, version, swizzle mode) is constant; per MMA only the 14-bit start
     // address field of the low word moves, in 16-byte units.
     const int m = warp == CTRL_W0 + 1 ? 0 : 1;
@@ -489,26 +494,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
           __syncwarp();
         } else {
+          // streamed weights: a ring stage holds b_tps consecutive taps (TAPS, KS or 1); taps of a kernel row are
+          // unrolled so their descriptor offsets are immediates
+          uint32_t b_lo0 = 0;
 #pragma unroll 1
-          for (int tap = 0; tap < TAPS; ++tap) {
-            mbar_wait(fullB + 8 * rb.idx, rb.phase);
-            tc_fence_after();
-            const uint32_t b_lo = (((b_base + rb.idx * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
-            const int dy = tap / KS, dx = tap - dy * KS;
-            const uint32_t at = a_lo + (uint32_t)((dy * HT + dx) * ROW16);
-            if (elect_one()) {
+          for (int dy = 0; dy < KS; ++dy) {
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                const uint32_t acc = k != 0 ? 1u : (tap != 0 ? 1u : accc);
-                tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
-                tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
-                       idesc, acc);
+            for (int dx = 0; dx < KS; ++dx) {
+              const int tap = dy * KS + dx;
+              const bool s_first = g.b_tps == 1 || (g.b_tps == KS ? dx == 0 : tap == 0);
+              const bool s_last = g.b_tps == 1 || (g.b_tps == KS ? dx == KS - 1 : tap == TAPS - 1);
+              if (s_first) {
+                mbar_wait(fullB + 8 * rb.idx, rb.phase);
+                tc_fence_after();
+                b_lo0 = (((b_base + rb.idx * g.b_tps * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
               }
-              tc_commit(emptyB + 8 * rb.idx);
-              if (tap == TAPS - 1) tc_commit(emptyA + 8 * ra.idx);
+              const int slot = g.b_tps == 1 ? 0 : (g.b_tps == KS ? dx : tap);
+              const uint32_t b_lo = b_lo0 + (uint32_t)slot * b_step;
+              const uint32_t at = a_lo + (uint32_t)(dy * HT * ROW16) + (uint32_t)(dx * ROW16);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint32_t acc = k != 0 ? 1u : (tap != 0 ? 1u : accc);
+                  tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
+                  tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
+                         idesc, acc);
+                }
+                if (s_last) tc_commit(emptyB + 8 * rb.idx);
+                if (tap == TAPS - 1) tc_commit(emptyA + 8 * ra.idx);
+              }
+              __syncwarp();
+              if (s_last) rb.advance(g.nb);
             }
-            __syncwarp();
-            rb.advance(g.nb);
           }
         }
         ra.advance(g.na);
@@ -603,6 +620,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       // group of a staging chunk hands the chunk to the TMA store
       auto do_group = [&](const uint32_t (&vr)[16], const int gi) {
         if (gg == 0 && side) mbar_wait(sideFull + 8 * rs.idx, rs.phase);
+        if (ew == 0 && gi == 0) DG_TRACE(2, k_it, 7);
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(vr[i]);
@@ -711,7 +729,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               else tma_store_4d(&tm.out, src, c0, cur.tw * 16, cur.th * 16, cur.n);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
-            if (ew == 0 && gi == ng - 1) DG_TRACE(2, k_it, 7);
             oslot ^= 1u;
           }
           gg = 0;

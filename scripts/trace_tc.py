@@ -27,7 +27,7 @@ for mk in kbench.CASES:
     t = buf.cpu().view(3, 40, 8)
     t0 = int(t[0, 0, 0])
     print("== %s (clocks relative to the producer's first item; P: top, emptyA ok, issued | M: top, accEmpty ok, "
-          "fullA ok, committed | E: start, accFull ok, item end, first group landed, last group staged, store drained, barrier passed, store issued)" % name)
+          "fullA ok, committed | E: start, accFull ok, item end, first group landed, last group staged, store drained, barrier passed, side inputs of the first chunk ready)" % name)
     for i in range(0, 40):
         if int(t[0, i, 0]) == 0:
             break

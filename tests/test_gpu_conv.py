@@ -260,3 +260,14 @@ def test_last_layer_ragged():
     got = conv2d_op(b.cuda(), wd.cuda(), use_tc=False).cpu()
     want, _ = ref_conv(b, wd)
     assert torch.allclose(got, want, atol=2e-4, rtol=1e-4)
+
+
+# ---- ring sharing between the two MMA issuers: shapes whose activation ring holds one item (na == nchunks), many items
+@pytest.mark.parametrize("cin,cout,H,W,N", [(96, 64, 64, 64, 16), (96, 96, 64, 64, 12), (128, 64, 32, 32, 48)])
+def test_tcgen05_ring_one_item_many_items(cin, cout, H, W, N):
+    from depgan_b200 import conv2d_op
+    x = _bf(_rand((N, H, W, cin), 1))
+    w = _bf(_rand((3, 3, cin, cout), 2, 1.0 / np.sqrt(9 * cin)))
+    got = conv2d_op(x.cuda(), w.cuda(), use_tc=True).cpu()
+    want, _ = ref_conv(x, w)
+    assert float((got - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
