@@ -111,12 +111,17 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-template <int KS>
+// KS = kernel size, C = input channels per chunk (one swizzle span): taps per MMA, tap groups and every descriptor
+// offset of the MMA stream are compile-time, so the issuing warp's loop is a run of UTCHMMA with immediate offsets.
+template <int KS, int C>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                                  const __grid_constant__ CUtensorMap tmX1,
                                                                  const __grid_constant__ CUtensorMap tmB, float* dw,
                                                                  float alpha, int N, const WgGeom g) {
   constexpr int PAD = KS / 2, HT = 16 + KS - 1;
+  constexpr int SPAN = C * 2;       // bytes per pixel row of the x tile
+  constexpr int TPM = 128 / C;      // dx taps stacked in one M=128 MMA
+  constexpr int G = (KS + TPM - 1) / TPM;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -148,10 +153,9 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const long long it1 = it0 + per < items ? it0 + per : items;
   const int chunk = blockIdx.y;
   const bool from0 = chunk < g.nchunk0;
-  const int c_src = (from0 ? chunk : chunk - g.nchunk0) * g.C;                 // channel offset inside its source
-  const int c_glob = from0 ? chunk * g.C : g.nchunk0 * g.C + (chunk - g.nchunk0) * g.C;  // ... inside the weight
+  const int c_src = (from0 ? chunk : chunk - g.nchunk0) * C;                 // channel offset inside its source
+  const int c_glob = from0 ? chunk * C : g.nchunk0 * C + (chunk - g.nchunk0) * C;  // ... inside the weight
   const int co0 = blockIdx.z * g.nblk;
-  const int span = g.C * 2;  // bytes per pixel row of the x tile
   const int nb_blocks = g.nblk / g.nspan;
 
   if (warp == 0) {
@@ -178,8 +182,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(g.nblk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // A: M blocks (C channels) step by one pixel (LBO = span); K groups of 8 pixels step by 8 pixels (SBO = 8*span)
-    const uint32_t hiA = ((uint32_t)(8 * span) >> 4) | (1u << 14) | (g.lay_x << 29);
-    const uint32_t loA_lbo = ((uint32_t)span >> 4) << 16;
+    const uint32_t hiA = ((uint32_t)(8 * SPAN) >> 4) | (1u << 14) | (g.lay_x << 29);
+    constexpr uint32_t loA_lbo = ((uint32_t)SPAN >> 4) << 16;
     // B: N blocks of nspan channels are separate [R*16 px] sub-tiles (LBO = sub-tile bytes); SBO = 8 pixel rows
     const uint32_t bspan = g.nspan * 2;
     const uint32_t hiB = ((uint32_t)(8 * bspan) >> 4) | (1u << 14) | (g.lay_b << 29);
@@ -192,16 +196,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       tc_fence_after();
       const uint32_t st = base + s * g.stage_bytes;
       const uint32_t xa = ((st & 0x3FFFFu) >> 4), ba = (((st + g.x_bytes) & 0x3FFFFu) >> 4);
+      const uint32_t b_row = (uint32_t)((16 * bspan) >> 4);  // one tile row of b in descriptor units
       if (elect_one()) {
-#pragma unroll 1
+#pragma unroll
         for (int r = 0; r < R; ++r) {
-          const uint32_t b_lo = (ba + (uint32_t)((r * 16 * bspan) >> 4)) | loB_lbo;
-          const uint32_t acc = (first && r == 0) ? 0u : 1u;
+          const uint32_t b_lo = (ba + (uint32_t)r * b_row) | loB_lbo;
+          const uint32_t acc = r == 0 ? (first ^ 1u) : 1u;
 #pragma unroll
           for (int dy = 0; dy < KS; ++dy) {
-            for (int gi = 0; gi < g.G; ++gi) {
-              const uint32_t a_lo = (xa + (uint32_t)((((r + dy) * HT + gi * g.tpm) * span) >> 4)) | loA_lbo;
-              tc_mma(tmem_base + (uint32_t)((dy * g.G + gi) * g.nblk), ((uint64_t)hiA << 32) | a_lo,
+#pragma unroll
+            for (int gi = 0; gi < G; ++gi) {
+              const uint32_t a_lo = (xa + (uint32_t)((((r + dy) * HT + gi * TPM) * SPAN) >> 4)) | loA_lbo;
+              tc_mma(tmem_base + (uint32_t)(dy * G + gi) * (uint32_t)g.nblk, ((uint64_t)hiA << 32) | a_lo,
                      ((uint64_t)hiB << 32) | b_lo, idesc, acc);
             }
           }
@@ -220,13 +226,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     tc_fence_after();
     const int q = warp & 3;
     const int m = q * 32 + lane;        // accumulator row = (dx_local, ci)
-    const int dxl = m / g.C, ci = m - dxl * g.C;
+    const int dxl = m / C, ci = m - dxl * C;
     for (int dy = 0; dy < KS; ++dy)
-      for (int gi = 0; gi < g.G; ++gi) {
-        const int dx = gi * g.tpm + dxl;
+      for (int gi = 0; gi < G; ++gi) {
+        const int dx = gi * TPM + dxl;
         for (int j = 0; j < g.nblk / 16; ++j) {
           float v[16];
-          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((dy * g.G + gi) * g.nblk + j * 16), v);
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((dy * G + gi) * g.nblk + j * 16), v);
           if (dx < KS) {
             float* dst = dw + ((size_t)(dy * KS + dx) * g.cin_total + c_glob + ci) * g.cout_total + co0 + j * 16;
 #pragma unroll
@@ -323,9 +329,12 @@ int wgrad_tc_init() {
   int dev = 0;
   DG_CHECK_CUDA(cudaGetDevice(&dev));
   DG_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms_w, cudaDevAttrMultiProcessorCount, dev));
-  DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+#define DG_WG_ATTR(KS_, C_) \
+  DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KS_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DG_WG_ATTR(1, 16) DG_WG_ATTR(1, 32) DG_WG_ATTR(1, 64)
+  DG_WG_ATTR(3, 16) DG_WG_ATTR(3, 32) DG_WG_ATTR(3, 64)
+  DG_WG_ATTR(5, 16) DG_WG_ATTR(5, 32) DG_WG_ATTR(5, 64)
+#undef DG_WG_ATTR
   return 0;
 }
 
@@ -347,11 +356,15 @@ int conv_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   if (gx < 1) gx = 1;
   if (gx > items) gx = items;
   dim3 grid((unsigned)gx, chunks, coblocks);
-  switch (a.ks) {
-    case 1: wgrad_tc_kernel<1><<<grid, WG_THREADS, smem, st>>>(tmX0, tmX1, tmB, a.dw, a.alpha, a.N, g); break;
-    case 3: wgrad_tc_kernel<3><<<grid, WG_THREADS, smem, st>>>(tmX0, tmX1, tmB, a.dw, a.alpha, a.N, g); break;
-    case 5: wgrad_tc_kernel<5><<<grid, WG_THREADS, smem, st>>>(tmX0, tmX1, tmB, a.dw, a.alpha, a.N, g); break;
+#define DG_WG_CASE(KS_, C_) \
+  case KS_ * 100 + C_: wgrad_tc_kernel<KS_, C_><<<grid, WG_THREADS, smem, st>>>(tmX0, tmX1, tmB, a.dw, a.alpha, a.N, g); break;
+  switch (a.ks * 100 + g.C) {
+    DG_WG_CASE(1, 16) DG_WG_CASE(1, 32) DG_WG_CASE(1, 64)
+    DG_WG_CASE(3, 16) DG_WG_CASE(3, 32) DG_WG_CASE(3, 64)
+    DG_WG_CASE(5, 16) DG_WG_CASE(5, 32) DG_WG_CASE(5, 64)
+    default: depgan_set_error("conv_wgrad_tc: no kernel for this (ks, C)"); return -2;
   }
+#undef DG_WG_CASE
   DG_LAUNCH_CHECK();
   return 0;
 }
