@@ -191,15 +191,22 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     int s = 0;
     uint32_t ph = 0;
     uint32_t first = 1;
+    uint32_t ready = 0;  // the next stage's barrier was already seen complete (probed mid-stage, see below)
     for (long long it = it0; it < it1; ++it) {
-      mbar_wait(full + 8 * s, ph);
+      if (!ready) mbar_wait(full + 8 * s, ph);
       tc_fence_after();
+      const int sn = s + 1 == g.S ? 0 : s + 1;
+      const uint32_t phn = s + 1 == g.S ? ph ^ 1u : ph;
+      uint32_t probe = 0;
       const uint32_t st = base + s * g.stage_bytes;
       const uint32_t xa = ((st & 0x3FFFFu) >> 4), ba = (((st + g.x_bytes) & 0x3FFFFu) >> 4);
       const uint32_t b_row = (uint32_t)((16 * bspan) >> 4);  // one tile row of b in descriptor units
       if (elect_one()) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
+          // The MMA queue is only a couple of instructions deep, so a barrier round trip at the stage boundary idles
+          // the tensor pipe: probe the next stage's barrier while this stage's MMAs are still being fed.
+          if (r == R - 2) probe = mbar_try_wait(full + 8 * sn, phn);
           const uint32_t b_lo = (ba + (uint32_t)r * b_row) | loB_lbo;
           const uint32_t acc = r == 0 ? (first ^ 1u) : 1u;
 #pragma unroll
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
         }
         tc_commit(empty + 8 * s);
       }
-      __syncwarp();
+      ready = __any_sync(0xffffffffu, probe != 0) ? 1u : 0u;
       first = 0;
       if (++s == g.S) { s = 0; ph ^= 1u; }
     }
@@ -236,7 +243,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           if (dx < KS) {
             float* dst = dw + ((size_t)(dy * KS + dx) * g.cin_total + c_glob + ci) * g.cout_total + co0 + j * 16;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(dst + i, alpha * v[i]);
+            for (int i = 0; i < 16; i += 4)  // 16-byte vector reductions (dst is 64-byte aligned)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(alpha * v[i]),
+                           "f"(alpha * v[i + 1]), "f"(alpha * v[i + 2]), "f"(alpha * v[i + 3])
+                           : "memory");
           }
         }
       }
