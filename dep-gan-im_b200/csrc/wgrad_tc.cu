@@ -10,10 +10,14 @@
 //     (LBO = span): one M=128 MMA covers 128/C horizontally adjacent taps dx at once -- the Toeplitz structure of the
 //     convolution is expressed in the descriptor, nothing is replicated in memory.  dy and the remaining dx groups
 //     are further MMAs on shifted start addresses of the same tile.
-//   * b: [R rows][16 cols][N], N-contiguous in blocks of <= 64 channels.
-//   * K = 16 pixels per MMA = one tile row.
+//     dx groups beyond the first (C = 64, or C = 32 with ks = 5) are further MMAs on shifted start addresses.
+//   * b: ONE box [R+ks-1 rows][16 cols][nb channels], nb <= 64 = one swizzle span, rows h0-pad .. (zero outside the
+//     image).  The vertical taps are stacked on N the same way: "next N block" is made "next tile row" (LBO = row
+//     pitch), so N = ks * nb and accumulator column block j holds tap dy = ks-1-j
+//     (sum_p x[p + (dy,dx)] b[p] = sum_q x[q + dx] b[q - dy*W]).
+//   * K = 16 pixels per MMA = one tile row; one row costs ceil(ks / (128/C)) MMAs of M = 128, N = ks * nb.
 // Persistent CTAs split the pixel range; grid.y = input-channel chunk, grid.z = output-channel block.  Accumulators:
-// ks * ceil(ks / (128/C)) tap groups x N columns in TMEM.
+// ceil(ks / (128/C)) dx groups x (ks * nb) columns in TMEM.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -35,8 +39,8 @@ struct WgGeom {
   int nchunk0;    // chunks taken from x0 (the rest from x1)
   int tpm;        // dx taps stacked in one M=128 MMA
   int G;          // dx groups
-  int nblk;       // output channels per CTA
-  int nspan;      // channels per N block in smem (<= 64)
+  int nblk;       // output channels per CTA = one swizzle span (<= 64)
+  int nspan;      // == nblk
   int S;          // pipeline stages
   uint32_t x_bytes, b_bytes, stage_bytes, x_tx, b_tx;
   uint32_t lay_x, lay_b;  // UMMA layout codes
@@ -156,7 +160,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   const int c_src = (from0 ? chunk : chunk - g.nchunk0) * C;                 // channel offset inside its source
   const int c_glob = from0 ? chunk * C : g.nchunk0 * C + (chunk - g.nchunk0) * C;  // ... inside the weight
   const int co0 = blockIdx.z * g.nblk;
-  const int nb_blocks = g.nblk / g.nspan;
 
   if (warp == 0) {
     int s = 0;
@@ -170,24 +173,24 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
       if (elect_one()) {
         const uint32_t st = base + s * g.stage_bytes;
         mbar_expect_tx(full + 8 * s, g.x_tx + g.b_tx);
-        tma_load_4d(st, from0 ? &tmX0 : &tmX1, full + 8 * s, c_src, w0 - PAD, h0 - PAD, n);
-        for (int j = 0; j < nb_blocks; ++j)
-          tma_load_4d(st + g.x_bytes + j * (R * 16 * g.nspan * 2), &tmB, full + 8 * s, co0 + j * g.nspan, w0, h0, n);
+        tma_load_4d(st, from0 ? &tmX0 : &tmX1, full + 8 * s, c_src, w0 - PAD, h0, n);
+        tma_load_4d(st + g.x_bytes, &tmB, full + 8 * s, co0, w0, h0 - PAD, n);
       }
       __syncwarp();
       if (++s == g.S) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // instruction descriptor: D=f32, A=B=bf16, A and B MN-major, M=128, N=nblk
+    const uint32_t ncols = (uint32_t)(KS * g.nblk);  // N = vertical taps x output channels
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                           ((uint32_t)(g.nblk >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                           ((ncols >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     // A: M blocks (C channels) step by one pixel (LBO = span); K groups of 8 pixels step by 8 pixels (SBO = 8*span)
     const uint32_t hiA = ((uint32_t)(8 * SPAN) >> 4) | (1u << 14) | (g.lay_x << 29);
     constexpr uint32_t loA_lbo = ((uint32_t)SPAN >> 4) << 16;
-    // B: N blocks of nspan channels are separate [R*16 px] sub-tiles (LBO = sub-tile bytes); SBO = 8 pixel rows
+    // B: N blocks (nb channels) step by one tile row (LBO = 16 pixels); K groups of 8 pixels step by 8 pixels
     const uint32_t bspan = g.nspan * 2;
     const uint32_t hiB = ((uint32_t)(8 * bspan) >> 4) | (1u << 14) | (g.lay_b << 29);
-    const uint32_t loB_lbo = ((uint32_t)(R * 16 * bspan) >> 4) << 16;
+    const uint32_t loB_lbo = ((uint32_t)(16 * bspan) >> 4) << 16;
     int s = 0;
     uint32_t ph = 0;
     uint32_t first = 1;
@@ -210,13 +213,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           const uint32_t b_lo = (ba + (uint32_t)r * b_row) | loB_lbo;
           const uint32_t acc = r == 0 ? (first ^ 1u) : 1u;
 #pragma unroll
-          for (int dy = 0; dy < KS; ++dy) {
-#pragma unroll
-            for (int gi = 0; gi < G; ++gi) {
-              const uint32_t a_lo = (xa + (uint32_t)((((r + dy) * HT + gi * TPM) * SPAN) >> 4)) | loA_lbo;
-              tc_mma(tmem_base + (uint32_t)(dy * G + gi) * (uint32_t)g.nblk, ((uint64_t)hiA << 32) | a_lo,
-                     ((uint64_t)hiB << 32) | b_lo, idesc, acc);
-            }
+          for (int gi = 0; gi < G; ++gi) {
+            const uint32_t a_lo = (xa + (uint32_t)(((r * HT + gi * TPM) * SPAN) >> 4)) | loA_lbo;
+            tc_mma(tmem_base + (uint32_t)gi * ncols, ((uint64_t)hiA << 32) | a_lo, ((uint64_t)hiB << 32) | b_lo, idesc,
+                   acc);
           }
         }
         tc_commit(empty + 8 * s);
@@ -234,12 +234,13 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     const int q = warp & 3;
     const int m = q * 32 + lane;        // accumulator row = (dx_local, ci)
     const int dxl = m / C, ci = m - dxl * C;
-    for (int dy = 0; dy < KS; ++dy)
-      for (int gi = 0; gi < G; ++gi) {
-        const int dx = gi * TPM + dxl;
+    for (int gi = 0; gi < G; ++gi) {
+      const int dx = gi * TPM + dxl;
+      for (int jb = 0; jb < KS; ++jb) {
+        const int dy = KS - 1 - jb;  // column block jb pairs x row r with b row r - pad + jb
         for (int j = 0; j < g.nblk / 16; ++j) {
           float v[16];
-          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((dy * G + gi) * g.nblk + j * 16), v);
+          tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(gi * KS * g.nblk + jb * g.nblk + j * 16), v);
           if (dx < KS) {
             float* dst = dw + ((size_t)(dy * KS + dx) * g.cin_total + c_glob + ci) * g.cout_total + co0 + j * 16;
 #pragma unroll
@@ -250,6 +251,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           }
         }
       }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -289,18 +291,16 @@ bool plan_w(const WgradArgs& a, WgGeom* g, uint32_t* smem) {
   while (C > 16 && (a.C0 % C || a.C1 % C)) C /= 2;
   const int tpm = 128 / C;
   const int G = (a.ks + tpm - 1) / tpm;
-  // output-channel block: as large as TMEM (ks*G*nblk <= 512 columns) and the MMA (N <= 256) allow
-  int nblk = a.Cout;
-  while (nblk > 16 && (a.ks * G * nblk > 512 || nblk > 256 || a.Cout % nblk)) nblk /= 2;
-  if (a.ks * G * nblk > 512 || nblk % 16 || a.Cout % nblk) return false;
-  int nspan = 64;
-  while (nspan > 16 && nblk % nspan) nspan /= 2;
-  if (nblk % nspan) return false;
+  // output-channel block per CTA: one swizzle span, with N = ks * nblk <= 256 and G * N <= 512 TMEM columns
+  int nblk = 64;
+  while (nblk > 16 && (a.Cout % nblk || a.ks * nblk > 256 || G * a.ks * nblk > 512)) nblk /= 2;
+  if (a.Cout % nblk || a.ks * nblk > 256 || G * a.ks * nblk > 512) return false;
+  const int nspan = nblk;
   const int ht = 16 + a.ks - 1;
   g->tiles_w = a.W / 16; g->tiles_h = a.H / 16;
   g->C = C; g->nchunk0 = a.C0 / C; g->tpm = tpm; g->G = G; g->nblk = nblk; g->nspan = nspan;
-  g->x_tx = (uint32_t)(R + a.ks - 1) * ht * C * 2;
-  g->b_tx = (uint32_t)R * 16 * nblk * 2;
+  g->x_tx = (uint32_t)R * ht * C * 2;
+  g->b_tx = (uint32_t)(R + a.ks - 1) * 16 * nblk * 2;
   // the last dx group may read up to tpm-1 pixels past the halo row end of the last row: keep slack inside the stage
   g->x_bytes = round1024(g->x_tx + 128 * 2 * 8);
   g->b_bytes = round1024(g->b_tx);
@@ -311,7 +311,7 @@ bool plan_w(const WgradArgs& a, WgGeom* g, uint32_t* smem) {
   g->S = S;
   g->lay_x = lay_code(C); g->lay_b = lay_code(nspan);
   int cols = 32;
-  while (cols < a.ks * G * nblk) cols *= 2;
+  while (cols < a.ks * G * nblk) cols *= 2;  // G dx groups x (ks * nblk) columns
   g->tmem_cols = cols;
   g->cin_total = a.C0 + a.C1; g->cout_total = a.Cout;
   *smem = 1024 + S * g->stage_bytes + 8 * (2 * S + 1) + 64;
@@ -356,10 +356,10 @@ int conv_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   DG_REQUIRE(plan_w(a, &g, &smem), "conv_wgrad_tc: unsupported shape");
   const int ht = 16 + a.ks - 1;
   CUtensorMap tmX0, tmX1, tmB;
-  DG_TRY(make_map(&tmX0, a.x0, a.C0, a.W, a.H, a.N, g.C, ht, R + a.ks - 1));
-  if (a.C1 > 0) DG_TRY(make_map(&tmX1, a.x1, a.C1, a.W, a.H, a.N, g.C, ht, R + a.ks - 1));
+  DG_TRY(make_map(&tmX0, a.x0, a.C0, a.W, a.H, a.N, g.C, ht, R));
+  if (a.C1 > 0) DG_TRY(make_map(&tmX1, a.x1, a.C1, a.W, a.H, a.N, g.C, ht, R));
   else tmX1 = tmX0;
-  DG_TRY(make_map(&tmB, a.dy, a.Cout, a.W, a.H, a.N, g.nspan, 16, R));
+  DG_TRY(make_map(&tmB, a.dy, a.Cout, a.W, a.H, a.N, g.nspan, 16, R + a.ks - 1));
   const int chunks = (a.C0 + a.C1) / g.C, coblocks = a.Cout / g.nblk;
   const long long items = (long long)g.tiles_w * g.tiles_h * 2 * a.N;
   long long gx = g_sms_w / (chunks * coblocks);
