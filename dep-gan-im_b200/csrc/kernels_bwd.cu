@@ -187,6 +187,95 @@ __global__ void __launch_bounds__(256) critic_head_bwd_kernel(const T* h, const 
   }
 }
 
+
+// ---- 8-channel (16-byte) bf16 vector helpers for the bandwidth-bound passes below ----
+struct Bf8 {
+  uint4 q;
+  __device__ __forceinline__ void load(const bf16* p) { q = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = q; }
+  __device__ __forceinline__ float get(int i) const {
+    const uint32_t w = (&q.x)[i >> 1];
+    return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
+  }
+  __device__ __forceinline__ void set(const float (&v)[8]) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  }
+};
+
+// bf16 fast path of critic_head_bwd_kernel (C % 8 == 0): 16-byte accesses, grid = (rows, SPLIT) over the pixels.
+__global__ void __launch_bounds__(256) critic_head_bwd_vec_kernel(const bf16* h, const bf16* v, const float* go,
+                                                                  const float* w9, const float* b9, const float* wd,
+                                                                  bf16* dh, float* d_w9, float* d_b9, float* d_wd,
+                                                                  float* d_bd, int n_reg, int HW, int C,
+                                                                  int want_param_grads) {
+  extern __shared__ float s_w9acc[];  // [C] partial d_w9 of this CTA
+  const int s = blockIdx.x;
+  const float g = go[s];
+  const bool reg = s < n_reg;
+  const bf16* hs = h + (size_t)s * HW * C;
+  const bf16* src = reg ? hs : (v ? v + (size_t)(s - n_reg) * HW * C : nullptr);
+  const float wgt = reg ? g : 1.f;
+  const int cv = C / 8;                       // vectors per pixel
+  const int ppc = (HW + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * ppc, p1 = min(HW, p0 + ppc);
+  if (dh) {
+    bf16* o = dh + (size_t)s * HW * C;
+    for (int i = p0 * cv + threadIdx.x; i < p1 * cv; i += blockDim.x) {
+      const int p = i / cv, c0 = (i - p * cv) * 8;
+      Bf8 hv, ov;
+      hv.load(hs + (size_t)i * 8);
+      const float gw = g * wd[p];
+      float r[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = hv.get(k) > 0.f ? gw * w9[c0 + k] : 0.f;
+      ov.set(r);
+      ov.store(o + (size_t)i * 8);
+    }
+  }
+  if (!want_param_grads || !src) return;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_w9acc[c] = 0.f;
+  __syncthreads();
+  // warp per pixel: d_wd[p] += wgt * (sum_c w9[c] src[p,c] + (reg ? b9 : 0)); lanes keep d_w9 partials of their channels
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int cb0 = 0; cb0 < cv; cb0 += 32) {
+    const int cb = cb0 + lane;
+    const bool act = cb < cv;
+    float w8[8], acc9[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { w8[k] = act ? w9[cb * 8 + k] : 0.f; acc9[k] = 0.f; }
+    for (int p = p0 + warp; p < p1; p += 8) {
+      float d = 0.f;
+      if (act) {
+        Bf8 x;
+        x.load(src + ((size_t)p * cv + cb) * 8);
+        const float wp = wd[p];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xv = x.get(k);
+          d = fmaf(xv, w8[k], d);
+          acc9[k] = fmaf(xv, wp, acc9[k]);
+        }
+      }
+      d = warp_sum(d);
+      if (lane == 0) atomicAdd(d_wd + p, wgt * (d + ((reg && cb0 == 0) ? b9[0] : 0.f)));
+    }
+    if (act) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&s_w9acc[cb * 8 + k], acc9[k]);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(d_w9 + c, wgt * s_w9acc[c]);
+  if (reg && blockIdx.y == 0 && threadIdx.x == 0) {
+    float swd = 0.f;
+    for (int p = 0; p < HW; ++p) swd += wd[p];
+    atomicAdd(d_b9, g * swd);
+    atomicAdd(d_bd, g);
+  }
+}
+
 // Gradient penalty pieces (TG:543-545): per sample norm = sqrt(sum g^2); gp_partial += (norm-1)^2 / global_n;
 // u = delta * (2/global_n) * (norm-1)/norm * g  (the input of the JVP pass).  One CTA per sample.
 __global__ void __launch_bounds__(256) gp_kernel(const float* g, float* u, float* gp_out, long long hw, float delta,
@@ -356,6 +445,80 @@ __global__ void s2d_mask_kernel(const T* d_up, int dstride, const T* up, T* out,
   }
 }
 
+// bf16 fast path (C, dstride multiples of 8): one thread per 8 channels, 16-byte accesses
+__global__ void s2d_mask_vec_kernel(const bf16* d_up, int dstride, const bf16* up, bf16* out, int N, int H, int W, int C) {
+  const int cv = C / 8;
+  const size_t total = (size_t)N * H * W * 4 * cv;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    const int ab = (int)((i / cv) % 4);
+    const size_t p = i / (4 * (size_t)cv);
+    const int w = (int)(p % W), h = (int)((p / W) % H);
+    const size_t n = p / ((size_t)W * H);
+    const size_t op = (n * 2 * H + 2 * h + (ab >> 1)) * (2 * (size_t)W) + 2 * w + (ab & 1);
+    Bf8 d, o;
+    d.load(d_up + op * dstride + c0);
+    if (up) {
+      Bf8 m;
+      m.load(up + op * C + c0);
+      float r[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = m.get(k) > 0.f ? d.get(k) : 0.f;
+      o.set(r);
+    } else {
+      o = d;
+    }
+    o.store(out + i * 8);
+  }
+}
+
+// bf16 fast path of gen_head_bwd_kernel (C % 8 == 0, C <= 256): C/8 lanes share a pixel, 16-byte accesses
+__global__ void __launch_bounds__(256) gen_head_bwd_vec_kernel(const float* gy2, const float* gdem, const float* l1g,
+                                                               const float* dem, const bf16* o, const float* w, bf16* d_o,
+                                                               float* d_w, float* d_b, long long npix, int C) {
+  extern __shared__ float s_dw[];  // [C] + 1
+  for (int i = threadIdx.x; i <= C; i += blockDim.x) s_dw[i] = 0.f;
+  __syncthreads();
+  const int cv = C / 8;                 // lanes per pixel (power of two <= 32)
+  const int cl = threadIdx.x % cv;      // this thread's channel group
+  const long long slot = (blockIdx.x * (long long)blockDim.x + threadIdx.x) / cv;
+  const long long nslots = ((long long)gridDim.x * blockDim.x) / cv;
+  float w8[8], accw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { w8[k] = w[cl * 8 + k]; accw[k] = 0.f; }
+  float accb = 0.f;
+  for (long long p = slot; p < npix; p += nslots) {
+    const float d = dem[p];
+    const float ds = (gy2[p] + gdem[p] + l1g[p]) * (1.f - d * d);
+    if (cl == 0) accb += ds;
+    Bf8 ov, dv;
+    ov.load(o + p * C + cl * 8);
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float x = ov.get(k);
+      accw[k] = fmaf(x, ds, accw[k]);
+      r[k] = x > 0.f ? ds * w8[k] : 0.f;
+    }
+    dv.set(r);
+    dv.store(d_o + p * C + cl * 8);
+  }
+  // lanes with the same channel group sit cv apart: fold them inside the warp first
+  for (int off = 16; off >= cv; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) accw[k] += __shfl_down_sync(0xffffffffu, accw[k], off);
+    accb += __shfl_down_sync(0xffffffffu, accb, off);
+  }
+  if ((threadIdx.x & 31) < cv) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomicAdd(&s_dw[cl * 8 + k], accw[k]);
+    if (cl == 0) atomicAdd(&s_dw[C], accb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(d_w + i, s_dw[i]);
+  if (threadIdx.x == 0) atomicAdd(d_b, s_dw[C]);
+}
+
 // dst[row, 0:C] = src[row, off:off+C] (+ add[row, 0:C])   -- channel slice of the concat gradient
 template <typename T>
 __global__ void slice_add_kernel(const T* src, int sstride, int off, const T* add, T* dst, long long rows, int C) {
@@ -521,6 +684,14 @@ int k_critic_head_bwd(const void* h, const void* v, const float* go, const float
                       void* dh, float* d_w9, float* d_b9, float* d_wd, float* d_bd, int rows, int n_reg, int HW, int C,
                       int want_param_grads, int dt, cudaStream_t st) {
   if (rows == 0) return 0;
+  if (dt == DT_BF16 && C % 8 == 0) {
+    const int split = HW >= 64 ? 4 : 1;
+    critic_head_bwd_vec_kernel<<<dim3(rows, split), 256, C * sizeof(float), st>>>(
+        (const bf16*)h, (const bf16*)v, go, w9, b9, wd, (bf16*)dh, d_w9, d_b9, d_wd, d_bd, n_reg, HW, C,
+        want_param_grads);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (critic_head_bwd_kernel<float><<<rows, 256, 0, st>>>((const float*)h, (const float*)v, go, w9, b9, wd,
                                                                   (float*)dh, d_w9, d_b9, d_wd, d_bd, n_reg, HW, C,
@@ -567,6 +738,12 @@ int k_gen_head_bwd(const float* gy2, const float* gdem, const float* l1g, const 
   DG_REQUIRE(C <= 256, "gen_head_bwd: C must be <= 256");
   const int grid = grid_for(npix * 32, 256, 148 * 8);
   const size_t smem = (C + 1) * sizeof(float);
+  if (dt == DT_BF16 && C % 8 == 0 && (C / 8 == 1 || C / 8 == 2 || C / 8 == 4 || C / 8 == 8 || C / 8 == 16 || C / 8 == 32)) {
+    gen_head_bwd_vec_kernel<<<grid_for(npix * (C / 8), 256, 148 * 8), 256, smem, st>>>(
+        gy2, gdem, l1g, dem, (const bf16*)o, w, (bf16*)d_o, d_w, d_b, npix, C);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (gen_head_bwd_kernel<float><<<grid, 256, smem, st>>>(gy2, gdem, l1g, dem, (const float*)o, w, (float*)d_o,
                                                                   d_w, d_b, npix, C)),
@@ -607,6 +784,12 @@ int k_s2d_mask(const void* d_up, int dstride, const void* up, void* out, int N, 
                cudaStream_t st) {
   const long long total = (long long)N * H * W * 4 * C;
   if (total == 0) return 0;
+  if (dt == DT_BF16 && C % 8 == 0 && dstride % 8 == 0) {
+    s2d_mask_vec_kernel<<<grid_for(total / 8), 256, 0, st>>>((const bf16*)d_up, dstride, (const bf16*)up, (bf16*)out, N,
+                                                             H, W, C);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (s2d_mask_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)d_up, dstride, (const float*)up,
                                                                       (float*)out, N, H, W, C)),

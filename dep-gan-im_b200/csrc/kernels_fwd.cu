@@ -237,6 +237,43 @@ __global__ void __launch_bounds__(256) critic_head_fwd_kernel(const T* in, const
   }
 }
 
+// bf16 fast path (C % 8 == 0): 16-byte loads, each lane owns 8 channels of a pixel
+__global__ void __launch_bounds__(256) critic_head_fwd_vec_kernel(const bf16* in, const float* w9, const float* b9,
+                                                                  const float* wd, const float* bd, float* out, int HW,
+                                                                  int C) {
+  __shared__ float s_part[8];
+  const int n = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cv = C / 8;
+  float acc = 0.f;
+  for (int cb = lane; cb < cv; cb += 32) {
+    float w8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) w8[k] = w9[cb * 8 + k];
+    for (int p = warp; p < HW; p += 8) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(in + ((size_t)n * HW + p) * C + cb * 8));
+      const uint32_t* u = &q.x;
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        d = fmaf(__uint_as_float(u[k] << 16), w8[2 * k], d);
+        d = fmaf(__uint_as_float(u[k] & 0xFFFF0000u), w8[2 * k + 1], d);
+      }
+      acc = fmaf(d, wd[p], acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) s_part[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = bd[0];
+    for (int i = 0; i < 8; ++i) s += s_part[i];
+    float swd = 0.f;  // the dis_9 bias reaches every pixel of the Dense layer
+    for (int p = 0; p < HW; ++p) swd += wd[p];
+    out[n] = s + b9[0] * swd;
+  }
+}
+
 template <typename T>
 __global__ void convert_in_kernel(const float* src, T* dst, long long n) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -420,6 +457,8 @@ int k_critic_head_fwd(const void* in, const float* w9, const float* b9, const fl
   if (N == 0) return 0;
   if (dt == DT_F32)
     critic_head_fwd_kernel<float><<<N, 256, 0, st>>>((const float*)in, w9, b9, wd, bd, out, HW, C);
+  else if (C % 8 == 0)
+    critic_head_fwd_vec_kernel<<<N, 256, 0, st>>>((const bf16*)in, w9, b9, wd, bd, out, HW, C);
   else
     critic_head_fwd_kernel<bf16><<<N, 256, 0, st>>>((const bf16*)in, w9, b9, wd, bd, out, HW, C);
   DG_LAUNCH_CHECK();
