@@ -36,6 +36,94 @@ __device__ __forceinline__ int first_argmax(const T* b, size_t C, size_t WC) {
   return k;
 }
 
+// ---- 8-channel (16-byte) bf16 vector helpers for the bandwidth-bound passes below ----
+struct Bf8 {
+  uint4 q;
+  __device__ __forceinline__ void load(const bf16* p) { q = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = q; }
+  __device__ __forceinline__ float get(int i) const {
+    const uint32_t w = (&q.x)[i >> 1];
+    return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
+  }
+  __device__ __forceinline__ void set(const float (&v)[8]) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  }
+};
+
+// bf16 fast paths of the two max-pool passes below (C % 8 == 0): one thread per pooled pixel and 8 channels
+__device__ __forceinline__ void pool_window8(const bf16* x, size_t base, size_t C, size_t WC, int (&k)[8]) {
+  Bf8 w[4];
+  w[0].load(x + base); w[1].load(x + base + C); w[2].load(x + base + WC); w[3].load(x + base + WC + C);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float m = w[0].get(j);
+    int kk = 0;
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float v = w[q].get(j);
+      if (v > m) { m = v; kk = q; }
+    }
+    k[j] = kk;
+  }
+}
+__global__ void maxpool_bwd_vec_kernel(const bf16* dy, const bf16* x, const bf16* add_src, bf16* dx, int N, int H, int W,
+                                       int C) {
+  const int Ho = H / 2, Wo = W / 2, cv = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * cv;
+  const size_t WC = (size_t)W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    const size_t p = i / cv;
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho);
+    const size_t n = p / ((size_t)Wo * Ho);
+    const size_t base = ((n * H + 2 * ho) * W + 2 * wo) * C + c0;
+    int k[8];
+    pool_window8(x, base, C, WC, k);
+    Bf8 g;
+    g.load(dy + i * 8);
+    const size_t offs[4] = {base, base + (size_t)C, base + WC, base + WC + C};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = k[j] == q ? g.get(j) : 0.f;
+      if (add_src) {
+        Bf8 ad;
+        ad.load(add_src + offs[q]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += ad.get(j);
+      }
+      Bf8 o;
+      o.set(v);
+      o.store(dx + offs[q]);
+    }
+  }
+}
+__global__ void maxpool_select_vec_kernel(const bf16* v, const bf16* x, bf16* out, int N, int H, int W, int C) {
+  const int Ho = H / 2, Wo = W / 2, cv = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * cv;
+  const size_t WC = (size_t)W * C;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    const size_t p = i / cv;
+    const int wo = (int)(p % Wo), ho = (int)((p / Wo) % Ho);
+    const size_t n = p / ((size_t)Wo * Ho);
+    const size_t base = ((n * H + 2 * ho) * W + 2 * wo) * C + c0;
+    int k[8];
+    pool_window8(x, base, C, WC, k);
+    Bf8 w[4];
+    w[0].load(v + base); w[1].load(v + base + C); w[2].load(v + base + WC); w[3].load(v + base + WC + C);
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = k[j] == 0 ? w[0].get(j) : k[j] == 1 ? w[1].get(j) : k[j] == 2 ? w[2].get(j) : w[3].get(j);
+    Bf8 o;
+    o.set(r);
+    o.store(out + i * 8);
+  }
+}
+
 // dx (N,H,W,C) = route dy (N,H/2,W/2,C) to the first argmax of x in each window; optional add_src accumulates
 // a second gradient arriving at the same tensor (skip connections of the generator).
 template <typename T>
@@ -80,6 +168,39 @@ __global__ void maxpool_select_kernel(const T* v, const T* x, T* out, int N, int
 }
 
 // out[c] += alpha * sum_rows src[row, c]   (rows x C row-major).  CTA = 32 channels x 8 row lanes.
+// bf16 fast path of channel_sum_kernel (C % 8 == 0, C/8 divides 256): 16-byte loads, a warp reads 512 contiguous bytes
+__global__ void __launch_bounds__(256) channel_sum_vec_kernel(const bf16* src, long long rows, int C, float* out,
+                                                              float alpha, long long rows_per_cta) {
+  extern __shared__ float s_cs[];  // [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s_cs[i] = 0.f;
+  __syncthreads();
+  const int cv = C / 8;
+  const int cg = threadIdx.x % cv, ro = threadIdx.x / cv, rstep = blockDim.x / cv;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  const long long r1 = min(rows, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  long long r = r0 + ro;
+  for (; r + rstep < r1; r += 2 * rstep) {  // two independent loads in flight
+    Bf8 x0, x1;
+    x0.load(src + (r * cv + cg) * 8);
+    x1.load(src + ((r + rstep) * cv + cg) * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += x0.get(k) + x1.get(k);
+  }
+  if (r < r1) {
+    Bf8 x0;
+    x0.load(src + (r * cv + cg) * 8);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] += x0.get(k);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) atomicAdd(&s_cs[cg * 8 + k], acc[k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(out + i, alpha * s_cs[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) channel_sum_kernel(const T* src, long long rows, int C, float* out, float alpha,
                                                           long long rows_per_cta) {
@@ -187,22 +308,6 @@ __global__ void __launch_bounds__(256) critic_head_bwd_kernel(const T* h, const 
   }
 }
 
-
-// ---- 8-channel (16-byte) bf16 vector helpers for the bandwidth-bound passes below ----
-struct Bf8 {
-  uint4 q;
-  __device__ __forceinline__ void load(const bf16* p) { q = __ldg(reinterpret_cast<const uint4*>(p)); }
-  __device__ __forceinline__ void store(bf16* p) const { *reinterpret_cast<uint4*>(p) = q; }
-  __device__ __forceinline__ float get(int i) const {
-    const uint32_t w = (&q.x)[i >> 1];
-    return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
-  }
-  __device__ __forceinline__ void set(const float (&v)[8]) {
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  }
-};
 
 // bf16 fast path of critic_head_bwd_kernel (C % 8 == 0): 16-byte accesses, grid = (rows, SPLIT) over the pixels.
 __global__ void __launch_bounds__(256) critic_head_bwd_vec_kernel(const bf16* h, const bf16* v, const float* go,
@@ -638,6 +743,12 @@ int k_maxpool_bwd(const void* dy, const void* x, const void* add_src, void* dx, 
                   cudaStream_t st) {
   const long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total == 0) return 0;
+  if (dt == DT_BF16 && C % 8 == 0) {
+    maxpool_bwd_vec_kernel<<<grid_for(total / 8), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)add_src,
+                                                                (bf16*)dx, N, H, W, C);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (maxpool_bwd_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)dy, (const float*)x,
                                                                          (const float*)add_src, (float*)dx, N, H, W, C)),
@@ -650,6 +761,11 @@ int k_maxpool_bwd(const void* dy, const void* x, const void* add_src, void* dx, 
 int k_maxpool_select(const void* v, const void* x, void* out, int N, int H, int W, int C, int dt, cudaStream_t st) {
   const long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total == 0) return 0;
+  if (dt == DT_BF16 && C % 8 == 0) {
+    maxpool_select_vec_kernel<<<grid_for(total / 8), 256, 0, st>>>((const bf16*)v, (const bf16*)x, (bf16*)out, N, H, W, C);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (maxpool_select_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)v, (const float*)x,
                                                                             (float*)out, N, H, W, C)),
@@ -661,6 +777,15 @@ int k_maxpool_select(const void* v, const void* x, void* out, int N, int H, int 
 
 int k_channel_sum(const void* src, long long rows, int C, float* out, float alpha, int dt, cudaStream_t st) {
   if (rows == 0) return 0;
+  if (dt == DT_BF16 && C % 8 == 0 && 256 % (C / 8) == 0) {
+    long long gv = (rows + 1023) / 1024;
+    if (gv > 148 * 8) gv = 148 * 8;
+    const long long rpcv = (rows + gv - 1) / gv;
+    channel_sum_vec_kernel<<<(unsigned)((rows + rpcv - 1) / rpcv), 256, C * sizeof(float), st>>>((const bf16*)src, rows, C,
+                                                                                                 out, alpha, rpcv);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   long long gx = (rows + 2047) / 2048;
   if (gx > 148 * 4) gx = 148 * 4;
   const long long rpc = (rows + gx - 1) / gx;
