@@ -55,6 +55,8 @@ int k_dem_accumulate(double* acc, const float* pred, const float* mask, long lon
 int k_dem_postproc(const float* x, int nicg, const double* acc, double n_repeat, const float* mask, double thr,
                    double* dem_out, double* fake2_out, unsigned char* labels, unsigned long long* count,
                    long long npix, cudaStream_t st);
+int k_label_confusion(const unsigned char* fake, const unsigned char* real, long long n, unsigned long long* conf,
+                      cudaStream_t st);
 int k_uresnet_labels(const double* acc, double n_repeat, int chan, double* mean_out, unsigned char* labels,
                      unsigned long long* count, long long npix, cudaStream_t st);
 

@@ -360,6 +360,35 @@ __global__ void uresnet_labels_kernel(const double* acc, double n_repeat, int ch
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, local);
 }
 
+// 4x4 confusion counts of two label maps with values 0..3 (conf[4*real + fake]); everything the evaluation rows need
+// (EG:688-807, EU:606-704) derives from these 16 integers.  Labels outside 0..3 are counted nowhere.
+__global__ void __launch_bounds__(256) label_confusion_kernel(const unsigned char* fake, const unsigned char* real,
+                                                              long long n, unsigned long long* conf) {
+  __shared__ unsigned int s_c[16];
+  if (threadIdx.x < 16) s_c[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned int local[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) local[k] = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned int f = fake[i], r = real[i];
+    if (f < 4u && r < 4u) {
+      const unsigned int idx = 4u * r + f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) local[k] += (idx == (unsigned)k) ? 1u : 0u;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    unsigned int v = local[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_c[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 16 && s_c[threadIdx.x]) atomicAdd(conf + threadIdx.x, (unsigned long long)s_c[threadIdx.x]);
+}
+
 __global__ void adam_kernel(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2,
                             float eps, float gscale) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -520,6 +549,19 @@ int k_uresnet_labels(const double* acc, double n_repeat, int chan, double* mean_
   DG_CHECK_CUDA(cudaMemsetAsync(count, 0, sizeof(unsigned long long), st));
   if (npix == 0) return 0;
   uresnet_labels_kernel<<<grid_for(npix), 256, 0, st>>>(acc, n_repeat, chan, mean_out, labels, count, npix);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_label_confusion(const unsigned char* fake, const unsigned char* real, long long n, unsigned long long* conf,
+                      cudaStream_t st) {
+  DG_CHECK_CUDA(cudaMemsetAsync(conf, 0, 16 * sizeof(unsigned long long), st));
+  if (n == 0) return 0;
+  // per-thread counters are 32-bit: bound the elements a thread sees
+  long long blocks = (n + 256LL * 4096 - 1) / (256LL * 4096);
+  if (blocks < 148 * 4) blocks = 148 * 4;
+  if (blocks > (n + 255) / 256) blocks = (n + 255) / 256;
+  label_confusion_kernel<<<(unsigned)blocks, 256, 0, st>>>(fake, real, n, conf);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -555,6 +555,12 @@ int depgan_dem_postproc(const float* x_dev, int nicg, const double* acc_dev, dou
   return k_dem_postproc(x_dev, nicg, acc_dev, n_repeat, mask_dev, thr, dem_out_dev, fake2_out_dev, labels_dev,
                         count_dev, npix, (cudaStream_t)stream);
 }
+int depgan_label_confusion(const unsigned char* fake_labels_dev, const unsigned char* real_labels_dev, long long n,
+                            unsigned long long* conf16_dev, void* stream) {
+  DG_REQUIRE(n >= 0 && conf16_dev && (n == 0 || (fake_labels_dev && real_labels_dev)), "label_confusion: bad arguments");
+  return k_label_confusion(fake_labels_dev, real_labels_dev, n, conf16_dev, (cudaStream_t)stream);
+}
+
 int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, double* mean_out_dev,
                           unsigned char* labels_dev, unsigned long long* count_dev, long long npix, void* stream) {
   DG_REQUIRE(chan >= 1 && labels_dev && count_dev, "uresnet_labels: bad arguments");

@@ -16,7 +16,8 @@ import numpy as np
 from . import postproc
 from .api import _torch
 
-__all__ = ["shard_range", "shard_items", "predict_subject_dem", "predict_subject_uresnet", "cohort_sweep"]
+__all__ = ["shard_range", "shard_items", "predict_subject_dem", "predict_subject_uresnet", "evaluate_subject",
+           "cohort_sweep"]
 
 
 def shard_range(n_items, rank, world):
@@ -93,13 +94,28 @@ def predict_subject_uresnet(net, vol, mask, n_repeat=10, seed=0, noises=None):
     return {"prob_mean": mean.cpu().numpy(), "labels": labels.cpu().numpy(), "wmh_voxels": int(count.item())}
 
 
+def evaluate_subject(result, real_labels, vol_1tp_ml, vol_2tp_ml, voxel_mm3, device="cuda:0"):
+    """The 18-entry evaluation row of the testing scripts (EG:681-684, 688-807 / EU:597-704) for one subject:
+    vol_out_ml = wmh_voxels * prod(pixdim) / 1000, volume-direction flags, six Dice scores from the GPU confusion
+    counts of the predicted label map against `real_labels` (the ground-truth code volume, values 0..3)."""
+    vol_out_ml = result["wmh_voxels"] * voxel_mm3 / 1000
+    return postproc.evaluate_labels(result["labels"], real_labels, vol_1tp_ml, vol_2tp_ml, vol_out_ml, device=device)
+
+
 def cohort_sweep(net, subjects, thr, rank=0, world=1, n_repeat=10, kind="dem"):
-    """subjects: list of (subject_id, vol, mask).  Each rank processes its contiguous shard; returns
-    {subject_id: result dict}.  No collective: gather the dictionaries on the host if a global table is wanted."""
+    """subjects: list of (subject_id, vol, mask) or (subject_id, vol, mask, truth) with truth = dict(labels,
+    vol_1tp_ml, vol_2tp_ml, voxel_mm3).  Each rank processes its contiguous shard; returns {subject_id: result dict}
+    (with "eval_row" when truth is given).  No collective: gather the dictionaries on the host if a global table is
+    wanted."""
     res = {}
-    for sid, vol, mask in shard_items(subjects, rank, world):
+    for item in shard_items(subjects, rank, world):
+        sid, vol, mask = item[0], item[1], item[2]
         if kind == "dem":
             res[sid] = predict_subject_dem(net, vol, mask, thr, n_repeat=n_repeat, seed=hash(sid) & 0x7FFFFFFF)
         else:
             res[sid] = predict_subject_uresnet(net, vol, mask, n_repeat=n_repeat, seed=hash(sid) & 0x7FFFFFFF)
+        if len(item) > 3 and item[3] is not None:
+            t = item[3]
+            res[sid]["eval_row"] = evaluate_subject(res[sid], t["labels"], t["vol_1tp_ml"], t["vol_2tp_ml"],
+                                                    t["voxel_mm3"], device=str(net.device))
     return res

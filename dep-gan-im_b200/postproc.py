@@ -81,3 +81,67 @@ def uresnet_pipeline(preds, mask, device="cuda:0"):
                                                     mean.data_ptr(), labels.data_ptr(), count.data_ptr(), m.numel(),
                                                     _stream(torch)), "uresnet_labels")
     return mean.cpu().numpy(), labels.cpu().numpy(), int(count.item())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Evaluation row of the testing scripts (EG:688-807, EU:601-704)
+# ---------------------------------------------------------------------------------------------------------
+def label_confusion_device(fake_labels, real_labels):
+    """4x4 confusion counts conf[real, fake] (int64 CUDA tensor) of two uint8 label maps with values 0..3."""
+    torch = _torch()
+    assert fake_labels.dtype == torch.uint8 and real_labels.dtype == torch.uint8
+    assert fake_labels.numel() == real_labels.numel()
+    conf = torch.zeros(16, dtype=torch.int64, device=fake_labels.device)
+    with torch.cuda.device(fake_labels.device):
+        _lib.check(_lib.lib().depgan_label_confusion(fake_labels.data_ptr(), real_labels.data_ptr(),
+                                                     fake_labels.numel(), conf.data_ptr(), _stream(torch)),
+                   "label_confusion")
+    return conf.view(4, 4)
+
+
+def dice_scores_from_confusion(conf):
+    """(dice_1 .. dice_6) exactly as EG:745-794 computes them: (2*|A and B| + 1e-7) / (1e-7 + |A| + |B|) on
+    1 shrink, 2 grow, 3 stay, 4 any WMH (label > 0), 5 changing (label 1 or 2), 6 stay again.  conf[real, fake]."""
+    c = np.asarray(conf, dtype=np.int64).reshape(4, 4)
+    smooth = 1e-7
+
+    def dice(sel):
+        sel = list(sel)
+        inter = int(c[np.ix_(sel, sel)].sum())
+        n_real = int(c[sel, :].sum())
+        n_fake = int(c[:, sel].sum())
+        return (inter * 2.0 + smooth) / (smooth + n_real + n_fake)
+
+    return dice([1]), dice([2]), dice([3]), dice([1, 2, 3]), dice([1, 2]), dice([3])
+
+
+def evaluation_row(conf, vol_1tp_ml, vol_2tp_ml, vol_out_ml):
+    """The 18-entry CSV row of the testing scripts (EG:806-807 / EU:703-704):
+    [true_pred, prog, true_prog, regg, true_regg, vol1, vol2, vol_out, mse, err, d5, d6, avg56, d1, d2, d3, d4,
+    avg123] from the confusion counts and the three WMH volumes in ml."""
+    err_vol = vol_out_ml - vol_2tp_ml                        # EG:688
+    mse_vol = float(np.mean((vol_2tp_ml - vol_out_ml) ** 2))  # EG:689
+    true_pred = true_prog = true_regg = prog = regg = 0
+    if (vol_2tp_ml - vol_1tp_ml) >= 0:                       # EG:697-706
+        prog = 1
+        if vol_out_ml - vol_1tp_ml >= 0:
+            true_pred = true_prog = 1
+    else:
+        regg = 1
+        if vol_out_ml - vol_1tp_ml < 0:
+            true_pred = true_regg = 1
+    d1, d2, d3, d4, d5, d6 = dice_scores_from_confusion(conf)
+    avg_all = (d1 + d2 + d3) / 3.0
+    avg_56 = (d5 + d6) / 2.0
+    return [true_pred, prog, true_prog, regg, true_regg, vol_1tp_ml, vol_2tp_ml, vol_out_ml, mse_vol, err_vol, d5, d6,
+            avg_56, d1, d2, d3, d4, avg_all]
+
+
+def evaluate_labels(fake_labels, real_labels, vol_1tp_ml, vol_2tp_ml, vol_out_ml, device="cuda:0"):
+    """NumPy convenience wrapper: label maps (any integer / float dtype holding 0..3) -> the 18-entry row."""
+    torch = _torch()
+    dev = torch.device(device)
+    f = torch.from_numpy(np.ascontiguousarray(fake_labels).astype(np.uint8)).to(dev)
+    r = torch.from_numpy(np.ascontiguousarray(real_labels).astype(np.uint8)).to(dev)
+    conf = label_confusion_device(f, r).cpu().numpy()
+    return evaluation_row(conf, vol_1tp_ml, vol_2tp_ml, vol_out_ml)

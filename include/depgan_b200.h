@@ -123,6 +123,13 @@ int depgan_dem_postproc(const float* x_dev, int nicg, const double* acc_dev, dou
 int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, double* mean_out_dev,
                           unsigned char* labels_dev, unsigned long long* count_dev, long long npix, void* stream);
 
+/* ---- evaluation of a predicted label map against the ground-truth one (EG:688-807 / EU:606-704) ----
+ * conf16[4*real + fake] = number of voxels with ground-truth label `real` and predicted label `fake` (labels 0..3:
+ * background / shrink / grow / stay).  The six Dice scores of the reference's CSV row are ratios of sums of these
+ * integers, so the row is exact given the label maps.  conf16_dev: 16 unsigned long long (zeroed by the call). */
+int depgan_label_confusion(const unsigned char* fake_labels_dev, const unsigned char* real_labels_dev, long long n,
+                           unsigned long long* conf16_dev, void* stream);
+
 /* ---- introspection for tests / profiling ---- */
 /* Number of kernels this library launched since load (all handles). */
 long long depgan_launch_count(void);

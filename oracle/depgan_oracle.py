@@ -527,3 +527,44 @@ def uresnet_train_step(P, x, z, onehot, drop_mask, opt=None):
                 P[name + "/moving_mean"].mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * mean)
                 P[name + "/moving_variance"].mul_(BN_MOMENTUM).add_((1 - BN_MOMENTUM) * var_unb)
     return float(loss.detach()), {k: v.detach() for k, v in gd.items()}, stats
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Evaluation row (EG:688-807, identical in EU:601-704) -- literal NumPy restatement on the label volumes
+# ---------------------------------------------------------------------------------------------------------
+def evaluation_row(fake_labels, real_labels, vol_1tp_ml, vol_2tp_ml, vol_out_ml):
+    """[true_pred, prog, true_prog, regg, true_regg, vol1, vol2, vol_out, mse, err, d5, d6, avg56, d1, d2, d3, d4,
+    avg123] (EG:806-807).  fake_labels / real_labels: arrays with values 0..3 (EG:713-741; brain_code_2tp)."""
+    wmh_change_mask_fake = np.squeeze(np.asarray(fake_labels))
+    wmh_change_mask_real = np.squeeze(np.asarray(real_labels))
+    err_vol = vol_out_ml - vol_2tp_ml
+    mse_vol = np.mean((vol_2tp_ml - vol_out_ml) ** 2)
+    true_pred = true_prog = true_regg = prog = regg = 0
+    if (vol_2tp_ml - vol_1tp_ml) >= 0:
+        prog = 1
+        if vol_out_ml - vol_1tp_ml >= 0:
+            true_pred = 1
+            true_prog = 1
+    else:
+        regg = 1
+        if vol_out_ml - vol_1tp_ml < 0:
+            true_pred = 1
+            true_regg = 1
+    smooth = 1e-7
+
+    def dsc(fake, real, k):  # EG:745-794, one expression for all six
+        return (np.count_nonzero(fake[real == k] == k) * 2.0 + smooth) / \
+               (smooth + np.count_nonzero(real[real == k] == k) + np.count_nonzero(fake[fake == k] == k))
+
+    dice_1 = dsc(wmh_change_mask_fake, wmh_change_mask_real, 1)
+    dice_2 = dsc(wmh_change_mask_fake, wmh_change_mask_real, 2)
+    dice_3 = dsc(wmh_change_mask_fake, wmh_change_mask_real, 3)
+    dice_4 = dsc(wmh_change_mask_fake > 0, wmh_change_mask_real > 0, 1)
+    temp_a_fake = (wmh_change_mask_fake == 1).astype(np.int64) + (wmh_change_mask_fake == 2)
+    temp_a_real = (wmh_change_mask_real == 1).astype(np.int64) + (wmh_change_mask_real == 2)
+    dice_5 = dsc(temp_a_fake > 0, temp_a_real > 0, 1)
+    dice_6 = dsc(wmh_change_mask_fake == 3, wmh_change_mask_real == 3, 1)
+    avg_all_dice = (dice_1 + dice_2 + dice_3) / 3.0
+    avg_dice__56 = (dice_5 + dice_6) / 2.0
+    return [true_pred, prog, true_prog, regg, true_regg, vol_1tp_ml, vol_2tp_ml, vol_out_ml, mse_vol, err_vol, dice_5,
+            dice_6, avg_dice__56, dice_1, dice_2, dice_3, dice_4, avg_all_dice]
