@@ -96,6 +96,7 @@ struct ConvArgs {
 
 int conv_fwd_simt(const ConvArgs& a, cudaStream_t st);
 int conv_fwd_tc(const ConvArgs& a, cudaStream_t st);  // tcgen05 path (bf16 in/out)
+int conv_first_tc_try(const ConvArgs& a, cudaStream_t st);  // tcgen05 first layer (fp32 image in): 1 taken, 0 not a case
 bool conv_tc_supported(const ConvArgs& a);
 int conv_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
 

@@ -3,6 +3,8 @@
 // (BASELINE.json: "FP32-accumulate variant within 1e-4") and the layer of last resort for shapes the
 // tcgen05 path does not take (Cin < 16 first layers, Cout = 1 dgrad of the critic's first layer).
 // Replaces Keras Conv2D (+BatchNormalization, +Activation) of TG:285-304 and its K.gradients (TG:543-549).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -645,6 +647,12 @@ int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
   if (a.N <= 0) return 0;
   DG_REQUIRE(!a.deconv && !a.head_w, "conv_fwd_simt: deconv/head fusion are tcgen05-path epilogues");
   {
+    // bf16 networks: the first layer runs on the tensor cores (split-bf16 image, conv_first_tc.cu)
+    static const bool no_first_tc = getenv("DEPGAN_NO_FIRST_TC") != nullptr;  // A/B switch for measurements
+    if (!no_first_tc) {
+      const int r0 = conv_first_tc_try(a, st);
+      if (r0 != 0) return r0 < 0 ? r0 : 0;
+    }
     const int r = a.out_dt == DT_BF16 ? try_first<bf16>(a, st) : try_first<float>(a, st);
     if (r != 0) return r < 0 ? r : 0;
     const int r2 = a.in_dt == DT_BF16 ? try_last<bf16>(a, st) : try_last<float>(a, st);

@@ -271,3 +271,47 @@ def test_tcgen05_ring_one_item_many_items(cin, cout, H, W, N):
     got = conv2d_op(x.cuda(), w.cuda(), use_tc=True).cpu()
     want, _ = ref_conv(x, w)
     assert float((got - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
+
+
+# ---- first layer on the tensor cores (conv_first_tc.cu): fp32 image split into two bf16 halves, bf16 weights ----
+def _first_layer_bf16_out(x, w, sc, sh, relu, mask=None):
+    """fp32 image + fp32 Keras weights -> bf16 activations through depgan_op_conv2d (the route the bf16 networks take
+    for conv2d_gen_0 / conv2d_dis_0a)."""
+    import ctypes as C
+    from depgan_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    N, H, W, c0 = x.shape
+    ks, cout = w.shape[0], w.shape[3]
+    keep = [x.to(dev).contiguous(), w.reshape(ks * ks * c0, cout).to(dev).contiguous(), sc.to(dev), sh.to(dev)]
+    out = torch.empty((N, H, W, cout), dtype=torch.bfloat16, device=dev)
+    d = _lib.ConvDesc()
+    d.in0, d.C0, d.C1 = keep[0].data_ptr(), c0, 0
+    d.w_f32, d.scale, d.shift, d.out = keep[1].data_ptr(), keep[2].data_ptr(), keep[3].data_ptr(), out.data_ptr()
+    if mask is not None:
+        keep.append(mask.to(dev).to(torch.bfloat16).contiguous())
+        d.mask_src = keep[-1].data_ptr()
+    d.relu, d.deconv = int(relu), 0
+    d.N, d.H, d.W, d.Cout, d.ks = N, H, W, cout, ks
+    d.in_bf16, d.out_bf16, d.use_tc = 0, 1, 0
+    _lib.check(L.depgan_op_conv2d(C.byref(d), st), "op_conv2d")
+    torch.cuda.synchronize()
+    return out.float().cpu()
+
+
+@pytest.mark.parametrize("ks,c0,cout,H,W,N,use_mask", [(5, 1, 16, 64, 48, 7, False), (5, 1, 16, 32, 32, 40, True),
+                                                       (3, 1, 32, 64, 64, 5, False), (3, 2, 32, 48, 80, 9, False)])
+def test_first_layer_tensor_core(ks, c0, cout, H, W, N, use_mask):
+    x = _rand((N, H, W, c0), 1)
+    w = _rand((ks, ks, c0, cout), 3, 0.2)
+    sc, sh = 1 + 0.1 * _rand((cout,), 4), 0.1 * _rand((cout,), 5)
+    mask = _rand((N, H, W, cout), 6) if use_mask else None
+    got = _first_layer_bf16_out(x, w, sc, sh, relu=not use_mask, mask=mask)
+    # the kernel keeps 16 mantissa bits of the image and rounds the weights to bf16 (like every layer of a bf16 net)
+    want, _ = ref_conv(x, _bf(w), None, sc, sh, relu=not use_mask, mask=None if mask is None else _bf(mask))
+    err = float((got - want).abs().max())
+    assert err <= 8e-3 * max(1.0, float(want.abs().max())), err   # bf16 output rounding
+    # and against exact weights: weight rounding only
+    want32, _ = ref_conv(x, w, None, sc, sh, relu=not use_mask, mask=None if mask is None else _bf(mask))
+    assert float((got - want32).abs().max()) <= 2e-2 * max(1.0, float(want32.abs().max()))
