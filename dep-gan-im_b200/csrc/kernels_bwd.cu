@@ -521,6 +521,99 @@ __global__ void __launch_bounds__(256) film_bwd_kernel(const T* d_r, const T* y,
   atomicAdd(dbet + (size_t)n * fstride + cl, ab);
 }
 
+// bf16 fast path of film_bwd_kernel (C % 8 == 0, C/8 divides 256): thread = 8 channels, 16-byte accesses
+__global__ void __launch_bounds__(256) film_bwd_vec_kernel(const bf16* d_r, const bf16* y, const float* fg,
+                                                           const float* fb, int fstride, bf16* d_y, float* dgam,
+                                                           float* dbet, int HW, int C, int pix_per_cta) {
+  extern __shared__ float s_fb[];  // [2][C] partial (dgamma, dbeta) of this CTA
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) s_fb[i] = 0.f;
+  __syncthreads();
+  const int n = blockIdx.y, cv = C / 8;
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const int cg = threadIdx.x % cv, pl = threadIdx.x / cv, pstep = blockDim.x / cv;
+  float g[8], b[8], ag[8], ab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    g[k] = fg[(size_t)n * fstride + cg * 8 + k];
+    b[k] = fb[(size_t)n * fstride + cg * 8 + k];
+    ag[k] = ab[k] = 0.f;
+  }
+  for (int p = p0 + pl; p < p1; p += pstep) {
+    const size_t i = (((size_t)n * HW + p) * cv + cg) * 8;
+    Bf8 yv, dv, ov;
+    yv.load(y + i);
+    dv.load(d_r + i);
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float yk = yv.get(k);
+      const float dt = fmaf(yk, g[k], b[k]) > 0.f ? dv.get(k) : 0.f;
+      r[k] = dt * g[k];
+      ag[k] = fmaf(dt, yk, ag[k]);
+      ab[k] += dt;
+    }
+    ov.set(r);
+    ov.store(d_y + i);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    atomicAdd(&s_fb[cg * 8 + k], ag[k]);
+    atomicAdd(&s_fb[C + cg * 8 + k], ab[k]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(dgam + (size_t)n * fstride + c, s_fb[c]);
+    atomicAdd(dbet + (size_t)n * fstride + c, s_fb[C + c]);
+  }
+}
+
+// bf16 fast paths of add_mask_kernel / slice_add_kernel: 8 elements per thread
+__global__ void add_mask_vec_kernel(const bf16* a, const bf16* b, const bf16* m, bf16* out, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    Bf8 av, o;
+    av.load(a + i * 8);
+    float r[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = av.get(k);
+    if (b) {
+      Bf8 bv;
+      bv.load(b + i * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] += bv.get(k);
+    }
+    if (m) {
+      Bf8 mv;
+      mv.load(m + i * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r[k] = mv.get(k) > 0.f ? r[k] : 0.f;
+    }
+    o.set(r);
+    o.store(out + i * 8);
+  }
+}
+__global__ void slice_add_vec_kernel(const bf16* src, int sstride, int off, const bf16* add, bf16* dst, long long rows,
+                                     int C) {
+  const int cv = C / 8;
+  const long long total = rows * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cv;
+    const int c0 = (int)(i - r * cv) * 8;
+    Bf8 sv, o;
+    sv.load(src + r * sstride + off + c0);
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = sv.get(k);
+    if (add) {
+      Bf8 ad;
+      ad.load(add + i * 8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += ad.get(k);
+    }
+    o.set(v);
+    o.store(dst + i * 8);
+  }
+}
+
 // out = a (+ b) masked by (m > 0) -- used to merge gradient branches and apply ReLU masks
 template <typename T>
 __global__ void add_mask_kernel(const T* a, const T* b, const T* m, T* out, long long n) {
@@ -885,6 +978,12 @@ int k_film_bwd(const void* d_r, const void* y, const float* fg, const float* fb,
   int ppc = (HW + 63) / 64;  // <= 64 CTAs per sample
   if (ppc < 64) ppc = HW < 64 ? HW : 64;
   dim3 grid((HW + ppc - 1) / ppc, N);
+  if (dt == DT_BF16 && C % 8 == 0 && 256 % (C / 8) == 0) {
+    film_bwd_vec_kernel<<<grid, 256, 2 * C * sizeof(float), st>>>((const bf16*)d_r, (const bf16*)y, fg, fb, fstride,
+                                                                 (bf16*)d_y, dgam, dbet, HW, C, ppc);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (film_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)d_r, (const float*)y, fg, fb, fstride,
                                                            (float*)d_y, dgam, dbet, HW, C, ppc)),
@@ -896,6 +995,11 @@ int k_film_bwd(const void* d_r, const void* y, const float* fg, const float* fb,
 
 int k_add_mask(const void* a, const void* b, const void* m, void* out, long long n, int dt, cudaStream_t st) {
   if (n == 0) return 0;
+  if (dt == DT_BF16 && n % 8 == 0 && ((uintptr_t)a | (uintptr_t)b | (uintptr_t)m | (uintptr_t)out) % 16 == 0) {
+    add_mask_vec_kernel<<<grid_for(n / 8), 256, 0, st>>>((const bf16*)a, (const bf16*)b, (const bf16*)m, (bf16*)out, n / 8);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (add_mask_kernel<float><<<grid_for(n), 256, 0, st>>>((const float*)a, (const float*)b, (const float*)m,
                                                                   (float*)out, n)),
@@ -927,6 +1031,13 @@ int k_s2d_mask(const void* d_up, int dstride, const void* up, void* out, int N, 
 int k_slice_add(const void* src, int sstride, int off, const void* add, void* dst, long long rows, int C, int dt,
                 cudaStream_t st) {
   if (rows == 0) return 0;
+  if (dt == DT_BF16 && C % 8 == 0 && sstride % 8 == 0 && off % 8 == 0 &&
+      ((uintptr_t)src | (uintptr_t)add | (uintptr_t)dst) % 16 == 0) {
+    slice_add_vec_kernel<<<grid_for(rows * (C / 8)), 256, 0, st>>>((const bf16*)src, sstride, off, (const bf16*)add,
+                                                                   (bf16*)dst, rows, C);
+    DG_LAUNCH_CHECK();
+    return 0;
+  }
   DISPATCH_DT(dt,
               (slice_add_kernel<float><<<grid_for(rows * C), 256, 0, st>>>((const float*)src, sstride, off,
                                                                           (const float*)add, (float*)dst, rows, C)),
