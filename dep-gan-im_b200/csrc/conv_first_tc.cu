@@ -287,6 +287,189 @@ __global__ void __launch_bounds__(256) conv_first_tc_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient of the same first layers: dW[tap][ci][co] += alpha * sum_p x[p + off(tap)][ci] * dy[p][co].
+// GEMM with K = pixels: A = the im2col tile above read "MN-major" (a pixel's K taps are its contiguous M block, the
+// pixel pitch is the swizzle span), B = the dy tile [pixel][COUT] read MN-major, one MMA (K = 16) per tile row of 16
+// pixels, accumulator rows = taps (hi half and lo half of the split image land in rows k and K + k and are added by
+// the flush's atomics; rows beyond 2K hold garbage of the M = 128 instruction and are ignored).  The accumulator
+// stays in TMEM for the CTA's whole pixel range.
+// ---------------------------------------------------------------------------------------------------------
+template <int KS, int CIN, int COUT>
+__global__ void __launch_bounds__(256) wgrad_first_tc_kernel(const float* __restrict__ x, const bf16* __restrict__ dy,
+                                                             float* __restrict__ dw, int N, int H, int W, float alpha) {
+  typedef FirstGeom<KS, CIN> GEO;
+  constexpr int K = GEO::K, KP = GEO::KP, ROWB = GEO::ROWB, UNITS = GEO::UNITS, HT = GEO::HT, PAD = KS / 2;
+  constexpr int BROW = COUT * 2, BUNITS = BROW / 16;     // dy: bytes / 16-byte units per pixel (one swizzle span)
+  constexpr uint32_t BLAY = COUT == 32 ? 4u : 6u;        // SW64 / SW32
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - raw);
+  // [A: 256 rows x ROWB + one slack row group][B: 256 pixels x BROW][halo][barrier, tmem slot]
+  constexpr uint32_t A_BYTES = 256 * ROWB + 1024, B_BYTES = 256 * BROW;
+  uint8_t* sA = gen;
+  uint8_t* sB = gen + A_BYTES;
+  uint32_t* s_halo = reinterpret_cast<uint32_t*>(gen + A_BYTES + B_BYTES);
+  const uint32_t bar = base + A_BYTES + B_BYTES + (uint32_t)(HT * HT * CIN * 4 + 15) / 16 * 16;
+  const uint32_t tmem_slot = bar + 8;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(32) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < 1024 / 16; i += 256)  // slack rows read by the M = 128 instruction past the last pixel
+    reinterpret_cast<uint4*>(sA + 256 * ROWB)[i] = make_uint4(0u, 0u, 0u, 0u);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int py = tid >> 4, px = tid & 15;
+  const uint32_t a_off = (uint32_t)tid * ROWB, a_xor = (a_off >> 7) & (UNITS - 1);
+  const uint32_t b_off = (uint32_t)tid * BROW, b_xor = (b_off >> 7) & (BUNITS - 1);
+  // D = f32, A = B = bf16, both MN-major, M = 128, N = COUT
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(COUT >> 3) << 17) |
+                         ((uint32_t)(128 >> 4) << 24);
+  // A: the M block of KP taps is one pixel row (span); "next M block" = next pixel (LBO = span); K groups of 8 pixels
+  const uint32_t hiA = ((uint32_t)(8 * ROWB) >> 4) | (1u << 14) | (GEO::LAYOUT << 29);
+  const uint32_t loA = (((base)&0x3FFFFu) >> 4) | (((uint32_t)ROWB >> 4) << 16);
+  const uint32_t hiB = ((uint32_t)(8 * BROW) >> 4) | (1u << 14) | (BLAY << 29);
+  const uint32_t loB = (((base + A_BYTES) & 0x3FFFFu) >> 4) | (((uint32_t)(16 * BROW) >> 4) << 16);
+
+  const int tiles_w = W / 16, tiles_h = H / 16;
+  const int n_tiles = tiles_w * tiles_h * N;
+  constexpr int NPRE = (HT * HT * CIN + 255) / 256;
+  float pre[NPRE];
+  uint4 dpre[BUNITS];
+  auto fetch = [&](int t_) {
+    const int tw_ = t_ % tiles_w, th_ = (t_ / tiles_w) % tiles_h, n_ = t_ / (tiles_w * tiles_h);
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j) {
+      const int i = tid + 256 * j;
+      const int r = i / (HT * CIN), cc = i - r * (HT * CIN);
+      const int gy = th_ * 16 - PAD + r, gx = tw_ * 16 - PAD + cc / CIN, ci = cc % CIN;
+      pre[j] = (i < HT * HT * CIN && gy >= 0 && gy < H && gx >= 0 && gx < W)
+                   ? __ldg(x + (((size_t)n_ * H + gy) * W + gx) * CIN + ci) : 0.f;
+    }
+    const uint4* dp = reinterpret_cast<const uint4*>(dy + (((size_t)n_ * H + th_ * 16 + py) * W + tw_ * 16 + px) * COUT);
+#pragma unroll
+    for (int u = 0; u < BUNITS; ++u) dpre[u] = __ldg(dp + u);
+  };
+  uint32_t phase = 0, first = 1;
+  if ((int)blockIdx.x < n_tiles) fetch(blockIdx.x);
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    if (!first) {  // the previous tile's MMAs have consumed the operand tiles
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
+#pragma unroll
+    for (int j = 0; j < NPRE; ++j)
+      if (tid + 256 * j < HT * HT * CIN) s_halo[tid + 256 * j] = split_bf16(pre[j]);
+#pragma unroll
+    for (int u = 0; u < BUNITS; ++u) *reinterpret_cast<uint4*>(sB + b_off + ((((uint32_t)u) ^ b_xor) << 4)) = dpre[u];
+    __syncthreads();
+    {
+      uint32_t wv[K + 1];
+#pragma unroll
+      for (int dyy = 0; dyy < KS; ++dyy)
+#pragma unroll
+        for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci)
+            wv[(dyy * KS + dx) * CIN + ci] = s_halo[((py + dyy) * HT + px + dx) * CIN + ci];
+      wv[K] = 0u;
+      uint32_t row[KP / 2];
+#pragma unroll
+      for (int j = 0; j < KP / 2; ++j) {
+        uint32_t pr = 0u;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int e = 2 * j + h;
+          uint32_t half = 0u;
+          if (e < K) half = wv[e] & 0xFFFFu;
+          else if (e < 2 * K) half = wv[e - K] >> 16;
+          pr |= half << (16 * h);
+        }
+        row[j] = pr;
+      }
+#pragma unroll
+      for (int u = 0; u < UNITS; ++u)
+        *reinterpret_cast<uint4*>(sA + a_off + ((((uint32_t)u) ^ a_xor) << 4)) =
+            make_uint4(row[4 * u], row[4 * u + 1], row[4 * u + 2], row[4 * u + 3]);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (t + (int)gridDim.x < n_tiles) fetch(t + gridDim.x);
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int r = 0; r < 16; ++r)  // K = 16 pixels = one tile row per MMA
+        tc_mma(tmem_base, ((uint64_t)hiA << 32) | (loA + (uint32_t)((r * 16 * ROWB) >> 4)),
+               ((uint64_t)hiB << 32) | (loB + (uint32_t)((r * 16 * BROW) >> 4)), idesc, (first && r == 0) ? 0u : 1u);
+      tc_commit(bar);
+    }
+    first = 0;
+  }
+  // ---- flush: rows k (hi) and K + k (lo) of the accumulator both add into dW[k][co] ----
+  if (!first) {
+    mbar_wait(bar, phase);
+    tc_fence_after();
+    if (warp < 4) {
+      const int m = warp * 32 + (tid & 31);
+#pragma unroll
+      for (int g = 0; g < COUT / 16; ++g) {
+        float v[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 16), v);
+        if (m < 2 * K) {
+          float* dst = dw + (size_t)(m < K ? m : m - K) * COUT + g * 16;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + i, alpha * v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(32) : "memory");
+  }
+}
+
+template <int KS, int CIN, int COUT>
+int launch_wgrad_first_tc(const WgradArgs& a, cudaStream_t st) {
+  typedef FirstGeom<KS, CIN> GEO;
+  constexpr uint32_t smem = 1024 + 256 * GEO::ROWB + 1024 + 256 * COUT * 2 + GEO::HT * GEO::HT * CIN * 4 + 16 + 32;
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_tc_kernel<KS, CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_tc_kernel<KS, CIN, COUT>,
+                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    cudaFuncAttributes fa;
+    DG_CHECK_CUDA(cudaFuncGetAttributes(&fa, wgrad_first_tc_kernel<KS, CIN, COUT>));
+    int occ = (int)((216u * 1024u) / (smem + 1024u));
+    const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * 256);
+    if (occ > by_regs) occ = by_regs;
+    if (occ > 8) occ = 8;
+    per_sm = occ < 1 ? 1 : occ;
+  }
+  int dev = 0, sms = 148;
+  DG_CHECK_CUDA(cudaGetDevice(&dev));
+  DG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int n_tiles = (a.W / 16) * (a.H / 16) * a.N;
+  const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
+  wgrad_first_tc_kernel<KS, CIN, COUT><<<grid, 256, smem, st>>>((const float*)a.x0, (const bf16*)a.dy, a.dw, a.N, a.H,
+                                                                a.W, a.alpha);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
 template <int KS, int CIN, int COUT>
 int launch_first_tc(const ConvArgs& a, cudaStream_t st) {
   typedef FirstGeom<KS, CIN> GEO;
@@ -336,5 +519,15 @@ int conv_first_tc_try(const ConvArgs& a, cudaStream_t st) {
   else if (a.ks == 3 && a.C0 <= 2 && a.Cout == 32 && getenv("DEPGAN_FIRST_TC_GEN")) {
     r = a.C0 == 1 ? launch_first_tc<3, 1, 32>(a, st) : launch_first_tc<3, 2, 32>(a, st);
   } else return 0;
+  return r < 0 ? r : 1;
+}
+
+// Weight gradient of conv2d_dis_0a in a bf16 network (fp32 image, bf16 gradient): 1 taken, 0 not a case, < 0 error.
+int wgrad_first_tc_try(const WgradArgs& a, cudaStream_t st) {
+  if (a.x_dt != DT_F32 || a.dy_dt != DT_BF16 || a.C1 != 0 || !a.dw) return 0;
+  if (a.H % 16 || a.W % 16 || a.H < 16 || a.W < 16) return 0;
+  int r = 1;
+  if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) r = launch_wgrad_first_tc<5, 1, 16>(a, st);
+  else return 0;
   return r < 0 ? r : 1;
 }

@@ -669,6 +669,11 @@ int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
 int conv_wgrad_simt(const WgradArgs& a, cudaStream_t st) {
   if (a.N <= 0) return 0;
   {
+    static const bool no_first_tc = getenv("DEPGAN_NO_FIRST_TC") != nullptr;  // A/B switch for measurements
+    if (!no_first_tc) {
+      const int r0 = wgrad_first_tc_try(a, st);
+      if (r0 != 0) return r0 < 0 ? r0 : 0;
+    }
     const int r = a.dy_dt == DT_BF16 ? try_wgrad_first<bf16>(a, st) : try_wgrad_first<float>(a, st);
     if (r != 0) return r < 0 ? r : 0;
   }

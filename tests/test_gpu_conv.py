@@ -315,3 +315,21 @@ def test_first_layer_tensor_core(ks, c0, cout, H, W, N, use_mask):
     # and against exact weights: weight rounding only
     want32, _ = ref_conv(x, w, None, sc, sh, relu=not use_mask, mask=None if mask is None else _bf(mask))
     assert float((got - want32).abs().max()) <= 2e-2 * max(1.0, float(want32.abs().max()))
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 32, 48), (20, 64, 64), (5, 256, 256)])
+def test_first_layer_wgrad_tensor_core(N, H, W):
+    """conv2d_dis_0a weight gradient of a bf16 critic: fp32 image (split into two bf16 halves), bf16 gradient."""
+    import ctypes as C
+    from depgan_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x, dy = _rand((N, H, W, 1), 1), _bf(_rand((N, H, W, 16), 2))
+    xd, dyd = x.to(dev).contiguous(), dy.to(dev).to(torch.bfloat16).contiguous()
+    dw = torch.zeros(25 * 16, device=dev)
+    _lib.check(L.depgan_op_wgrad(xd.data_ptr(), None, 1, 0, dyd.data_ptr(), dw.data_ptr(), N, H, W, 16, 5, 2, st), "wgrad")
+    torch.cuda.synchronize()
+    want = ref_wgrad(x, dy, 5)
+    got = dw.cpu().view(5, 5, 1, 16)
+    assert float((got - want).abs().max()) <= 2e-4 * float(want.abs().max()) + 1e-4
