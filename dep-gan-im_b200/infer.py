@@ -11,6 +11,8 @@ reproducible), float64 accumulation of mask * prediction, mean, clip, threshold 
 """
 from __future__ import annotations
 
+import zlib
+
 import numpy as np
 
 from . import postproc
@@ -110,10 +112,11 @@ def cohort_sweep(net, subjects, thr, rank=0, world=1, n_repeat=10, kind="dem"):
     res = {}
     for item in shard_items(subjects, rank, world):
         sid, vol, mask = item[0], item[1], item[2]
+        seed = zlib.crc32(str(sid).encode()) & 0x7FFFFFFF  # per-subject noise stream, the same in every process
         if kind == "dem":
-            res[sid] = predict_subject_dem(net, vol, mask, thr, n_repeat=n_repeat, seed=hash(sid) & 0x7FFFFFFF)
+            res[sid] = predict_subject_dem(net, vol, mask, thr, n_repeat=n_repeat, seed=seed)
         else:
-            res[sid] = predict_subject_uresnet(net, vol, mask, n_repeat=n_repeat, seed=hash(sid) & 0x7FFFFFFF)
+            res[sid] = predict_subject_uresnet(net, vol, mask, n_repeat=n_repeat, seed=seed)
         if len(item) > 3 and item[3] is not None:
             t = item[3]
             res[sid]["eval_row"] = evaluate_subject(res[sid], t["labels"], t["vol_1tp_ml"], t["vol_2tp_ml"],
