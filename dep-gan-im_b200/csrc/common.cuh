@@ -110,9 +110,10 @@ struct WgradArgs {
   int N, H, W, Cout, ks;
   int x_dt, dy_dt;
   float alpha;  // scale applied to the accumulated sum
+  float* csum;  // optional: csum[co] += sum_p dy[p][co] (the bias / BN-shift gradient), fused when the kernel can
 };
 int conv_wgrad_simt(const WgradArgs& a, cudaStream_t st);
-int conv_wgrad_tc(const WgradArgs& a, cudaStream_t st);  // tcgen05 path (bf16 x and dy)
+int conv_wgrad_tc(const WgradArgs& a, cudaStream_t st);  // tcgen05 path (bf16 x and dy); handles a.csum itself
 bool wgrad_tc_supported(const WgradArgs& a);
 int wgrad_tc_init();
 int wgrad_first_tc_try(const WgradArgs& a, cudaStream_t st);  // tcgen05 first-layer wgrad (conv_first_tc.cu)

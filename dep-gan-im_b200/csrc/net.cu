@@ -667,6 +667,16 @@ int depgan_op_wgrad(const void* x0, const void* x1, int C0, int C1, const void* 
   return conv_wgrad_simt(a, (cudaStream_t)stream);
 }
 
+int depgan_op_wgrad_csum(const void* x0, const void* x1, int C0, int C1, const void* dy, float* dw, float* csum, int N,
+                         int H, int W, int Cout, int ks, void* stream) {
+  WgradArgs a{};
+  a.x0 = x0; a.x1 = x1; a.C0 = C0; a.C1 = C1; a.dy = dy; a.dw = dw; a.N = N; a.H = H; a.W = W; a.Cout = Cout;
+  a.ks = ks; a.alpha = 1.f; a.csum = csum;
+  a.x_dt = a.dy_dt = DT_BF16;
+  DG_REQUIRE(wgrad_tc_supported(a), "op_wgrad_csum: shape not supported by the tcgen05 path");
+  return conv_wgrad_tc(a, (cudaStream_t)stream);
+}
+
 // fp32 [taps][Cin][Cout] (Keras HWIO) -> bf16 [taps][Cout][Cin] (the tcgen05 B operand); tests / benchmarks.
 int depgan_op_pack_weights(const float* w_f32_dev, void* w_bf16_dev, int taps, int cin, int cout, void* stream) {
   return k_pack_conv_weights(w_f32_dev, nullptr, (bf16*)w_bf16_dev, nullptr, nullptr, taps, cin, cout,

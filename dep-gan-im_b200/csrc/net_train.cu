@@ -121,16 +121,24 @@ int dgrad_conv(depgan_net* h, const ConvL& L, const void* dy, void* dx, int dx_d
   return conv_fwd_simt(a, st);
 }
 
+// csum (optional): per-channel sums of dy over the same n rows, accumulated into csum[cout] -- fused into the tcgen05
+// kernel when that path takes the call, otherwise a separate bandwidth pass.
 int wgrad_conv(depgan_net* h, const ConvL& L, const void* x0, int C0, const void* x1, int C1, int x_dt, const void* dy,
-               float* dw, int n, cudaStream_t st) {
+               float* dw, int n, cudaStream_t st, float* csum = nullptr) {
   WgradArgs a{};
   a.x0 = x0; a.x1 = x1; a.C0 = C0; a.C1 = C1; a.dy = dy; a.dw = dw;
   a.N = n; a.H = h->lvl_h(L.lvl); a.W = h->lvl_w(L.lvl); a.Cout = L.cout; a.ks = L.ks;
   a.x_dt = x_dt; a.dy_dt = h->act_dt; a.alpha = 1.f;
   const bool tc = wgrad_tc_supported(a);
-  ProfScope prof(a, tc, st);
-  if (tc) return conv_wgrad_tc(a, st);
-  return conv_wgrad_simt(a, st);
+  if (tc) a.csum = csum;
+  {
+    ProfScope prof(a, tc, st);
+    if (tc) DG_TRY(conv_wgrad_tc(a, st));
+    else DG_TRY(conv_wgrad_simt(a, st));
+  }
+  if (csum && !tc)
+    DG_TRY(k_channel_sum(dy, (long long)n * a.H * a.W, L.cout, csum, 1.f, h->act_dt, st));
+  return 0;
 }
 
 size_t rows_off(depgan_net* h, const ConvL& L, int row) {  // byte offset of sample `row` in an activation of L
@@ -245,11 +253,10 @@ int depgan_critic_grads(depgan_net* d, depgan_net* g, int which, const float* re
                               : ((i - 1 == 1 || i - 1 == 3 || i - 1 == 5 || i - 1 == 7) ? (const void*)T.vp[(i - 1) / 2]
                                                                                          : (const void*)T.v[i - 1]);
     const int x_dt = i == 0 ? DT_F32 : d->act_dt;
-    DG_TRY(wgrad_conv(d, L, x_reg, L.cin, nullptr, 0, x_dt, T.b[i], d->G(L.k_off), 2 * n, st));
+    // the bias gradient (channel sums of the regular rows' dy) rides along with the first weight-gradient pass
+    DG_TRY(wgrad_conv(d, L, x_reg, L.cin, nullptr, 0, x_dt, T.b[i], d->G(L.k_off), 2 * n, st, d->G(L.b_off)));
     DG_TRY(wgrad_conv(d, L, x_gp, L.cin, nullptr, 0, x_dt, off_ptr((const void*)T.b[i], rows_off(d, L, 2 * n)),
                       d->G(L.k_off), n, st));
-    DG_TRY(k_channel_sum(T.b[i], (long long)2 * n * d->lvl_h(L.lvl) * d->lvl_w(L.lvl), L.cout, d->G(L.b_off), 1.f,
-                         d->act_dt, st));
   }
   const int hw4 = d->lvl_h(4) * d->lvl_w(4);
   DG_TRY(k_critic_head_bwd(d->c_act[10], T.v[10], T.go, d->P(d->d9_k), d->P(d->d9_b), d->P(d->dd_k), nullptr,

@@ -73,6 +73,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
   asm volatile(
@@ -121,7 +124,7 @@ template <int KS, int C>
 __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                                  const __grid_constant__ CUtensorMap tmX1,
                                                                  const __grid_constant__ CUtensorMap tmB, float* dw,
-                                                                 float alpha, int N, const WgGeom g) {
+                                                                 float alpha, int N, const WgGeom g, float* csum) {
   constexpr int PAD = KS / 2, HT = 16 + KS - 1;
   constexpr int SPAN = C * 2;       // bytes per pixel row of the x tile
   constexpr int TPM = 128 / C;      // dx taps stacked in one M=128 MMA
@@ -134,8 +137,11 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
+  // channel sums of dy (bias gradient) ride along: the four flush warps, idle during the main loop, add up the
+  // central rows of every b tile (CTAs of the first input-channel chunk only; every chunk sees the same dy)
+  const bool do_cs = csum != nullptr && blockIdx.y == 0;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < g.S; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, 1); }
+    for (int i = 0; i < g.S; ++i) { mbar_init(full + 8 * i, 1); mbar_init(empty + 8 * i, do_cs ? 5 : 1); }
     mbar_init(accFull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -227,7 +233,50 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
     }
     if (elect_one()) tc_commit(accFull);
     __syncwarp();
-  } else if (it1 > it0) {
+  } else {
+    if (do_cs) {
+      const int t = threadIdx.x - 64;                 // pixel of the R x 16 central block of the b tile
+      const uint32_t bspan = g.nspan * 2, units = bspan / 16;
+      const uint32_t po = (uint32_t)((PAD + (t >> 4)) * 16 + (t & 15)) * bspan;
+      const uint32_t pxor = (po >> 7) & (units - 1);
+      float acc[8][8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long it = it0; it < it1; ++it) {
+        mbar_wait(full + 8 * s, ph);
+        const uint8_t* bt = smem_raw + (base + s * g.stage_bytes + g.x_bytes - raw);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if ((uint32_t)u < units) {
+            const uint4 q = *reinterpret_cast<const uint4*>(bt + po + ((((uint32_t)u) ^ pxor) << 4));
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[u][2 * k] += __uint_as_float(w4[k] << 16);
+              acc[u][2 * k + 1] += __uint_as_float(w4[k] & 0xFFFF0000u);
+            }
+          }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8 * s);
+        if (++s == g.S) { s = 0; ph ^= 1u; }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if ((uint32_t)u < units) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float v = acc[u][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(csum + co0 + u * 8 + k, v);
+          }
+        }
+    }
+    if (it1 > it0) {
     // ===== final flush: TMEM -> red.add into dW[dy][dx][ci][co] =====
     mbar_wait(accFull, 0);
     tc_fence_after();
@@ -251,6 +300,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
           }
         }
       }
+    }
     }
   }
   tc_fence_before();
@@ -367,7 +417,7 @@ int conv_wgrad_tc(const WgradArgs& a, cudaStream_t st) {
   if (gx > items) gx = items;
   dim3 grid((unsigned)gx, chunks, coblocks);
 #define DG_WG_CASE(KS_, C_) \
-  case KS_ * 100 + C_: wgrad_tc_kernel<KS_, C_><<<grid, WG_THREADS, smem, st>>>(tmX0, tmX1, tmB, a.dw, a.alpha, a.N, g); break;
+  case KS_ * 100 + C_: wgrad_tc_kernel<KS_, C_><<<grid, WG_THREADS, smem, st>>>(tmX0, tmX1, tmB, a.dw, a.alpha, a.N, g, a.csum); break;
   switch (a.ks * 100 + g.C) {
     DG_WG_CASE(1, 16) DG_WG_CASE(1, 32) DG_WG_CASE(1, 64)
     DG_WG_CASE(3, 16) DG_WG_CASE(3, 32) DG_WG_CASE(3, 64)

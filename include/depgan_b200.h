@@ -172,6 +172,10 @@ int depgan_op_conv2d(const depgan_conv_desc* d, void* stream);
  * x float32 and dy bf16 (the first layer of a bf16 network).  The caller zeroes dw. */
 int depgan_op_wgrad(const void* x0, const void* x1, int C0, int C1, const void* dy, float* dw, int N, int H, int W,
                     int Cout, int ks, int use_tc, void* stream);
+/* tcgen05 weight gradient (x, dy bf16) that also accumulates the bias gradient csum[co] += sum_p dy[p][co] from the same
+ * pass over dy (the caller zeroes dw and csum). */
+int depgan_op_wgrad_csum(const void* x0, const void* x1, int C0, int C1, const void* dy, float* dw, float* csum, int N,
+                         int H, int W, int Cout, int ks, void* stream);
 int depgan_op_pack_weights(const float* w_f32_dev, void* w_bf16_dev, int taps, int cin, int cout, void* stream);
 int depgan_op_f32_to_bf16(const float* src_dev, void* dst_dev, long long n, void* stream);
 int depgan_op_bf16_to_f32(const void* src_dev, float* dst_dev, long long n, void* stream);

@@ -333,3 +333,26 @@ def test_first_layer_wgrad_tensor_core(N, H, W):
     want = ref_wgrad(x, dy, 5)
     got = dw.cpu().view(5, 5, 1, 16)
     assert float((got - want).abs().max()) <= 2e-4 * float(want.abs().max()) + 1e-4
+
+
+@pytest.mark.parametrize("ks,cin,cout,H,W,N", [(5, 16, 16, 64, 64, 9), (3, 32, 32, 32, 48, 7), (3, 64, 64, 32, 32, 12),
+                                               (3, 96, 96, 16, 16, 20), (5, 32, 16, 32, 32, 5)])
+def test_tcgen05_wgrad_with_fused_channel_sums(ks, cin, cout, H, W, N):
+    """The bias gradient sum_p dy[p][co] accumulated by the weight-gradient kernel's otherwise idle warps."""
+    import ctypes as C
+    from depgan_b200 import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda:0")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x, dy = _bf(_rand((N, H, W, cin), 1)), _bf(_rand((N, H, W, cout), 2))
+    xd, dyd = x.to(dev).to(torch.bfloat16).contiguous(), dy.to(dev).to(torch.bfloat16).contiguous()
+    dw = torch.zeros(ks * ks * cin * cout, device=dev)
+    cs = torch.zeros(cout, device=dev)
+    _lib.check(L.depgan_op_wgrad_csum(xd.data_ptr(), None, cin, 0, dyd.data_ptr(), dw.data_ptr(), cs.data_ptr(), N, H, W,
+                                      cout, ks, st), "wgrad_csum")
+    torch.cuda.synchronize()
+    want = ref_wgrad(x, dy, ks)
+    got = dw.cpu().view(ks, ks, cin, cout)
+    assert float((got - want).abs().max()) <= 1e-3 * float(want.abs().max())
+    want_cs = dy.double().sum(dim=(0, 1, 2)).float()
+    assert float((cs.cpu() - want_cs).abs().max()) <= 1e-4 * float(dy.abs().sum(dim=(0, 1, 2)).max())
