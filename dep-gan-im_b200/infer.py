@@ -19,7 +19,7 @@ from . import postproc
 from .api import _torch
 
 __all__ = ["shard_range", "shard_items", "predict_subject_dem", "predict_subject_uresnet", "evaluate_subject",
-           "cohort_sweep"]
+           "save_subject_outputs", "cohort_sweep"]
 
 
 def shard_range(n_items, rank, world):
@@ -102,6 +102,22 @@ def evaluate_subject(result, real_labels, vol_1tp_ml, vol_2tp_ml, voxel_mm3, dev
     counts of the predicted label map against `real_labels` (the ground-truth code volume, values 0..3)."""
     vol_out_ml = result["wmh_voxels"] * voxel_mm3 / 1000
     return postproc.evaluate_labels(result["labels"], real_labels, vol_1tp_ml, vol_2tp_ml, vol_out_ml, device=device)
+
+
+def save_subject_outputs(result, affine, out_dir, name):
+    """Writes the three volumes the DEP-GAN testing script saves per subject (EG:813-832): the predicted follow-up map
+    ``<name>_2tp_prob_fake.nii.gz``, the disease evolution map ``<name>_network_output.nii.gz`` and the label map
+    ``<name>_2tp_code_fake.nii.gz`` -- each through ``data_prep_save``, as float32, with the baseline scan's affine.
+    Returns the three paths."""
+    import os
+    from . import nifti, preproc
+    paths = []
+    for key, suffix in (("fake2", "_2tp_prob_fake"), ("dem", "_network_output"), ("labels", "_2tp_code_fake")):
+        vol = preproc.data_prep_save(np.asarray(result[key])).astype("float32")
+        path = os.path.join(str(out_dir), str(name) + suffix + ".nii.gz")
+        nifti.save(vol, affine, path)
+        paths.append(path)
+    return paths
 
 
 def cohort_sweep(net, subjects, thr, rank=0, world=1, n_repeat=10, kind="dem"):
