@@ -25,7 +25,50 @@ import numpy as np
 from . import _lib
 from .api import _stream, _torch
 
-__all__ = ["DepGanTrainer"]
+__all__ = ["DepGanTrainer", "ScalarLog", "epoch_schedule"]
+
+
+def epoch_schedule(batches, gen_iterations, Diters=5):
+    """The order in which one epoch of the reference loop (TG:790-894) touches its mini-batches, as a generator of
+    ``("y2", i)``, ``("dem", ii)`` and ``("gen", b, gen_iterations)`` events: per generator iteration up to ``_Diters``
+    Y2-critic updates on batches i, i+1, ... (``_Diters`` = 100 while ``gen_iterations < 25`` or every 500th iteration,
+    else ``Diters``; TG:792-797), up to ``_Diters`` DEM-critic updates on its own cursor ii (TG:814-829), then the noise
+    search and ONE generator update on the batch the critics saw last (index ``b``; TG:867-878)."""
+    i = ii = 0
+    last = None
+    while i < batches:
+        d = 100 if (gen_iterations < 25 or gen_iterations % 500 == 0) else Diters
+        j = jj = 0
+        while j < d and i < batches:
+            j += 1
+            last = i
+            yield ("y2", i)
+            i += 1
+        while jj < d and ii < batches:
+            jj += 1
+            last = ii
+            yield ("dem", ii)
+            ii += 1
+        yield ("gen", last, gen_iterations)
+        gen_iterations += 1
+
+
+class ScalarLog:
+    """Minimal stand-in for the reference's TensorBoard ``Logger`` (TG:167-248): ``log_scalar(tag, value, step)`` keeps
+    the series in memory (``.series[tag] = [(step, value), ...]``) and, if a path is given, appends CSV lines."""
+
+    def __init__(self, csv_path=None):
+        self.series = {}
+        self.csv_path = csv_path
+
+    def log_scalar(self, tag, value, step):
+        self.series.setdefault(tag, []).append((int(step), float(value)))
+        if self.csv_path:
+            with open(self.csv_path, "a") as f:
+                f.write("%s,%d,%.9g\n" % (tag, int(step), float(value)))
+
+    def log_images(self, tag, images, step, *args):  # image summaries are not kept
+        self.series.setdefault(tag, []).append((int(step), float(np.asarray(images).shape[0])))
 
 
 class DepGanTrainer:
@@ -173,3 +216,73 @@ class DepGanTrainer:
         out = self.netG_train([x1d, r2d, self._dev(noises[k])])
         self.gen_iterations += 1
         return k, losses, out
+
+
+    # ---- the reference's training loop (TG:780-894) ------------------------------------------------------
+    def fit(self, x1_train, y2_train, niter=1, batchSize=16, Diters=5, noiseSize=32, k_noise=10, val=None,
+            fixed_noise=None, logger=None, save_path=None, save_every=1, seed=None, shuffle=True, verbose=False):
+        """``niter`` epochs of the DEP-GAN loop on host arrays ``x1_train (M,H,W,nicg)`` / ``y2_train (M,H,W,1)``:
+        per epoch a shuffle (TG:785-788), then :func:`epoch_schedule`; noise ~ N(0,1), ep ~ U(0,1) per critic update
+        (TG:807-808, 822-823), ``k_noise`` candidate noises for the generator and the argmin rule (TG:869-878); the
+        scalars of TG:810-840 and 879-885 go to ``logger.log_scalar``; every 10th generator iteration the three
+        validation means of TG:845-855 on ``val = (x1_val, y2_val)`` with ``fixed_noise``; ``netG.save(save_path)`` every
+        ``save_every`` generator iterations (the reference saves after each, TG:892).  The reference draws from the
+        global NumPy RNG; ``seed`` makes the run reproducible.  Returns the logger."""
+        rng = np.random.default_rng(seed)
+        logger = logger if logger is not None else ScalarLog()
+        x1_train = np.ascontiguousarray(x1_train, np.float32)
+        y2_train = np.ascontiguousarray(y2_train, np.float32)
+        crit_it = crit_dem_it = 0
+        errD = errD_real = errD_fake = errD_dem = errD_real_dem = errD_fake_dem = 0.0
+        for epoch in range(niter):
+            idx = np.arange(x1_train.shape[0])
+            if shuffle:
+                rng.shuffle(idx)
+            x1_e, y2_e = x1_train[idx], y2_train[idx]
+            batches = x1_e.shape[0] // batchSize
+            for ev in epoch_schedule(batches, self.gen_iterations, Diters):
+                if ev[0] in ("y2", "dem"):
+                    b = ev[1]
+                    r1, r2 = x1_e[b * batchSize:(b + 1) * batchSize], y2_e[b * batchSize:(b + 1) * batchSize]
+                    noise = rng.standard_normal((batchSize, noiseSize, 1))
+                    ep = rng.uniform(size=(batchSize, 1, 1, 1))
+                    if ev[0] == "y2":
+                        errD_real, errD_fake = self.netD_y2_train([r2, r1, noise, ep])
+                        errD = errD_real - errD_fake
+                        logger.log_scalar("errCrit_aaLosses", errD, crit_it)
+                        logger.log_scalar("errCrit_aReal_losses", errD_real, crit_it)
+                        logger.log_scalar("errCrit_aFake_losses", errD_fake, crit_it)
+                        crit_it += 1
+                    else:
+                        errD_real_dem, errD_fake_dem = self.netD_dem_train([r2, r1, noise, ep])
+                        errD_dem = errD_real_dem - errD_fake_dem
+                        logger.log_scalar("errCrit_DEM_aaLosses", errD_dem, crit_dem_it)
+                        logger.log_scalar("errCrit_DEM_aReal_losses", errD_real_dem, crit_dem_it)
+                        logger.log_scalar("errCrit_DEM_aFake_losses", errD_fake_dem, crit_dem_it)
+                        crit_dem_it += 1
+                    continue
+                b, g_it = ev[1], self.gen_iterations
+                for tag, v in (("errDC_aaLosses", errD), ("errDC_aReal_losses", errD_real), ("errDC_aFake_losses", errD_fake),
+                               ("errDC_DEM_aaLosses", errD_dem), ("errDC_DEM_aReal_losses", errD_real_dem),
+                               ("errDC_DEM_aFake_losses", errD_fake_dem)):
+                    logger.log_scalar(tag, v, g_it)
+                if val is not None and g_it % 10 == 0:                         # TG:842-855
+                    x1_v, y2_v = val
+                    fz = fixed_noise if fixed_noise is not None else np.zeros((x1_v.shape[0], noiseSize, 1), np.float32)
+                    v_fake = float(np.mean(self.Dy2.predict(np.ascontiguousarray(x1_v[..., :1], np.float32))))
+                    v_real = float(np.mean(self.Dy2.predict(np.ascontiguousarray(y2_v, np.float32))))
+                    v_gen = float(np.mean(self.Dy2.predict(self.G.predict([x1_v, fz]))))
+                    logger.log_scalar("val_D_fake_loss", v_fake, g_it)
+                    logger.log_scalar("val_D_real_loss", v_real, g_it)
+                    logger.log_scalar("val_D_real_generated_loss", v_gen, g_it)
+                r1, r2 = x1_e[b * batchSize:(b + 1) * batchSize], y2_e[b * batchSize:(b + 1) * batchSize]
+                noises = rng.standard_normal((k_noise, batchSize, noiseSize, 1)).astype("float32")
+                _, _, out = self.gen_iteration([], [], r1, r2, noises)        # TG:867-878
+                for tag, v in zip(("errG_losses", "errG_CY2_losses", "errG_DEM_losses", "errG_MSE_losses",
+                                   "errG_VOL_losses", "errG_WMH_losses"), out):
+                    logger.log_scalar(tag, float(v), g_it)
+                if verbose:
+                    print("GEN ERR [%d/%d][%d] errG: %f" % (epoch, niter, g_it, float(out[0])))
+                if save_path and save_every and (g_it + 1) % save_every == 0:
+                    self.G.save(save_path)                                    # TG:892
+        return logger

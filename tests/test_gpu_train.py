@@ -147,3 +147,31 @@ def test_generator_iteration_schedule_selects_same_noise_as_oracle():
         num = sum(float(np.abs(w[k] - P[k].detach().numpy()).sum()) for k in w)
         den = sum(float(np.abs(P[k].detach().numpy()).sum()) for k in w)
         assert num / den < 1e-4
+
+
+def test_fit_runs_the_reference_loop(tmp_path):
+    """DepGanTrainer.fit (TG:780-894): event counts follow epoch_schedule, scalars are logged under the reference's
+    tags, validation runs on iterations 0, 10, ..., the generator is saved and reloads to the same weights."""
+    from depgan_b200 import Gen_UNet2D
+    from depgan_b200.trainer import ScalarLog, epoch_schedule
+    H, B = 32, 2
+    tr, _, _ = _setup(H, B, "bf16")
+    x1, y2, _ = synth.make_im_pair(12, H, H, nicg=1, thr=THR, seed=31)
+    xv, yv, _ = synth.make_im_pair(4, H, H, nicg=1, thr=THR, seed=32)
+    tr.G.cfg  # networks were created with max_batch = B; validation predicts in batches of B
+    path = str(tmp_path / "netG.h5")
+    lg = tr.fit(x1, y2, niter=2, batchSize=B, val=(xv, yv), fixed_noise=synth.make_noise(4, seed=33), logger=ScalarLog(),
+                save_path=path, seed=7)
+    ev = list(epoch_schedule(6, 0, 5)) + list(epoch_schedule(6, 1, 5))
+    n_y2 = sum(e[0] == "y2" for e in ev)
+    n_dem = sum(e[0] == "dem" for e in ev)
+    n_gen = sum(e[0] == "gen" for e in ev)
+    assert (n_y2, n_dem, n_gen) == (12, 12, 2) and tr.gen_iterations == 2
+    assert len(lg.series["errCrit_aaLosses"]) == n_y2 and len(lg.series["errCrit_DEM_aaLosses"]) == n_dem
+    assert [s for s, _ in lg.series["errG_losses"]] == [0, 1]
+    assert [s for s, _ in lg.series["val_D_real_loss"]] == [0]
+    assert all(np.isfinite(v) for series in lg.series.values() for _, v in series)
+    g2 = Gen_UNet2D((H, H, 1), (32, 1), 32, 1, precision="bf16", max_batch=B)
+    g2.load_weights(path)
+    a, b = tr.G.get_weights(), g2.get_weights()
+    assert all(np.array_equal(a[k], b[k]) for k in a)
