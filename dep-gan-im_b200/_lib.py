@@ -61,6 +61,7 @@ SIGNATURES = {
     "depgan_dem_postproc": (_I, [_P, _I, _P, _D, _P, _D, _P, _P, _P, _P, _LL, _P]),
     "depgan_uresnet_labels": (_I, [_P, _D, _I, _P, _P, _P, _LL, _P]),
     "depgan_label_confusion": (_I, [_P, _P, _LL, _P, _P]),
+    "depgan_set_sync_hook": (_I, [_P, _P, _I]),
     "depgan_launch_count": (_LL, []),
     "depgan_profile_begin": (_I, []),
     "depgan_profile_end": (_I, [_P, _P, _P, _P, _I]),

@@ -203,6 +203,34 @@ class Gen_UNet2D(_Net):
         return out
 
     # ---- DEP-UResNet supervised training: my_network.fit(...) TU:602-606 (model compiled at TU:427) ----------
+    def enable_data_parallel(self):
+        """Data-parallel ``fit`` under torchrun (one process per GPU, ``torch.distributed`` initialised with NCCL):
+        BatchNorm statistics become batch-global (synchronised BN: the C library calls back into an all-reduce for every
+        BN layer, forward and backward), the loss is scaled by the global pixel count, and ``train_on_batch_device``
+        sums the gradient bucket and the loss over the ranks, so every rank applies the update a single GPU would apply
+        to the concatenated batch."""
+        torch = self._torch
+        dist = torch.distributed
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+            raise RuntimeError("enable_data_parallel needs an initialised torch.distributed group with world size >= 2")
+        ws = self.workspace
+        base, nbytes = ws.data_ptr(), ws.numel()
+
+        def hook(user, ptr, count, is_f64, stream):
+            try:
+                off, size = ptr - base, count * (8 if is_f64 else 4)
+                if off < 0 or off + size > nbytes:
+                    return -1
+                dist.all_reduce(ws[off:off + size].view(torch.float64 if is_f64 else torch.float32))
+                return 0
+            except Exception:  # never let an exception cross the C boundary
+                return -1
+
+        self._sync_cb = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p)(hook)
+        self._dist = dist
+        _lib.check(_lib.lib().depgan_set_sync_hook(C.cast(self._sync_cb, C.c_void_p), None, dist.get_world_size()),
+                   "set_sync_hook")
+
     def train_on_batch_device(self, x, z, onehot, keep):
         """One Keras training-phase step on CUDA tensors (x (n,H,W,1) f32, z (n,L,1) f32, onehot (n,H,W,nc) f32,
         keep (n,H/4,W/4,96) uint8 Dropout keep mask).  Gradients + Adam(1e-4, 0.9, 0.999); returns the loss tensor."""
@@ -216,6 +244,9 @@ class Gen_UNet2D(_Net):
             _lib.check(_lib.lib().depgan_uresnet_grads(self.handle, x.data_ptr(), z.data_ptr(), onehot.data_ptr(),
                                                        keep.data_ptr(), self._loss.data_ptr(), n, _stream(torch)),
                        "uresnet_grads")
+        if getattr(self, "_dist", None) is not None:  # partial sums of the global-batch mean
+            self._dist.all_reduce(self.grads)
+            self._dist.all_reduce(self._loss)
         loss = self._loss.clone()
         self.adam_step(1e-4, 0.9, 0.999)  # keras.optimizers.Adam(lr=1e-4) defaults (TU:427)
         return loss
@@ -251,21 +282,30 @@ class Gen_UNet2D(_Net):
         n = x.shape[0]
         rng = np.random.default_rng(seed)
         hist = {"loss": [], "val_loss": []}
-        bs = min(int(batch_size), self.cfg.max_batch)
+        dp = getattr(self, "_dist", None)
+        rank, world = (dp.get_rank(), dp.get_world_size()) if dp is not None else (0, 1)
+        bs = int(batch_size) if dp is not None else min(int(batch_size), self.cfg.max_batch)
         for _ in range(int(epochs)):
             order = rng.permutation(n) if shuffle else np.arange(n)
             tot, cnt = 0.0, 0
             for i in range(0, n, bs):
                 idx = order[i:i + bs]
-                if len(idx) < 2:
-                    continue  # batch statistics need at least two samples
+                if len(idx) < 2 * world:
+                    continue  # batch statistics need at least two samples (per rank)
                 keep = (rng.uniform(size=(len(idx), self.cfg.H // 4, self.cfg.W // 4, 96)) >= 0.25).astype(np.uint8)
+                if dp is not None:  # every rank draws the same global batch and mask and takes its contiguous shard
+                    if len(idx) % world:
+                        continue
+                    per = len(idx) // world
+                    if per > self.cfg.max_batch:
+                        raise ValueError("batch_size / world exceeds max_batch")
+                    idx, keep = idx[rank * per:(rank + 1) * per], keep[rank * per:(rank + 1) * per]
                 loss = self.train_on_batch_device(torch.from_numpy(x[idx]).to(self.device),
                                                   torch.from_numpy(z[idx]).to(self.device),
                                                   torch.from_numpy(y[idx]).to(self.device),
                                                   torch.from_numpy(keep).to(self.device))
-                tot += float(loss.item()) * len(idx)
-                cnt += len(idx)
+                tot += float(loss.item()) * len(idx) * world
+                cnt += len(idx) * world
             hist["loss"].append(tot / max(cnt, 1))
             if validation_data is not None:
                 (xv, zv), yv = validation_data

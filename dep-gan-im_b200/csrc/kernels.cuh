@@ -99,6 +99,9 @@ int k_pack_deconv_dgrad(const float* src, const float* scale, float* dst_f32, bf
                         cudaStream_t st);
 
 // ---- training-phase BatchNorm / Dropout / softmax-CCE / dense helpers (kernels_bn.cu) ----------------------
+typedef int (*depgan_allreduce_fn)(void* user, void* dev_ptr, long long count, int is_f64, void* stream);
+int bn_set_sync_hook(depgan_allreduce_fn fn, void* user, int world);
+int bn_sync_world();
 int k_bn_stats(const void* x, long long rows, int C, double* sums_scratch, float* mean, float* inv_std, float* mov_mean,
                float* mov_var, float momentum, int dt, cudaStream_t st);
 int k_bn_apply(const void* x, const float* mean, const float* inv_std, const float* gamma, const float* beta, void* out,

@@ -125,9 +125,9 @@ __global__ void bn_bwd_apply_kernel(const T* dy, const T* x, const T* relu_out, 
   }
 }
 
-__global__ void copy2_kernel(const float* red, float* dbeta, float* dgamma, int C) {
+__global__ void copy2_kernel(const float* red, float* dbeta, float* dgamma, int C, float scale) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) { dbeta[c] = red[c]; dgamma[c] = red[C + c]; }
+  if (c < C) { dbeta[c] = red[c] * scale; dgamma[c] = red[C + c] * scale; }
 }
 
 template <typename T>
@@ -246,6 +246,20 @@ __global__ void __launch_bounds__(256) head_bwd_multi_kernel(const float* dseg, 
     if ((dt) == DT_F32) { CALL_F32; } else { CALL_BF16; } \
   } while (0)
 
+// ---- synchronised BatchNorm for data-parallel training: the per-channel batch sums of the forward pass
+// and of the backward reduction are summed over the ranks by a caller-supplied hook before they are used, and the
+// element count becomes the global one.  One process drives one GPU, so the hook is process-global.
+static depgan_allreduce_fn g_sync_fn = nullptr;
+static void* g_sync_user = nullptr;
+static int g_sync_world = 1;
+int bn_set_sync_hook(depgan_allreduce_fn fn, void* user, int world) {
+  g_sync_fn = world > 1 ? fn : nullptr;
+  g_sync_user = user;
+  g_sync_world = (world > 1 && fn) ? world : 1;
+  return 0;
+}
+int bn_sync_world() { return g_sync_world; }
+
 int k_bn_stats(const void* x, long long rows, int C, double* sums_scratch, float* mean, float* inv_std, float* mov_mean,
                float* mov_var, float momentum, int dt, cudaStream_t st) {
   if (rows == 0) return 0;
@@ -257,8 +271,14 @@ int k_bn_stats(const void* x, long long rows, int C, double* sums_scratch, float
   DISPATCH_DT(dt, (bn_sums_kernel<float><<<grid, 256, 0, st>>>((const float*)x, rows, C, sums_scratch, rpc)),
               (bn_sums_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, rows, C, sums_scratch, rpc)));
   DG_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, (double)rows, C, mean, inv_std, mov_mean, mov_var,
-                                                      momentum);
+  if (g_sync_fn) {
+    if (g_sync_fn(g_sync_user, sums_scratch, 2LL * C, 1, (void*)st) != 0) {
+      depgan_set_error("bn_stats: the all-reduce hook failed");
+      return -1;
+    }
+  }
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums_scratch, (double)rows * g_sync_world, C, mean, inv_std,
+                                                      mov_mean, mov_var, momentum);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -296,18 +316,27 @@ int k_bn_bwd(const void* dy, const void* x, const void* relu_out, const float* m
               (bn_bwd_reduce_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)relu_out,
                                                                 mean, inv_std, rows, C, red_scratch, rpc)));
   DG_LAUNCH_CHECK();
+  if (g_sync_fn) {
+    if (g_sync_fn(g_sync_user, red_scratch, 2LL * C, 0, (void*)st) != 0) {
+      depgan_set_error("bn_bwd: the all-reduce hook failed");
+      return -1;
+    }
+  }
+  const float inv_rows = 1.0f / ((float)rows * (float)g_sync_world);
   const long long total = rows * C;
   DISPATCH_DT(dt,
               (bn_bwd_apply_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)dy, (const float*)x,
                                                                           (const float*)relu_out, mean, inv_std, gamma,
-                                                                          red_scratch, 1.0f / (float)rows, (float*)dx,
+                                                                          red_scratch, inv_rows, (float*)dx,
                                                                           total, C)),
               (bn_bwd_apply_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)dy, (const bf16*)x,
                                                                          (const bf16*)relu_out, mean, inv_std, gamma,
-                                                                         red_scratch, 1.0f / (float)rows, (bf16*)dx,
+                                                                         red_scratch, inv_rows, (bf16*)dx,
                                                                          total, C)));
   DG_LAUNCH_CHECK();
-  copy2_kernel<<<(C + 127) / 128, 128, 0, st>>>(red_scratch, dbeta, dgamma, C);
+  // synchronised: red_scratch already holds the GLOBAL sums; the flat gradient bucket is summed over the ranks later,
+  // so each rank contributes 1/world of them
+  copy2_kernel<<<(C + 127) / 128, 128, 0, st>>>(red_scratch, dbeta, dgamma, C, 1.0f / (float)g_sync_world);
   DG_LAUNCH_CHECK();
   return 0;
 }

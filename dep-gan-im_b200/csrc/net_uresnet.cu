@@ -83,6 +83,8 @@ int dense_bn_fwd(Ctx& c, const DenseL& D, BnState& s, const float* X, int rows, 
 
 extern "C" {
 
+int depgan_set_sync_hook(depgan_allreduce_fn fn, void* user, int world) { return bn_set_sync_hook(fn, user, world); }
+
 int depgan_cce_loss(const float* prob_dev, const float* onehot_dev, float* dseg_scratch_dev, float* loss_dev,
                     long long npix, int nc, float inv_total, void* stream) {
   DG_REQUIRE(prob_dev && onehot_dev && dseg_scratch_dev && loss_dev, "cce_loss: null pointer");
@@ -153,7 +155,10 @@ int depgan_uresnet_grads(depgan_net* g, const float* x_dev, const float* z_dev, 
   DG_TRY(k_head_fwd(g->act_o[6], g->P(g->g_seg.k_off), g->P(g->g_seg.b_off), g->dem_f32, (long long)n * hw, f, nc, 1,
                     g->act_dt, st));
   DG_CHECK_CUDA(cudaMemsetAsync(loss_dev, 0, sizeof(float), st));
-  DG_TRY(k_softmax_cce(g->dem_f32, onehot_dev, T.dseg, loss_dev, (long long)n * hw, nc, 1.0f / ((float)n * (float)hw),
+  // data parallel: the loss and its gradient seed are scaled by the GLOBAL pixel count, so summing the ranks' losses
+  // and gradient buckets gives the global-batch mean
+  DG_TRY(k_softmax_cce(g->dem_f32, onehot_dev, T.dseg, loss_dev, (long long)n * hw, nc,
+                       1.0f / ((float)n * (float)bn_sync_world() * (float)hw),
                        st));
 
   // ================= backward =================

@@ -123,6 +123,16 @@ int depgan_dem_postproc(const float* x_dev, int nicg, const double* acc_dev, dou
 int depgan_uresnet_labels(const double* acc_dev, double n_repeat, int chan, double* mean_out_dev,
                           unsigned char* labels_dev, unsigned long long* count_dev, long long npix, void* stream);
 
+/* ---- data-parallel DEP-UResNet fit: synchronised BatchNorm ----
+ * With a hook installed, depgan_uresnet_grads sums every BatchNorm layer's batch statistics (forward: 2*C doubles,
+ * backward reduction: 2*C floats, both in the handle's workspace) over the ranks through `fn` before using them,
+ * counts world * n samples, and scales the loss / gradient seed by the global pixel count; the caller then sums the
+ * flat gradient bucket and the loss over the ranks.  fn must enqueue an in-place sum all-reduce of `count` elements at
+ * dev_ptr on `stream` (or order it after that stream) and return 0.  world <= 1 or fn == NULL removes the hook.
+ * Process-global: one process drives one GPU. */
+typedef int (*depgan_allreduce_fn)(void* user, void* dev_ptr, long long count, int is_f64, void* stream);
+int depgan_set_sync_hook(depgan_allreduce_fn fn, void* user, int world);
+
 /* ---- evaluation of a predicted label map against the ground-truth one (EG:688-807 / EU:606-704) ----
  * conf16[4*real + fake] = number of voxels with ground-truth label `real` and predicted label `fake` (labels 0..3:
  * background / shrink / grow / stay).  The six Dice scores of the reference's CSV row are ratios of sums of these

@@ -114,3 +114,61 @@ def test_data_parallel_two_gpus_reproduce_global_batch_step():
         w = w.numpy()
         if np.linalg.norm(w) > 1e-9:
             assert np.linalg.norm(out["g_grads"][k] - w) / np.linalg.norm(w) < 2e-3, k
+
+
+# ---- data-parallel DEP-UResNet fit: synchronised BatchNorm over two GPUs == one GPU on the concatenated batch ----
+def _fit_data(H, N, seed=0):
+    x, _ = synth.make_flair(N, H, H, seed=seed + 2)
+    z = synth.make_noise(N, seed=seed + 3)
+    rng = np.random.default_rng(seed)
+    onehot = np.eye(4, dtype=np.float32)[rng.integers(0, 4, (N, H, H))]
+    keep = (rng.uniform(size=(N, H // 4, H // 4, 96)) >= 0.25).astype(np.uint8)
+    return x, z, onehot, keep
+
+
+def _fit_dp_worker(rank, world, port, out):
+    import torch.distributed as dist
+    from depgan_b200 import Gen_UNet2D
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    H, N = 32, 8
+    dev = "cuda:%d" % rank
+    per = N // world
+    g = Gen_UNet2D((H, H, 1), (32, 1), 32, 4, precision="fp32", max_batch=per, device=dev, training="fit")
+    g.set_weights(util.gen_weights(1, 4, seed=1))
+    g.enable_data_parallel()
+    sl = slice(rank * per, (rank + 1) * per)
+    loss = g.train_on_batch_device(*[torch.from_numpy(a[sl]).to(dev) for a in _fit_data(H, N)])
+    if rank == 0:
+        out["loss"] = float(loss.item())
+        out["grads"] = g.get_grads()
+        out["weights"] = g.get_weights()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_uresnet_fit_data_parallel_sync_bn_matches_single_gpu():
+    import torch.multiprocessing as mp
+    from depgan_b200 import Gen_UNet2D
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fit_dp_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    H, N = 32, 8
+    g = Gen_UNet2D((H, H, 1), (32, 1), 32, 4, precision="fp32", max_batch=N, training="fit")
+    g.set_weights(util.gen_weights(1, 4, seed=1))
+    loss = g.train_on_batch_device(*[torch.from_numpy(a).cuda() for a in _fit_data(H, N)])
+    assert abs(out["loss"] - float(loss.item())) <= 1e-5 * max(1.0, abs(float(loss.item())))
+    want = g.get_grads()
+    a = np.concatenate([out["grads"][k].ravel() for k in want])
+    b = np.concatenate([want[k].ravel() for k in want])
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4
+    for k, w in want.items():
+        nrm = np.linalg.norm(w)
+        if nrm > 1e-6:
+            assert np.linalg.norm(out["grads"][k] - w) / nrm < 5e-3, k
+    wts = g.get_weights()  # after the Adam step, moving statistics included
+    for k in wts:
+        assert np.allclose(out["weights"][k], wts[k], rtol=2e-4, atol=2e-5), k
