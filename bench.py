@@ -221,7 +221,7 @@ def run_gpu(args, w, rank, world, local_rank):
     xh, zh = torch.from_numpy(x).pin_memory(), torch.from_numpy(z).pin_memory()
     ohs = [torch.empty((B, 256, 256, w["nc_out"]), dtype=torch.float32).pin_memory() for _ in range(2)]
     oh = ohs[0]
-    pipe = InferencePipeline(g)
+    pipe = InferencePipeline(g, depth=int(os.environ.get("DEPGAN_PIPE_DEPTH", "2")))
     for i in range(max(3, args.warmup)):
         pipe.submit(xh, zh, ohs[i % 2])
     pipe.flush()
