@@ -17,9 +17,10 @@
 //     hardware swizzle is a function of the shared-memory address, so views starting at any pixel are valid
 //     as long as the TMA destination is pattern (1024 B) aligned.  Activations are read from L2/HBM once per
 //     tile (x1.27 halo overhead) instead of once per tap.
-//   * B (weights, [tap][n][k] bf16) streams through its own TMA ring, one (tap, chunk) tile per stage.
-//     When every (chunk, tap) tile of the layer fits next to the activation ring (32->32 ... 96->96 3x3 layers)
-//     the weights are loaded ONCE per CTA and stay resident (template RES).
+//   * B (weights, [tap][n][k] bf16): when every (chunk, tap) tile of the layer fits next to the activation ring
+//     (32->32 ... 96->96 3x3 layers) the weights are loaded ONCE per CTA and stay resident (template RES); otherwise
+//     they stream through their own TMA ring whose stage holds all taps of a channel chunk (or one kernel row, or
+//     one tap, whichever fits), so the issuer waits once per stage.
 //   * Persistent: grid = min(#work items, #SMs), one CTA per SM looping over (tile, n-split) items.
 //     Control warps: TMA producer of the A/B rings, TMA producer of the epilogue side inputs, and two MMA issuers
 //     (tcgen05.mma.cta_group::1.kind::f16), one per TMEM accumulator stage (4*ncta <= 512 columns), so the barrier
@@ -28,7 +29,10 @@
 //     2 add / mask sources) never touches global memory with per-thread accesses: side inputs arrive as TMA tiles
 //     [16][16][ch] in a 2-stage ring, results are packed to bf16 into a swizzled staging tile and leave by one TMA
 //     store per ch-channel chunk (5-D map for the transposed conv's 2x2 scatter), double-buffered with bulk-group
-//     waits.  The TMEM stage is handed back to the issuer as soon as its last column is in registers.
+//     waits.  The TMEM stage is handed back to the issuer as soon as its last column is in registers.  (The fp32
+//     pre-FiLM copy `out_pre` of the training forward is the one per-thread global store left.)
+//   * What bounds it: for N < 128 the 128 B/clk shared-memory port (A and B slices are re-read by every SS-mode MMA;
+//     TMA fills and the epilogue staging share the port), not the tensor pipe -- see DESIGN.md section 4.
 #pragma once
 #include <cuda.h>
 
