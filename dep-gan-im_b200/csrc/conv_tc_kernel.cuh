@@ -29,7 +29,7 @@
 //     2 add / mask sources) never touches global memory with per-thread accesses: side inputs arrive as TMA tiles
 //     [16][16][ch] in a 2-stage ring, results are packed to bf16 into a swizzled staging tile and leave by one TMA
 //     store per ch-channel chunk (5-D map for the transposed conv's 2x2 scatter), double-buffered with bulk-group
-//     waits.  The TMEM stage is handed back to the issuer as soon as its last column is in registers.  (The fp32
+//     waits.  The TMEM stage is handed back to the issuer as soon as its last column is in registers.  (The bf16
 //     pre-FiLM copy `out_pre` of the training forward is the one per-thread global store left.)
 //   * What bounds it: for N < 128 the 128 B/clk shared-memory port (A and B slices are re-read by every SS-mode MMA;
 //     TMA fills and the epilogue staging share the port), not the tensor pipe -- see DESIGN.md section 4.
