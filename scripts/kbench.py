@@ -24,7 +24,7 @@ def act(shape, bf16, seed):
 
 
 def conv_case(name, N, H, W, c0, cout, ks, *, c1=0, tc=True, in_bf16=None, film=False, add=False, mask=False,
-              deconv=False, pre=False, relu=True, out_bf16=True, head=0):
+              deconv=False, pre=False, relu=True, out_bf16=True, head=0, film_self=False):
     in_bf16 = tc if in_bf16 is None else in_bf16
     keep = []
     d = _lib.ConvDesc()
@@ -57,7 +57,8 @@ def conv_case(name, N, H, W, c0, cout, ks, *, c1=0, tc=True, in_bf16=None, film=
         p = torch.empty_like(out); keep.append(p); d.out_pre = p.data_ptr(); nbytes += out.numel() * out.element_size()
     if film:
         g, b = torch.ones(N, cout, device=dev), torch.zeros(N, cout, device=dev); keep += [g, b]
-        r = act((N, H, W, cout), out_bf16, 3); keep.append(r)
+        r = x if film_self else act((N, H, W, cout), out_bf16, 3)  # film_self: the residual is the conv input (as in the nets)
+        keep.append(r)
         d.film_g, d.film_b, d.film_stride, d.res = g.data_ptr(), b.data_ptr(), cout, r.data_ptr()
         nbytes += r.numel() * r.element_size()
     if add:
@@ -107,6 +108,9 @@ CASES = [
     lambda: wgrad_case("wgrad_first_3x3_1to32_N32", 32, 256, 256, 1, 32, 3, 2),
     lambda: conv_case("tc_3x3_32to32_plain_N64", 64, 256, 256, 32, 32, 3),
     lambda: conv_case("tc_3x3_32to32_film_N64", 64, 256, 256, 32, 32, 3, film=True, relu=False),
+    lambda: conv_case("tc_3x3_32to32_filmA_N64", 64, 256, 256, 32, 32, 3, film=True, relu=False, film_self=True),
+    lambda: conv_case("tc_3x3_64to64_filmA_N64", 64, 128, 128, 64, 64, 3, film=True, relu=False, film_self=True),
+    lambda: conv_case("tc_3x3_96to96_filmA_N64", 64, 64, 64, 96, 96, 3, film=True, relu=False, film_self=True),
     lambda: conv_case("tc_3x3_32to32_film_pre_N32", 32, 256, 256, 32, 32, 3, film=True, relu=False, pre=True),
     lambda: conv_case("tc_3x3_32to32_mask_N32", 32, 256, 256, 32, 32, 3, mask=True, relu=False),
     lambda: conv_case("tc_3x3_32to32_head_N64", 64, 256, 256, 32, 32, 3, head=4),
