@@ -383,26 +383,45 @@ __global__ void __launch_bounds__(256) critic_head_bwd_vec_kernel(const bf16* h,
 
 // Gradient penalty pieces (TG:543-545): per sample norm = sqrt(sum g^2); gp_partial += (norm-1)^2 / global_n;
 // u = delta * (2/global_n) * (norm-1)/norm * g  (the input of the JVP pass).  One CTA per sample.
-__global__ void __launch_bounds__(256) gp_kernel(const float* g, float* u, float* gp_out, long long hw, float delta,
-                                                 float inv_n) {
-  __shared__ double red[8];
+__global__ void __launch_bounds__(1024) gp_kernel(const float* g, float* u, float* gp_out, long long hw, float delta,
+                                                  float inv_n) {
+  __shared__ double red[32];
   __shared__ float coef;
   const float* gs = g + (size_t)blockIdx.x * hw;
+  float* us = u + (size_t)blockIdx.x * hw;
+  const bool vec = (hw & 3) == 0;  // 16-byte rows (hw = H*W is a multiple of 256 for the networks)
   double acc = 0.0;
-  for (long long i = threadIdx.x; i < hw; i += blockDim.x) acc += (double)gs[i] * gs[i];
+  if (vec) {
+    const float4* g4 = reinterpret_cast<const float4*>(gs);
+    for (long long i = threadIdx.x; i < hw / 4; i += blockDim.x) {
+      const float4 v = __ldg(g4 + i);
+      acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+  } else {
+    for (long long i = threadIdx.x; i < hw; i += blockDim.x) acc += (double)gs[i] * gs[i];
+  }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int i = 0; i < 8; ++i) t += red[i];
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
     const float norm = (float)sqrt(t);
     atomicAdd(gp_out, (norm - 1.f) * (norm - 1.f) * inv_n);
     coef = norm > 0.f ? delta * 2.f * inv_n * (norm - 1.f) / norm : 0.f;
   }
   __syncthreads();
-  float* us = u + (size_t)blockIdx.x * hw;
-  for (long long i = threadIdx.x; i < hw; i += blockDim.x) us[i] = coef * gs[i];
+  if (vec) {
+    const float4* g4 = reinterpret_cast<const float4*>(gs);
+    float4* u4 = reinterpret_cast<float4*>(us);
+    const float c = coef;
+    for (long long i = threadIdx.x; i < hw / 4; i += blockDim.x) {
+      const float4 v = __ldg(g4 + i);
+      u4[i] = make_float4(c * v.x, c * v.y, c * v.z, c * v.w);
+    }
+  } else {
+    for (long long i = threadIdx.x; i < hw; i += blockDim.x) us[i] = coef * gs[i];
+  }
 }
 
 // out[k] += alpha * sum_i src[i] for k-th segment of `seg` elements (critic score means)
@@ -923,7 +942,7 @@ int k_critic_head_bwd(const void* h, const void* v, const float* go, const float
 
 int k_gp(const float* g, float* u, float* gp_out, int n, long long hw, float delta, float inv_n, cudaStream_t st) {
   if (n == 0) return 0;
-  gp_kernel<<<n, 256, 0, st>>>(g, u, gp_out, hw, delta, inv_n);
+  gp_kernel<<<n, 1024, 0, st>>>(g, u, gp_out, hw, delta, inv_n);
   DG_LAUNCH_CHECK();
   return 0;
 }
