@@ -195,8 +195,19 @@ __global__ void __launch_bounds__(32 * FILM_KS) film_stage_b_kernel(FilmMlpArgs 
   for (int s = 0; s < 8; ++s) acc[s] = 0.f;
   const int kpart = (K + FILM_KS - 1) / FILM_KS;
   const int k_end = min(K, (kq + 1) * kpart);
-  for (int k = kq * kpart; k < k_end; ++k) {
-    const float wv = W[(size_t)k * C + cl0 + cx];
+  // the weight loads are the latency: keep 8 of them in flight
+  int k = kq * kpart;
+  for (; k + 8 <= k_end; k += 8) {
+    float wv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) wv[u] = __ldg(W + (size_t)(k + u) * C + cl0 + cx);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+      for (int s = 0; s < 8; ++s) acc[s] = fmaf(s_h2[s * K + k + u], wv[u], acc[s]);
+  }
+  for (; k < k_end; ++k) {
+    const float wv = __ldg(W + (size_t)k * C + cl0 + cx);
 #pragma unroll
     for (int s = 0; s < 8; ++s) acc[s] = fmaf(s_h2[s * K + k], wv, acc[s]);
   }
