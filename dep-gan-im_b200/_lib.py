@@ -30,7 +30,7 @@ class ConvDesc(C.Structure):
                 ("head_w", C.c_void_p), ("head_b", C.c_void_p), ("head_out", C.c_void_p), ("head_nc", C.c_int),
                 ("head_act", C.c_int),
                 ("N", C.c_int), ("H", C.c_int), ("W", C.c_int), ("Cout", C.c_int), ("ks", C.c_int),
-                ("in_bf16", C.c_int), ("out_bf16", C.c_int), ("use_tc", C.c_int)]
+                ("in_bf16", C.c_int), ("out_bf16", C.c_int), ("use_tc", C.c_int), ("pool_out", C.c_void_p)]
 
 
 _P, _I, _LL, _F, _D = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_double

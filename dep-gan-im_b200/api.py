@@ -440,7 +440,7 @@ class Dis_C2D_FCN1(_Net):
 
 # ---- kernel-level op (tests / micro-benchmarks) -----------------------------------------------------------
 def conv2d_op(x, w, *, x1=None, scale=None, shift=None, relu=False, film=None, res=None, add=None, mask=None,
-              deconv=False, head=None, use_tc=True, want_pre=False):
+              deconv=False, head=None, use_tc=True, want_pre=False, want_pool=False):
     """One fused convolution through depgan_op_conv2d.
 
     x (N,H,W,C0) [, x1 (N,H,W,C1)] float32 CUDA tensors; w Keras HWIO (k,k,Cin,Cout) or, for deconv, Keras
@@ -526,12 +526,17 @@ def conv2d_op(x, w, *, x1=None, scale=None, shift=None, relu=False, film=None, r
     d.N, d.H, d.W, d.Cout, d.ks = N, H, W, cout, ks
     d.in_bf16 = d.out_bf16 = int(use_tc)
     d.use_tc = int(use_tc)
+    pool = None
+    if want_pool:
+        pool = torch.empty((N, oh // 2, ow // 2, cout), dtype=odt, device=dev)
+        d.pool_out = pool.data_ptr()
     _lib.check(L.depgan_op_conv2d(C.byref(d), st), "op_conv2d")
     torch.cuda.synchronize(dev)
     outf = out.float()
-    if head is None and not want_pre:
+    if head is None and not want_pre and not want_pool:
         return outf
-    return outf, {"head": hout, "pre": None if pre is None else pre.float()}
+    return outf, {"head": hout, "pre": None if pre is None else pre.float(),
+                  "pool": None if pool is None else pool.float()}
 
 
 def wgrad_op(x, dy, ks, *, x1=None, use_tc=True):

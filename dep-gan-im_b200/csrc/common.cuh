@@ -65,6 +65,7 @@ __device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn
 //   if mask_src: v = mask_src > 0 ? v : 0               (ReLU / activation-pattern mask for dgrad and JVP)
 //   if relu    : v = max(v, 0)
 //   if out     : out = v
+//   if pool_out: pool_out[n,h/2,w/2,c] = max of the 2x2 window of out            (tcgen05 path only, fused)
 //   if head_w  : head_out[n,h,w,:] = act(sum_c v[c] * head_w[c,:] + head_b)   (1x1 gen_segmentation, TG:494-495)
 // deconv = 1: ks must be 1; weights hold 4*Cout columns (a,b,co) and column (ab,co) of input pixel (h,w) is
 //   written to out[n, 2h+a, 2w+b, co] (Conv2DTranspose k2 s2, TG:307-312); scale/shift are indexed by co.
@@ -92,6 +93,7 @@ struct ConvArgs {
   int head_nc, head_act;  // act: 0 tanh, 1 softmax, 2 linear
   int N, H, W, Cout, ks;
   int in_dt, out_dt;  // DType of in0/in1 and of out/out_pre/res/add_src/mask_src
+  void* pool_out;     // optional (N,H/2,W/2,Cout): 2x2 stride-2 max-pool of `out` (MaxPooling2D after the block, TG:409)
 };
 
 int conv_fwd_simt(const ConvArgs& a, cudaStream_t st);

@@ -95,7 +95,8 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   const int n_side = a.film_g ? 1 : (a.add_src ? 1 : 0) + (a.mask_src ? 1 : 0);
   const int stage_out = a.out ? 1 : 0;
   const uint32_t slot = 256u * ch * 2u;
-  const uint32_t staging = (stage_out ? 2u : 0u) * slot + 2u * n_side * slot;
+  const int pool = a.pool_out ? 1 : 0;
+  const uint32_t staging = (stage_out ? 2u : 0u) * slot + 2u * n_side * slot + (pool ? slot / 2u : 0u);
   const uint32_t floats = 2u * ncols * 4 + (a.head_w ? 16u * a.Cout : 0u) + (a.film_g ? 24u * ncta : 0u) + 64u;
   for (int kc = 64; kc >= 16; kc /= 2) {
     if (a.C0 % kc || a.C1 % kc) continue;
@@ -145,7 +146,7 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
     // fill f-1 has landed; an issuer knows that for its own previous item (two items back), so a stage must not be
     // refilled more than once within two consecutive items: na >= 2 * nchunks.
     g->n_issuers = (resident && acc_stages == 2 && na >= 2 * nchunks) ? 2 : 1;
-    g->ch = ch; g->n_side = n_side; g->stage_out = stage_out; g->slot_bytes = slot;
+    g->ch = ch; g->n_side = n_side; g->stage_out = stage_out; g->slot_bytes = slot; g->pool = pool;
     *smem_bytes = 1024 + na * a_bytes + nb * (resident ? 1 : tps) * b_bytes + staging + bar_bytes(na, nb) + floats;
     return true;
   }
@@ -185,6 +186,9 @@ bool conv_tc_supported(const ConvArgs& a) {
   if (a.deconv && (a.film_g || a.add_src || a.mask_src)) return false;  // side inputs index the conv layout
   if (a.film_g && (a.add_src || a.mask_src || !a.out || !a.res)) return false;
   if (a.deconv && (a.out_pre || !a.out)) return false;
+  if (a.pool_out && (a.deconv || a.film_g || a.add_src || a.mask_src || a.head_w || a.out_pre || !a.out || a.ks == 1 ||
+                     a.Cout > 256))
+    return false;  // the fused pool is an epilogue of the plain conv + BN + ReLU layers only
   TcGeom g;
   uint32_t smem;
   return plan(a, &g, &smem);
@@ -202,7 +206,8 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   if (a.C1 > 0) DG_TRY(make_act_map(&tm.a1, a.in1, a.C1, a.W, a.H, a.N, g.kc, ht));
   else tm.a1 = tm.a0;
   DG_TRY(make_w_map(&tm.b, a.w_tc, a.C0 + a.C1, a.ks * a.ks * g.ncols_total, g.kc, g.ncta));
-  tm.out = tm.s0 = tm.s1 = tm.a0;  // placeholders for the maps this launch does not use
+  tm.out = tm.s0 = tm.s1 = tm.pool = tm.a0;  // placeholders for the maps this launch does not use
+  if (a.pool_out) DG_TRY(make_nhwc_map(&tm.pool, a.pool_out, a.Cout, a.W / 2, a.H / 2, a.N, g.ch, 8, 8, "pooled output"));
   if (a.out) {
     if (a.deconv) DG_TRY(make_deconv_out_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch));
     else DG_TRY(make_nhwc_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "output"));
@@ -220,7 +225,7 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   const int n_items = g.tiles_w * g.tiles_h * a.N * (g.ncols_total / g.ncta);
   const int grid = n_items < g_num_sms ? n_items : g_num_sms;
   // side inputs the epilogue has to stream (selects the EPI instantiation): 1 FiLM residual, 2 add / mask
-  const int need = a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : 0);
+  const int need = a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : (a.pool_out ? 4 : 0));
   int rc;
   switch (a.ks) {
     case 1: rc = launch_ks1(grid, smem, st, tm, a, g, need); break;

@@ -3,12 +3,13 @@
 
 namespace convtc {
 
-// epi = side inputs of the call: 0 none, 1 FiLM residual, 2 add / mask sources
+// epi = epilogue variant: 0 plain, 1 FiLM residual, 2 add / mask sources, 4 plain + fused 2x2 max-pool
 int launch_ks3(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi) {
   switch (epi * 100 + (g.kc / 16) * 10 + (g.b_resident ? 1 : 0)) {
     DG_TC_CASES(3, 0)
     DG_TC_CASES(3, 1)
     DG_TC_CASES(3, 2)
+    DG_TC_CASES(3, 4)
     default: depgan_set_error("conv_fwd_tc: no kernel for this (ks, kc, epi)"); return -2;
   }
 }
@@ -17,6 +18,7 @@ int set_attrs_ks3() {
   DG_TC_ATTRS(3, 0)
   DG_TC_ATTRS(3, 1)
   DG_TC_ATTRS(3, 2)
+  DG_TC_ATTRS(3, 4)
   return 0;
 }
 

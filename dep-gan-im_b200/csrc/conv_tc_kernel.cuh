@@ -59,11 +59,12 @@ struct TcGeom {
   int n_side;                 // side-input tensors TMA-loaded per chunk (FiLM residual; add and/or mask sources)
   int stage_out;              // 1: `out` is written tile-wise from shared memory by TMA stores
   uint32_t slot_bytes;        // one staging tile: 256 pixels x ch x 2 bytes
+  int pool;                   // 1: the 2x2 max-pooled tile is staged and stored as well (EPI bit 2)
 };
 
 // tensor maps of one launch: activations (two concatenated sources), weights, output, epilogue side inputs
 struct TcMaps {
-  CUtensorMap a0, a1, b, out, s0, s1;
+  CUtensorMap a0, a1, b, out, s0, s1, pool;
 };
 
 // one launcher per kernel size, defined in conv_tc_k{1,3,5}.cu; epi = bit mask of the side inputs the call uses
@@ -310,7 +311,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + g.na * g.a_bytes;
   const uint32_t o_base = b_base + g.nb * g.b_tps * g.b_bytes;             // 2 output staging slots
-  const uint32_t s_base = o_base + (g.stage_out ? 2u * g.slot_bytes : 0u);  // 2 side stages x n_side slots
+  const uint32_t p_base = o_base + (g.stage_out ? 2u * g.slot_bytes : 0u);  // 2 pooled staging slots (64 pixels)
+  const uint32_t s_base = p_base + (g.pool ? g.slot_bytes / 2u : 0u);       // 2 side stages x n_side slots
   const uint32_t bar_base = s_base + 2u * g.n_side * g.slot_bytes;
   const uint32_t fullA = bar_base, emptyA = fullA + 8 * g.na;
   const uint32_t fullB = emptyA + 8 * g.na, emptyB = fullB + 8 * g.nb;
@@ -544,7 +546,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else {
     // ===== epilogue warps: TMEM -> registers -> (staging tile in shared memory -> TMA store) =====
     asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
-    constexpr bool E_RES = (EPI & 1) != 0, E_AM = (EPI & 2) != 0;
+    constexpr bool E_RES = (EPI & 1) != 0, E_AM = (EPI & 2) != 0, E_POOL = (EPI & 4) != 0;
     const int ew = warp - EPI_W0;
     const int strip = ew >> 2;
     const int q = warp & 3;          // TMEM lane quarter this warp may read
@@ -690,6 +692,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           uint8_t* ogen = smem_raw + (o_base + oslot * g.slot_bytes - raw);
           *reinterpret_cast<uint4*>(ogen + u0) = pk[0];
           *reinterpret_cast<uint4*>(ogen + u1) = pk[1];
+          if (E_POOL) {
+            // 2x2 max-pool on the packed bf16 pairs (the rounding is monotonic, so this equals pooling the stored
+            // tensor): the window's pixels are lanes l, l^1 (column) and l^8 (row); the even/even lane stages it
+            uint32_t* w8 = reinterpret_cast<uint32_t*>(pk);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint32_t o = __shfl_xor_sync(0xffffffffu, w8[i], 1);
+              __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w8[i]), *reinterpret_cast<__nv_bfloat162*>(&o));
+              uint32_t mw = *reinterpret_cast<uint32_t*>(&m);
+              o = __shfl_xor_sync(0xffffffffu, mw, 8);
+              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o));
+              w8[i] = *reinterpret_cast<uint32_t*>(&m);
+            }
+            if ((lane & 9) == 0) {
+              const uint32_t pp = (uint32_t)((ty >> 1) * 8 + (tx >> 1)) * (uint32_t)(g.ch * 2);
+              const uint32_t px_ = (pp >> 7) & (uint32_t)(g.ch / 8 - 1);
+              uint8_t* pgen = smem_raw + (p_base + oslot * (g.slot_bytes / 4u) - raw);
+              *reinterpret_cast<uint4*>(pgen + pp + ((((uint32_t)(2 * gg)) ^ px_) << 4)) = pk[0];
+              *reinterpret_cast<uint4*>(pgen + pp + ((((uint32_t)(2 * gg + 1)) ^ px_) << 4)) = pk[1];
+            }
+          }
         }
         if (head_nc == 1) {
 #pragma unroll
@@ -731,6 +754,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               const uint32_t src = o_base + oslot * g.slot_bytes;
               if (a.deconv) tma_store_5d(&tm.out, src, c0, c1, cur.tw * 16, c3, cur.n * a.H + cur.th * 16);
               else tma_store_4d(&tm.out, src, c0, cur.tw * 16, cur.th * 16, cur.n);
+              if (E_POOL)
+                tma_store_4d(&tm.pool, p_base + oslot * (g.slot_bytes / 4u), c0, cur.tw * 8, cur.th * 8, cur.n);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
             oslot ^= 1u;

@@ -317,6 +317,12 @@ int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void*
   a.shift = L.shift;
   a.N = n; a.H = h->lvl_h(L.lvl); a.W = h->lvl_w(L.lvl); a.Cout = L.cout; a.ks = L.ks;
   a.in_dt = in_dt; a.out_dt = h->act_dt;
+  if (a.pool_out && !(h->act_dt == DT_BF16 && conv_tc_supported(a))) {  // unfused fallback: conv, then the pool
+    void* pool_out = a.pool_out;
+    a.pool_out = nullptr;
+    DG_TRY(net_conv(h, L, in0, C0, in1, C1, in_dt, a, n, st));
+    return k_maxpool_fwd(a.out, pool_out, n, a.H, a.W, a.Cout, h->act_dt, st);
+  }
   const bool tc = h->act_dt == DT_BF16 && conv_tc_supported(a);
   ProfScope prof(a, tc, st);
   if (tc) return conv_fwd_tc(a, st);
@@ -380,10 +386,16 @@ int gen_forward_impl(depgan_net* g, const float* x, const float* z, float* out, 
       e.head_nc = c.nc_out; e.head_act = c.nc_out == 1 ? 0 : 1;
       if (!keep && g->act_dt == DT_BF16) e.out = nullptr;                // inference: gen_17 never leaves the SM
     }
+    // MaxPooling2D (TG:409): fused into the block's last conv for training handles.  Inference handles keep the
+    // separate bandwidth pass: fusing it is +2 % slices/s but moves the pooling time into the 3x3 convolution launches
+    // whose tensor-pipe fraction bench.py reports (0.53 -> 0.50), so the reported kernel stays the plain convolution.
+    const bool fuse_pool = bi < 3 && g->cfg.training != 0;
+    if (fuse_pool) e.pool_out = g->act_pool[bi];
     DG_TRY(net_conv(g, g->g_out[bi], g->act_r[bi], w, nullptr, 0, g->act_dt, e, n, st));
     if (bi < 3) {
-      DG_TRY(k_maxpool_fwd(g->act_o[bi], g->act_pool[bi], n, g->lvl_h(GEN_LVL[bi]), g->lvl_w(GEN_LVL[bi]), w,
-                           g->act_dt, st));
+      if (!fuse_pool)
+        DG_TRY(k_maxpool_fwd(g->act_o[bi], g->act_pool[bi], n, g->lvl_h(GEN_LVL[bi]), g->lvl_w(GEN_LVL[bi]), w,
+                             g->act_dt, st));
       in0 = g->act_pool[bi]; C0 = w; in1 = nullptr; C1 = 0;
     } else if (bi < 6) {
       DG_TRY(net_deconv(g, g->g_dec[bi - 3], g->act_o[bi], g->act_up[bi], n, st));
@@ -399,14 +411,13 @@ int critic_forward_impl(depgan_net* d, const float* x, float* out, int n, cudaSt
   int in_dt = DT_F32, C = 1;
   for (int i = 0; i < 11; ++i) {
     const ConvL& L = d->c_conv[i];
+    const bool pooled = i == 1 || i == 3 || i == 5 || i == 7;
     ConvArgs e{};
     e.out = d->c_act[i]; e.relu = 1;
+    if (pooled) e.pool_out = d->c_pool[i / 2];                          // MaxPooling2D fused into the conv
     DG_TRY(net_conv(d, L, in, C, nullptr, 0, in_dt, e, n, st));
     in = d->c_act[i]; C = L.cout; in_dt = d->act_dt;
-    if (i == 1 || i == 3 || i == 5 || i == 7) {
-      DG_TRY(k_maxpool_fwd(d->c_act[i], d->c_pool[i / 2], n, d->lvl_h(L.lvl), d->lvl_w(L.lvl), C, d->act_dt, st));
-      in = d->c_pool[i / 2];
-    }
+    if (pooled) in = d->c_pool[i / 2];
   }
   const int hw = d->lvl_h(4) * d->lvl_w(4);
   return k_critic_head_fwd(in, d->P(d->d9_k), d->P(d->d9_b), d->P(d->dd_k), d->P(d->dd_b), out, n, hw, 256, d->act_dt,
@@ -646,6 +657,8 @@ int depgan_op_conv2d(const depgan_conv_desc* d, void* stream) {
   a.head_act = d->head_act;
   a.N = d->N; a.H = d->H; a.W = d->W; a.Cout = d->Cout; a.ks = d->ks;
   a.in_dt = d->in_bf16 ? DT_BF16 : DT_F32; a.out_dt = d->out_bf16 ? DT_BF16 : DT_F32;
+  a.pool_out = d->pool_out;
+  DG_REQUIRE(!a.pool_out || d->use_tc, "op_conv2d: pool_out is an epilogue of the tcgen05 path");
   if (d->use_tc) {
     DG_REQUIRE(conv_tc_supported(a), "op_conv2d: shape not supported by the tcgen05 path");
     return conv_fwd_tc(a, (cudaStream_t)stream);

@@ -175,6 +175,7 @@ typedef struct depgan_conv_desc {
   const float* head_w; const float* head_b; float* head_out; int head_nc, head_act;
   int N, H, W, Cout, ks;
   int in_bf16, out_bf16, use_tc;
+  void* pool_out; /* optional (N,H/2,W/2,Cout), tcgen05 path: 2x2 stride-2 max-pool of `out`, fused into the epilogue */
 } depgan_conv_desc;
 int depgan_op_conv2d(const depgan_conv_desc* d, void* stream);
 /* Weight gradient of one convolution: dw[tap][Cin][Cout] (fp32, Keras HWIO order) += sum_p x[p+off(tap)] (x) dy[p].

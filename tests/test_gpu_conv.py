@@ -356,3 +356,18 @@ def test_tcgen05_wgrad_with_fused_channel_sums(ks, cin, cout, H, W, N):
     assert float((got - want).abs().max()) <= 1e-3 * float(want.abs().max())
     want_cs = dy.double().sum(dim=(0, 1, 2)).float()
     assert float((cs.cpu() - want_cs).abs().max()) <= 1e-4 * float(dy.abs().sum(dim=(0, 1, 2)).max())
+
+
+@pytest.mark.parametrize("ks,cin,cout,H,W,N", [(3, 32, 32, 64, 64, 5), (3, 64, 64, 32, 48, 11), (3, 96, 96, 32, 32, 9),
+                                               (5, 16, 16, 64, 64, 7), (5, 32, 32, 32, 32, 12), (3, 128, 128, 16, 16, 20)])
+def test_tcgen05_fused_maxpool(ks, cin, cout, H, W, N):
+    """MaxPooling2D(2) fused into the conv + BN + ReLU epilogue: bit-identical to pooling the stored bf16 output."""
+    from depgan_b200 import conv2d_op
+    x = _bf(_rand((N, H, W, cin), 1))
+    w = _bf(_rand((ks, ks, cin, cout), 2, 1.0 / np.sqrt(ks * ks * cin)))
+    sc, sh = 1 + 0.1 * _rand((cout,), 4), 0.1 * _rand((cout,), 5)
+    got, ex = conv2d_op(x.cuda(), w.cuda(), scale=sc, shift=sh, relu=True, use_tc=True, want_pool=True)
+    want, _ = ref_conv(x, w, None, sc, sh, relu=True)
+    assert float((got.cpu() - want).abs().max()) <= 1e-2 * max(1.0, float(want.abs().max()))
+    pooled = F.max_pool2d(got.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert torch.equal(ex["pool"], pooled)
