@@ -99,6 +99,22 @@ int k_pack_deconv_dgrad(const float* src, const float* scale, float* dst_f32, bf
                         cudaStream_t st);
 
 // ---- training-phase BatchNorm / Dropout / softmax-CCE / dense helpers (kernels_bn.cu) ----------------------
+// All conv layers of one network folded / packed by two launches (depgan_net_prepare runs after every optimiser step)
+struct PrepLayer {
+  const float *bias, *gamma, *beta, *mean, *var;
+  float *scale, *shift, *inv_std;
+  const float* w;
+  bf16* w_tc;
+  float* w_dg;
+  bf16* w_dg_tc;
+  int C, taps, cin, scale_dgrad;
+};
+struct PrepTable {
+  int n;
+  PrepLayer L[12];
+};
+int k_prepare_convs(const PrepTable& t, cudaStream_t st);
+
 typedef int (*depgan_allreduce_fn)(void* user, void* dev_ptr, long long count, int is_f64, void* stream);
 int bn_set_sync_hook(depgan_allreduce_fn fn, void* user, int world);
 int bn_sync_world();

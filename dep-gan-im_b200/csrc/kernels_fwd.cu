@@ -51,6 +51,41 @@ __global__ void pack_conv_kernel(const float* src, const float* scale, bf16* dst
   }
 }
 
+// ---- whole-network versions of the two kernels above: blockIdx.y (pack) / blockIdx.x (fold) selects the layer ----
+__global__ void prep_fold_all_kernel(const PrepTable t) {
+  const PrepLayer& L = t.L[blockIdx.x];
+  for (int c = threadIdx.x; c < L.C; c += blockDim.x) {
+    const float b = L.bias ? L.bias[c] : 0.f;
+    if (L.gamma) {
+      const float is = 1.0f / sqrtf(L.var[c] + BN_EPS);
+      const float s = L.gamma[c] * is;
+      L.scale[c] = s;
+      L.shift[c] = L.beta[c] + (b - L.mean[c]) * s;
+      if (L.inv_std) L.inv_std[c] = is;
+    } else {
+      L.scale[c] = 1.f;
+      L.shift[c] = b;
+      if (L.inv_std) L.inv_std[c] = 1.f;
+    }
+  }
+}
+__global__ void prep_pack_all_kernel(const PrepTable t) {
+  const PrepLayer& L = t.L[blockIdx.y];
+  const int Cin = L.cin, Cout = L.C, taps = L.taps;
+  const size_t total = (size_t)taps * Cin * Cout;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int co = i % Cout;
+    const int ci = (i / Cout) % Cin;
+    const int tap = i / ((size_t)Cout * Cin);
+    const float v = L.w[i];
+    if (L.w_tc) L.w_tc[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);
+    const int ft = taps - 1 - tap;
+    const float vs = L.scale_dgrad ? v * L.scale[co] : v;
+    if (L.w_dg) L.w_dg[((size_t)ft * Cout + co) * Cin + ci] = vs;
+    if (L.w_dg_tc) L.w_dg_tc[((size_t)ft * Cin + ci) * Cout + co] = __float2bfloat16_rn(vs);
+  }
+}
+
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* in, T* out, int N, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2;
@@ -433,6 +468,15 @@ int k_pack_conv_weights(const float* src, const float* scale, bf16* dst_tc, floa
   if (!dst_tc && !dst_dgrad && !dst_tc_dgrad) return 0;
   pack_conv_kernel<<<grid_for((long long)taps * Cin * Cout), 256, 0, st>>>(src, scale, dst_tc, dst_dgrad, dst_tc_dgrad,
                                                                          taps, Cin, Cout);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
+int k_prepare_convs(const PrepTable& t, cudaStream_t st) {
+  if (t.n <= 0) return 0;
+  prep_fold_all_kernel<<<t.n, 256, 0, st>>>(t);
+  DG_LAUNCH_CHECK();
+  prep_pack_all_kernel<<<dim3(24, t.n), 256, 0, st>>>(t);
   DG_LAUNCH_CHECK();
   return 0;
 }

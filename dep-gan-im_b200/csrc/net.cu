@@ -523,7 +523,18 @@ int depgan_net_prepare(depgan_net* h, void* stream) {
       DG_CHECK_CUDA(cudaStreamSynchronize(st));  // the host arrays above are stack temporaries
     }
   } else {
-    for (auto& L : h->c_conv) DG_TRY(fold_conv(h, L, st));
+    // the critics are re-prepared after each of their 10 updates per generator iteration: two launches for all layers
+    PrepTable t{};
+    for (auto& L : h->c_conv) {
+      if (L.deconv || t.n >= 12) { t.n = -1; break; }
+      PrepLayer& p = t.L[t.n++];
+      p.bias = h->P(L.b_off); p.gamma = h->P(L.g_off); p.beta = h->P(L.be_off); p.mean = h->P(L.mu_off);
+      p.var = h->P(L.var_off); p.scale = L.scale; p.shift = L.shift; p.inv_std = L.inv_std;
+      p.w = h->P(L.k_off); p.w_tc = L.w_tc; p.w_dg = L.w_dg; p.w_dg_tc = L.w_dg_tc;
+      p.C = L.cout; p.taps = L.ks * L.ks; p.cin = L.cin; p.scale_dgrad = h->cfg.training == 2 ? 0 : 1;
+    }
+    if (t.n > 0) DG_TRY(k_prepare_convs(t, st));
+    else for (auto& L : h->c_conv) DG_TRY(fold_conv(h, L, st));
   }
   h->prepared = true;
   return 0;
