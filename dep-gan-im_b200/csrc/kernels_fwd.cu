@@ -476,7 +476,7 @@ int k_prepare_convs(const PrepTable& t, cudaStream_t st) {
   if (t.n <= 0) return 0;
   prep_fold_all_kernel<<<t.n, 256, 0, st>>>(t);
   DG_LAUNCH_CHECK();
-  prep_pack_all_kernel<<<dim3(24, t.n), 256, 0, st>>>(t);
+  prep_pack_all_kernel<<<dim3(148, t.n), 256, 0, st>>>(t);  // 148 x 256 threads per layer: the 590k-element layers take ~16 strides
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -65,8 +65,8 @@ def full_summary(src, dst, traffic_json, batch, bench_batch, alg_bytes_b16):
 if __name__ == "__main__":
     t = launch_table(SRC / "infer_launches_b64.csv", OUT / "r01_v16_infer_launches_b64.csv")
     print("inference forward b64: %.1f us over all launches (cold, serialised)" % t)
-    if (SRC / "train_launches_v16.csv").exists():
-        t = launch_table(SRC / "train_launches_v16.csv", OUT / "r01_v16_train_launches_b32.csv")
+    if (SRC / "train_launches_v25.csv").exists():
+        t = launch_table(SRC / "train_launches_v25.csv", OUT / "r01_final_train_launches_b32.csv")
         print("train iteration b32: %.1f us" % t)
     full_summary(SRC / "infer_conv_tc_full_raw_b16.csv", OUT / "r01_v16_conv_tc_ncu_full_summary_b16.csv",
                  OUT / "ncu_traffic_r01.json", 16, 64, 2230382600.0)
