@@ -74,3 +74,13 @@ def test_no_cpu_fallback():
     buf = (C.c_float * 16)()
     h = L.depgan_net_create(0, C.byref(cfg), C.addressof(buf), None, C.addressof(buf), 64)
     assert not h and b"no CUDA device" in L.depgan_last_error()
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: no module of the shipped package may import or execute it."""
+    import pathlib
+    import re
+    pkg = pathlib.Path(__file__).resolve().parent.parent / "dep-gan-im_b200"
+    offenders = [p.name for p in list(pkg.glob("*.py")) + list((pkg / "csrc").glob("*"))
+                 if p.is_file() and re.search(r"\boracle\b", p.read_text(errors="ignore"))]
+    assert not offenders, offenders
