@@ -185,6 +185,7 @@ bool conv_tc_supported(const ConvArgs& a) {
   if (a.head_w && (a.deconv || a.Cout > 256 || a.head_nc > 4)) return false;
   if (a.deconv && (a.film_g || a.add_src || a.mask_src)) return false;  // side inputs index the conv layout
   if (a.film_g && (a.add_src || a.mask_src || !a.out || !a.res)) return false;
+  if (a.film_g && a.ks != 3) return false;  // the FiLM-residual epilogue is instantiated for the 3x3 kernels only
   if (a.deconv && (a.out_pre || !a.out)) return false;
   if (a.pool_out && (a.deconv || a.film_g || a.add_src || a.mask_src || a.head_w || a.out_pre || !a.out || a.ks == 1 ||
                      a.Cout > 256))

@@ -371,3 +371,53 @@ def test_tcgen05_fused_maxpool(ks, cin, cout, H, W, N):
     assert float((got.cpu() - want).abs().max()) <= 1e-2 * max(1.0, float(want.abs().max()))
     pooled = F.max_pool2d(got.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
     assert torch.equal(ex["pool"], pooled)
+
+
+def _random_tc_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < n:
+        ks = int(rng.choice([1, 3, 3, 5]))
+        c0 = int(rng.choice([16, 32, 48, 64, 96, 128]))
+        c1 = int(rng.choice([0, 0, 16, 32, 64]))
+        cout = int(rng.choice([16, 32, 48, 64, 96, 128, 160]))
+        H, W = int(rng.choice([16, 32, 48])), int(rng.choice([16, 32, 64]))
+        N = int(rng.integers(1, 24))
+        epi = str(rng.choice(["plain", "plain", "film", "addmask", "mask", "pool"]))
+        if epi == "film":  # the FiLM-residual epilogue exists for the 3x3 layers only (conv_tc_supported)
+            ks, c1, cout = 3, 0, c0
+        if epi == "pool" and ks == 1:
+            ks = 3
+        cases.append((ks, c0, c1, cout, H, W, N, epi))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_tc_cases(36, 1234), ids=lambda c: "-".join(map(str, c)))
+def test_tcgen05_random_shapes(case):
+    """Seeded random sweep over kernel size, channel counts (incl. 48 / 160 and two-source inputs), tile counts and
+    epilogue variants: exercises every ring / issuer / staging plan the planner can produce for small tensors."""
+    from depgan_b200 import conv2d_op
+    ks, c0, c1, cout, H, W, N, epi = case
+    x = _bf(_rand((N, H, W, c0), 1))
+    x1 = _bf(_rand((N, H, W, c1), 2)) if c1 else None
+    w = _bf(_rand((ks, ks, c0 + c1, cout), 3, 1.0 / np.sqrt(ks * ks * (c0 + c1))))
+    sc, sh = 1 + 0.1 * _rand((cout,), 4), 0.1 * _rand((cout,), 5)
+    kw, rkw = {}, {}
+    if epi == "film":
+        g, b, res = 1 + 0.3 * _rand((N, cout), 6), 0.2 * _rand((N, cout), 7), _bf(_rand((N, H, W, cout), 8))
+        kw = dict(film=(g, b), res=res.cuda())
+        rkw = dict(film=(g, b), res=res)
+    elif epi in ("addmask", "mask"):
+        mask = _bf(_rand((N, H, W, cout), 9))
+        add = _bf(_rand((N, H, W, cout), 10)) if epi == "addmask" else None
+        kw = dict(mask=mask.cuda(), add=None if add is None else add.cuda())
+        rkw = dict(mask=mask, add=add)
+    relu = epi in ("plain", "pool")
+    out = conv2d_op(x.cuda(), w.cuda(), x1=None if x1 is None else x1.cuda(), scale=sc, shift=sh, relu=relu, use_tc=True,
+                    want_pool=(epi == "pool"), **kw)
+    got = out[0] if isinstance(out, tuple) else out
+    want, _ = ref_conv(x, w, x1, sc, sh, relu=relu, **rkw)
+    assert float((got.cpu() - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
+    if epi == "pool":
+        pooled = F.max_pool2d(got.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+        assert torch.equal(out[1]["pool"], pooled)
