@@ -421,3 +421,35 @@ def test_tcgen05_random_shapes(case):
     if epi == "pool":
         pooled = F.max_pool2d(got.permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
         assert torch.equal(out[1]["pool"], pooled)
+
+
+def _random_wg_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    for _ in range(n):
+        ks = int(rng.choice([1, 3, 3, 5]))
+        c0 = int(rng.choice([16, 32, 48, 64, 96, 128, 256]))
+        c1 = int(rng.choice([0, 0, 32, 64]))
+        cout = int(rng.choice([16, 32, 64, 96, 128, 256]))
+        cases.append((ks, c0, c1, cout, int(rng.choice([16, 32, 48])), int(rng.choice([16, 32, 64])), int(rng.integers(1, 12))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_wg_cases(24, 4321), ids=lambda c: "-".join(map(str, c)))
+def test_tcgen05_wgrad_random_shapes(case):
+    """Seeded random sweep of the weight-gradient kernel's plans (tap stacking, channel groups, batch split).  A shape
+    the tcgen05 path does not take must be refused by the library with an error, never computed wrongly."""
+    from depgan_b200 import wgrad_op
+    ks, c0, c1, cout, H, W, N = case
+    x = _bf(_rand((N, H, W, c0), 1))
+    x1 = _bf(_rand((N, H, W, c1), 2)) if c1 else None
+    dy = _bf(_rand((N, H, W, cout), 3))
+    try:
+        got = wgrad_op(x.cuda(), dy.cuda(), ks, x1=None if x1 is None else x1.cuda(), use_tc=True).cpu()
+    except RuntimeError as e:
+        assert "not supported" in str(e) or "unsupported" in str(e), e
+        got = wgrad_op(x.cuda(), dy.cuda(), ks, x1=None if x1 is None else x1.cuda(), use_tc=False).cpu()
+    xa = x if x1 is None else torch.cat([x, x1], dim=3)
+    want = ref_wgrad(xa, dy, ks)
+    err = float((got - want).abs().max())
+    assert err <= 2e-3 * float(want.abs().max()), (err, float(want.abs().max()))
