@@ -263,6 +263,9 @@ def run_gpu(args, w, rank, world, local_rank):
                     "traffic": None, "avg_launch_ms": arr_ms[k] / arr_n[k],
                     "flops_per_launch": arr_fl[k] / arr_n[k],
                     "hbm_gbs_same_kernel": arr_by[k] / (arr_ms[k] * 1e-3) / 1e9,
+                    # the second ceiling of the same launches: the 32-channel 256x256 layers sit below the ridge
+                    # (134 FLOP/B vs 211), so their ceiling is the HBM one -- see DESIGN.md section 6
+                    "hbm_frac_same_kernel": arr_by[k] / (arr_ms[k] * 1e-3) / 1e9 / pk["hbm"], "hbm_peak": pk["hbm"],
                     "share_of_conv_time": conv_share,
                     "other_classes_ms_per_step": {"tc5x5": arr_ms[1] / psteps, "tc_deconv": arr_ms[2] / psteps,
                                                   "simt": arr_ms[3] / psteps, "tc3x3": arr_ms[0] / psteps}}
