@@ -107,6 +107,11 @@ CASES = [
     lambda: wgrad_case("wgrad_first_5x5_1to16_N64", 64, 256, 256, 1, 16, 5, 2),
     lambda: wgrad_case("wgrad_first_3x3_1to32_N32", 32, 256, 256, 1, 32, 3, 2),
     lambda: conv_case("tc_3x3_32to32_plain_N64", 64, 256, 256, 32, 32, 3),
+    lambda: conv_case("tc_3x3_32to32_plain_N8_l2", 8, 256, 256, 32, 32, 3),
+    lambda: conv_case("tc_3x3_32to32_plain_N16_l2", 16, 256, 256, 32, 32, 3),
+    lambda: conv_case("tc_3x3_32to32_filmA_N8_l2", 8, 256, 256, 32, 32, 3, film=True, relu=False, film_self=True),
+    lambda: conv_case("tc_3x3_96to32_N8_l2", 8, 256, 256, 64, 32, 3, c1=32),
+    lambda: conv_case("tc_deconv_64_N8_l2", 8, 128, 128, 64, 64, 1, deconv=True),
     lambda: conv_case("tc_3x3_32to32_film_N64", 64, 256, 256, 32, 32, 3, film=True, relu=False),
     lambda: conv_case("tc_3x3_32to32_filmA_N64", 64, 256, 256, 32, 32, 3, film=True, relu=False, film_self=True),
     lambda: conv_case("tc_3x3_64to64_filmA_N64", 64, 128, 128, 64, 64, 3, film=True, relu=False, film_self=True),
