@@ -350,6 +350,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // Programmatic dependent launch: the barrier / TMEM set-up above overlaps the previous kernel's tail.  Everything
+  // that touches global memory comes after the wait (= the previous grid has completed and flushed).  The trigger
+  // is only honoured once every CTA of this grid has issued it, i.e. is resident, so chains of launches cannot
+  // occupy SMs ahead of an unfinished predecessor.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   {  // BN scale / shift (or bias) once per CTA
     const int cmod = a.Cout;
     for (int i = threadIdx.x; i < g.ncols_total; i += TC_THREADS) {
@@ -843,7 +849,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ---- instantiation helpers used by conv_tc_k{1,3,5}.cu ----
 template <int KS, int KSTEPS, bool RES, int EPI>
 int launch_one(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g) {
-  conv_tc_kernel<KS, KSTEPS, RES, EPI><<<grid, TC_THREADS, smem, st>>>(tm, a, g);
+  static const bool pdl = getenv("DEPGAN_NO_PDL") == nullptr;  // A/B switch for the measurements in DESIGN.md
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  DG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KS, KSTEPS, RES, EPI>, tm, a, g));
   DG_LAUNCH_CHECK();
   return 0;
 }
