@@ -244,7 +244,7 @@ def run_gpu(args, w, rank, world, local_rank):
     roof = None
     if rank == 0:
         L = _lib.lib()
-        ncls = 4
+        ncls = 7  # 0 tc3x3, 1 tc5x5, 2 tc 1x1 / transposed, 3 simt, 4-5 weight gradients, 6 tc conv + fused max-pool
         arr_ms, arr_fl, arr_by = (C.c_double * ncls)(), (C.c_double * ncls)(), (C.c_double * ncls)()
         arr_n = (C.c_longlong * ncls)()
         L.depgan_profile_begin()
@@ -268,7 +268,13 @@ def run_gpu(args, w, rank, world, local_rank):
                     "hbm_frac_same_kernel": arr_by[k] / (arr_ms[k] * 1e-3) / 1e9 / pk["hbm"], "hbm_peak": pk["hbm"],
                     "share_of_conv_time": conv_share,
                     "other_classes_ms_per_step": {"tc5x5": arr_ms[1] / psteps, "tc_deconv": arr_ms[2] / psteps,
-                                                  "simt": arr_ms[3] / psteps, "tc3x3": arr_ms[0] / psteps}}
+                                                  "simt": arr_ms[3] / psteps, "tc3x3": arr_ms[0] / psteps,
+                                                  "tc3x3_fused_maxpool": arr_ms[6] / psteps},
+                    # every 3x3 launch, the ones with the fused 2x2 max-pool epilogue (conv_tc_kernel<3,*,*,4>) included
+                    "all_3x3_launches": {"launches_per_step": (arr_n[0] + arr_n[6]) // psteps,
+                                         "achieved": (arr_fl[0] + arr_fl[6]) / ((arr_ms[0] + arr_ms[6]) * 1e-3) / 1e12,
+                                         "frac": (arr_fl[0] + arr_fl[6]) / ((arr_ms[0] + arr_ms[6]) * 1e-3) / 1e12
+                                                 / pk["tf_sust"]}}
         prof_path = ROOT / "profiles" / "ncu_traffic_r01.json"
         if roof and prof_path.exists():
             try:
@@ -365,13 +371,13 @@ def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"
     if rank == 0 and os.environ.get("DEPGAN_PROFILE_LOG"):
         from depgan_b200 import _lib
         L = _lib.lib()
-        ncls = 6
+        ncls = 7
         a_ms, a_fl, a_by = (C.c_double * ncls)(), (C.c_double * ncls)(), (C.c_double * ncls)()
         a_n = (C.c_longlong * ncls)()
         L.depgan_profile_begin()
         step(0)
         _lib.check(L.depgan_profile_end(a_ms, a_fl, a_by, a_n, ncls), "profile_end")
-        names = ["tc3x3", "tc5x5", "tc1x1_deconv", "simt_conv", "simt_wgrad", "tc_wgrad"]
+        names = ["tc3x3", "tc5x5", "tc1x1_deconv", "simt_conv", "simt_wgrad", "tc_wgrad", "tc_conv_fused_maxpool"]
         prof = {nm: {"ms": a_ms[i], "launches": int(a_n[i]),
                      "tflops": (a_fl[i] / (a_ms[i] * 1e-3) / 1e12) if a_ms[i] > 0 else None}
                 for i, nm in enumerate(names)}
