@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -32,6 +33,33 @@ extern long long g_launch_count;
       return -1;                                                                                         \
     }                                                                                                    \
   } while (0)
+
+// Programmatic dependent launch (sm_90+): a kernel launched through dg_launch_pdl may be scheduled while its stream
+// predecessor is still draining; DG_PDL_ENTER() at the top of the kernel (before any access to global memory) lets
+// the next launch do the same and then waits for the predecessor to complete and flush.  Both instructions are no-ops
+// for an ordinary <<<>>> launch.  DEPGAN_NO_PDL=1 turns the attribute off (A/B measurements).
+#define DG_PDL_ENTER()                                                    \
+  do {                                                                    \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");       \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                    \
+  } while (0)
+#ifdef __CUDACC__
+template <typename K, typename... Args>
+inline cudaError_t dg_launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  static const bool pdl = getenv("DEPGAN_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#endif
 
 #define DG_REQUIRE(cond, msg)                                        \
   do {                                                               \

@@ -849,18 +849,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // ---- instantiation helpers used by conv_tc_k{1,3,5}.cu ----
 template <int KS, int KSTEPS, bool RES, int EPI>
 int launch_one(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g) {
-  static const bool pdl = getenv("DEPGAN_NO_PDL") == nullptr;  // A/B switch for the measurements in DESIGN.md
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(TC_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
-  DG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<KS, KSTEPS, RES, EPI>, tm, a, g));
+  DG_CHECK_CUDA(dg_launch_pdl(conv_tc_kernel<KS, KSTEPS, RES, EPI>, dim3(grid), dim3(TC_THREADS), smem, st, tm, a, g));
   DG_LAUNCH_CHECK();
   return 0;
 }
