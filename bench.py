@@ -98,10 +98,16 @@ def make_inputs(w, n, seed):
     return x, synth.make_noise(n, seed=seed + 1)
 
 
-def make_weights(w):
+def make_weights(w, net=None):
+    """Seeded synthetic weights in the Keras layout.  The GPU arm takes names / shapes from the library's own manifest
+    (C ABI); only the CPU arms (cpu_baseline leg, --impl reference) read the oracle's."""
     from depgan_b200 import synth
-    from oracle import depgan_oracle as O  # manifest only (names/shapes), shared with the tests
-    return synth.init_weights(O.gen_manifest(w["nicg"], w["nc_out"]), seed=0, trained_like=True)
+    if net is not None:
+        man = [(n.split("/")[0], n.split("/")[1], s) for n, s, _, _ in net.manifest]
+    else:
+        from oracle import depgan_oracle as O
+        man = O.gen_manifest(w["nicg"], w["nc_out"])
+    return synth.init_weights(man, seed=0, trained_like=True)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -168,9 +174,9 @@ def run_gpu(args, w, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or w["batch"]
-    P = make_weights(w)
     g = Gen_UNet2D((256, 256, w["nicg"]), (32, 1), 32, w["nc_out"], precision=args.precision, max_batch=B,
                    device=str(dev))
+    P = make_weights(w, g)
     # weights travel through the Keras-h5 layout, as load_weights would read the shipped files
     h5 = Path("/tmp/depgan_bench_rank%d.h5" % rank)
     from depgan_b200 import h5lite

@@ -7,12 +7,12 @@ import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 from depgan_b200 import Gen_UNet2D, synth  # noqa: E402
-from oracle import depgan_oracle as O  # noqa: E402
 
 B, steps = 64, 40
 dev = torch.device("cuda:0")
 g = Gen_UNet2D((256, 256, 1), (32, 1), 32, 4, precision="bf16", max_batch=B, device=str(dev))
-g.set_weights(synth.init_weights(O.gen_manifest(1, 4), seed=0, trained_like=True))
+g.set_weights(synth.init_weights([(n.split("/")[0], n.split("/")[1], s) for n, s, _, _ in g.manifest], seed=0,
+                                 trained_like=True))
 xh = torch.from_numpy(synth.make_flair(B, 256, 256, seed=1)[0]).pin_memory()
 zh = torch.from_numpy(synth.make_noise(B, seed=2)).pin_memory()
 ohs = [torch.empty((B, 256, 256, 4), dtype=torch.float32).pin_memory() for _ in range(2)]

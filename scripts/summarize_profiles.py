@@ -1,4 +1,4 @@
-"""Turns the raw ncu exports under gpurun_out/ into the small tracked summaries under profiles/ (round 1, build v16)."""
+"""Turns the raw ncu exports under gpurun_out/ into the small tracked summaries under profiles/ (round 1, final build; the v16 files of the same names were produced by an earlier revision of this script)."""
 import collections
 import csv
 import json
@@ -63,10 +63,12 @@ def full_summary(src, dst, traffic_json, batch, bench_batch, alg_bytes_b16):
 
 
 if __name__ == "__main__":
-    t = launch_table(SRC / "infer_launches_b64.csv", OUT / "r01_v16_infer_launches_b64.csv")
+    # final build of round 1 (programmatic dependent launch): launch list and --set full, both at the bench batch of 64
+    t = launch_table(SRC / "infer_launches_b64_final.csv", OUT / "r01_final_infer_launches_b64.csv")
     print("inference forward b64: %.1f us over all launches (cold, serialised)" % t)
     if (SRC / "train_launches_v25.csv").exists():
         t = launch_table(SRC / "train_launches_v25.csv", OUT / "r01_final_train_launches_b32.csv")
         print("train iteration b32: %.1f us" % t)
-    full_summary(SRC / "infer_conv_tc_full_raw_b16.csv", OUT / "r01_v16_conv_tc_ncu_full_summary_b16.csv",
-                 OUT / "ncu_traffic_r01.json", 16, 64, 2230382600.0)
+    # algorithmic bytes of the 20 3x3 launches: 2 230 382 600 at batch 16 x 4
+    full_summary(SRC / "infer_conv_tc_full_raw_b64.csv", OUT / "r01_final_conv_tc_ncu_full_summary_b64.csv",
+                 OUT / "ncu_traffic_r01.json", 64, 64, 4 * 2230382600.0)
