@@ -146,7 +146,7 @@ long long depgan_launch_count(void);
 /* Per-launch device timing of the convolution kernels (bench.py roofline leg): between begin and end every
  * convolution launch is bracketed by CUDA events on its stream.  Classes: 0 = tcgen05 3x3, 1 = tcgen05 5x5,
  * 2 = tcgen05 1x1 / transposed conv, 3 = fp32 CUDA-core conv, 4 = CUDA-core weight gradient, 5 = tcgen05 weight
- * gradient.  flops/bytes are the algorithmic figures of
+ * gradient, 6 = tcgen05 conv with the fused 2x2 max-pool epilogue.  flops/bytes are the algorithmic figures of
  * DESIGN.md (2*k*k*Cin*Cout per pixel; activation bytes read + written once). */
 int depgan_profile_begin(void);
 int depgan_profile_end(double* ms_by_class, double* flops_by_class, double* bytes_by_class,
