@@ -275,16 +275,40 @@ __global__ void __launch_bounds__(256, 2) conv_first_kernel(const float* __restr
       if (r < rows) {
         tile.row(r + KS - 1, col, win[(k + KS - 1) % KS]);
         float acc[CPT];
+        if constexpr (CPT % 2 == 0) {
+          // packed fp32x2 FMAs (one issue slot per two channels; per-lane IEEE fma, so the bits are those of fmaf)
+          unsigned long long a2[CPT / 2];
 #pragma unroll
-        for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
+          for (int c = 0; c < CPT / 2; ++c) a2[c] = 0ull;
 #pragma unroll
-        for (int dy = 0; dy < KS; ++dy)
+          for (int dy = 0; dy < KS; ++dy)
 #pragma unroll
-          for (int q = 0; q < KW; ++q) {
-            const float v = win[(k + dy) % KS][q];
+            for (int q = 0; q < KW; ++q) {
+              const float v = win[(k + dy) % KS][q];
+              unsigned long long v2;
+              asm("mov.b64 %0, {%1, %1};" : "=l"(v2) : "f"(v));
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) acc[c] = fmaf(v, wr[dy * KW + q][c], acc[c]);
-          }
+              for (int c = 0; c < CPT / 2; ++c) {
+                unsigned long long w2;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(w2) : "f"(wr[dy * KW + q][2 * c]), "f"(wr[dy * KW + q][2 * c + 1]));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a2[c]) : "l"(v2), "l"(w2));
+              }
+            }
+#pragma unroll
+          for (int c = 0; c < CPT / 2; ++c)
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(acc[2 * c]), "=f"(acc[2 * c + 1]) : "l"(a2[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) acc[c] = 0.f;
+#pragma unroll
+          for (int dy = 0; dy < KS; ++dy)
+#pragma unroll
+            for (int q = 0; q < KW; ++q) {
+              const float v = win[(k + dy) % KS][q];
+#pragma unroll
+              for (int c = 0; c < CPT; ++c) acc[c] = fmaf(v, wr[dy * KW + q][c], acc[c]);
+            }
+        }
         const size_t o = (((size_t)n * H + y0 + r) * W + xc) * COUT + c0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
