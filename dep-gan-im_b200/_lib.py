@@ -67,6 +67,7 @@ SIGNATURES = {
     "depgan_profile_end": (_I, [_P, _P, _P, _P, _I]),
     "depgan_debug_activation": (_I, [_P, C.c_char_p, _P, _LL, C.POINTER(_LL), _I, _P]),
     "depgan_op_conv2d": (_I, [C.POINTER(ConvDesc), _P]),
+    "depgan_op_conv_plan": (_I, [C.POINTER(ConvDesc), _P]),
     "depgan_op_wgrad": (_I, [_P, _P, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "depgan_op_wgrad_csum": (_I, [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "depgan_op_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -195,6 +195,16 @@ bool conv_tc_supported(const ConvArgs& a) {
   return plan(a, &g, &smem);
 }
 
+bool conv_tc_plan_query(const ConvArgs& a, int* o) {
+  TcGeom g;
+  uint32_t smem;
+  if (!conv_tc_supported(a) || !plan(a, &g, &smem)) return false;
+  const int v[16] = {g.kc, g.ncta, g.nchunk0 + g.nchunk1, g.na, g.nb, g.b_tps, g.b_resident, g.acc_stages, g.n_issuers,
+                     g.ch, g.n_side, g.tmem_cols, (int)smem, g.pool, g.stage_out, g.ncols_total / g.ncta};
+  for (int i = 0; i < 16; ++i) o[i] = v[i];
+  return true;
+}
+
 int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   if (a.N <= 0) return 0;
   DG_TRY(conv_tc_init());

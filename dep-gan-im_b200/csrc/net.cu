@@ -658,8 +658,7 @@ int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, lon
 }
 
 // Kernel-level entry point (tests / micro-benchmarks): one fused convolution on caller-owned buffers.
-int depgan_op_conv2d(const depgan_conv_desc* d, void* stream) {
-  DG_REQUIRE(d != nullptr, "op_conv2d: null descriptor");
+static ConvArgs conv_args_of(const depgan_conv_desc* d) {
   ConvArgs a{};
   a.in0 = d->in0; a.in1 = d->in1; a.C0 = d->C0; a.C1 = d->C1;
   a.w = d->w_f32; a.w_tc = (const bf16*)d->w_bf16;
@@ -671,6 +670,17 @@ int depgan_op_conv2d(const depgan_conv_desc* d, void* stream) {
   a.N = d->N; a.H = d->H; a.W = d->W; a.Cout = d->Cout; a.ks = d->ks;
   a.in_dt = d->in_bf16 ? DT_BF16 : DT_F32; a.out_dt = d->out_bf16 ? DT_BF16 : DT_F32;
   a.pool_out = d->pool_out;
+  return a;
+}
+
+int depgan_op_conv_plan(const depgan_conv_desc* d, int* plan16) {
+  DG_REQUIRE(d != nullptr && plan16 != nullptr, "op_conv_plan: null argument");
+  return conv_tc_plan_query(conv_args_of(d), plan16) ? 1 : 0;
+}
+
+int depgan_op_conv2d(const depgan_conv_desc* d, void* stream) {
+  DG_REQUIRE(d != nullptr, "op_conv2d: null descriptor");
+  ConvArgs a = conv_args_of(d);
   DG_REQUIRE(!a.pool_out || d->use_tc, "op_conv2d: pool_out is an epilogue of the tcgen05 path");
   if (d->use_tc) {
     DG_REQUIRE(conv_tc_supported(a), "op_conv2d: shape not supported by the tcgen05 path");

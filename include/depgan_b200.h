@@ -178,6 +178,11 @@ typedef struct depgan_conv_desc {
   void* pool_out; /* optional (N,H/2,W/2,Cout), tcgen05 path: 2x2 stride-2 max-pool of `out`, fused into the epilogue */
 } depgan_conv_desc;
 int depgan_op_conv2d(const depgan_conv_desc* d, void* stream);
+/* Host-only query of the tcgen05 convolution planner for the layer `d` describes (pointers are only tested for NULL,
+ * nothing is launched; works without a GPU).  Returns 1 and fills plan16 when the tcgen05 path takes the layer, 0 when
+ * it does not, <0 on bad arguments.  plan16 = { kc, ncta, nchunks, na, nb, b_tps, b_resident, acc_stages, n_issuers,
+ * ch, n_side, tmem_cols, smem_bytes, pool, stage_out, nsplit } (shared-memory ring / TMEM geometry). */
+int depgan_op_conv_plan(const depgan_conv_desc* d, int* plan16);
 /* Weight gradient of one convolution: dw[tap][Cin][Cout] (fp32, Keras HWIO order) += sum_p x[p+off(tap)] (x) dy[p].
  * use_tc=1: tcgen05 path (x, dy bf16); use_tc=0: fp32 CUDA-core path (x, dy float32); use_tc=2: CUDA-core path with
  * x float32 and dy bf16 (the first layer of a bf16 network).  The caller zeroes dw. */
