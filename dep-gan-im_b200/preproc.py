@@ -11,34 +11,47 @@ __all__ = ["data_prep", "data_prep_save", "map_image_to_intensity_range", "prepa
 
 
 def data_prep(image):
-    """(X, Y, Z) volume -> (Z, X, Y, 1) float32 stack of axial slices (TG:105-119: ``image[:, :, z]`` per slice, channel
-    axis appended).  Accepts the array or an object with an ``image`` attribute (``load_data`` / ``NiftiImage``)."""
-    image = getattr(image, "image", image)
-    images = np.array([image[:, :, z] for z in range(image.shape[2])], dtype="float32")
-    return np.expand_dims(images, axis=3)
+    """(X, Y, Z) volume -> (Z, X, Y, 1) float32 stack of axial slices (the reference's ``data_prep``, TG:105-119: slice
+    z of the stack is ``image[:, :, z]``, with a trailing channel axis).  Accepts the array or an object with an
+    ``image`` attribute (``load_data`` / ``NiftiImage``)."""
+    vol = np.asarray(getattr(image, "image", image))
+    if vol.ndim != 3:
+        raise ValueError("data_prep expects an (X, Y, Z) volume, got shape %s" % (vol.shape,))
+    return np.ascontiguousarray(np.moveaxis(vol, 2, 0), dtype=np.float32)[..., np.newaxis]
 
 
 def data_prep_save(image_data):
-    """Inverse of :func:`data_prep` applied before ``nib.save`` (TG:121-128): squeeze, swap axes 0 and 2, rotate by
-    90 degrees, flip the first axis -- (Z, X, Y[, 1]) back to (X, Y, Z)."""
-    image_data = np.squeeze(image_data)
-    output_img = np.swapaxes(image_data, 0, 2)
-    output_img = np.rot90(output_img)
-    return output_img[::-1, ...]
+    """Inverse of :func:`data_prep`, applied before a prediction is saved (the reference's ``data_prep_save``,
+    TG:121-128, whose squeeze / swapaxes(0, 2) / rot90 / flip sequence composes to exactly this axis move):
+    (Z, X, Y[, 1]) -> (X, Y, Z) with ``out[x, y, z] = in[z, x, y]``."""
+    stack = np.squeeze(np.asarray(image_data))
+    if stack.ndim != 3:
+        raise ValueError("data_prep_save expects a (Z, X, Y[, 1]) stack, got shape %s" % (np.shape(image_data),))
+    return np.moveaxis(stack, 0, 2)
 
 
 def map_image_to_intensity_range(image, min_o, max_o, percentiles=0):
-    """Linear map of [percentile(p), percentile(100 - p)] onto [min_o, max_o], clipped (TG:131-149)."""
-    if image.dtype in [np.uint8, np.uint16, np.uint32]:
-        assert min_o >= 0, 'Input image type is uintXX but you selected a negative min_o: %f' % min_o
-    if image.dtype == np.uint8:
-        assert max_o <= 255, 'Input image type is uint8 but you selected a max_o > 255: %f' % max_o
-    min_i = np.percentile(image, 0 + percentiles)
-    max_i = np.percentile(image, 100 - percentiles)
-    image = (np.divide((image - min_i), max_i - min_i) * (max_o - min_o) + min_o).copy()
-    image[image > max_o] = max_o
-    image[image < min_o] = min_o
-    return image
+    """Affine intensity normalisation used for the FLAIR channel (the reference's ``map_image_to_intensity_range``,
+    TG:131-149): the ``percentiles``-th and ``(100 - percentiles)``-th percentiles of ``image`` are sent to ``min_o`` and
+    ``max_o`` and everything outside is clamped.  ``percentiles == 0`` is plain min-max scaling.
+
+    Floating-point images keep their dtype (the reference ran NumPy 1.x, where the float64 percentile scalars do not
+    promote a float32 volume); integer images are computed in float64.  As in the reference, unsigned images reject a
+    target range they could not hold (AssertionError)."""
+    img = np.asarray(image)
+    if img.dtype.kind == "u" and img.dtype.itemsize <= 4:
+        if min_o < 0:
+            raise AssertionError("unsigned image (%s) cannot be mapped to a range starting at %g" % (img.dtype, min_o))
+        if img.dtype.itemsize == 1 and max_o > 255:
+            raise AssertionError("uint8 image cannot be mapped to a range ending at %g" % max_o)
+    work = img.dtype.type if img.dtype.kind == "f" else np.float64
+    lo, hi = work(np.percentile(img, percentiles)), work(np.percentile(img, 100 - percentiles))
+    with np.errstate(invalid="ignore", divide="ignore"):  # a constant image divides by zero, as in the reference
+        out = (img.astype(work, copy=True) - lo) / (hi - lo)
+    out *= work(max_o - min_o)
+    out += work(min_o)
+    np.clip(out, work(min_o), work(max_o), out=out)  # NaNs stay NaN, like the reference's two masked assignments
+    return out
 
 
 def _sq(v):

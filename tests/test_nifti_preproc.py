@@ -83,6 +83,63 @@ def test_map_image_to_intensity_range():
     assert out.min() == 0.0 and out.max() == 1.0 and np.isclose(out[50], 0.5)
 
 
+def _ref_save_axes(a):
+    """Test-side restatement of the reference's axis sequence before saving (TG:121-128)."""
+    a = np.swapaxes(np.squeeze(a), 0, 2)
+    return np.rot90(a)[::-1, ...]
+
+
+def _ref_intensity_map(image, min_o, max_o, p):
+    """Test-side restatement of TG:131-149 in the image's own float dtype (NumPy 1.x scalar casting)."""
+    t = image.dtype.type if image.dtype.kind == "f" else np.float64
+    lo, hi = t(np.percentile(image, p)), t(np.percentile(image, 100 - p))
+    out = (image.astype(t) - lo) / (hi - lo) * t(max_o - min_o) + t(min_o)
+    out[out > max_o] = max_o
+    out[out < min_o] = min_o
+    return out
+
+
+@pytest.mark.parametrize("shape", [(7, 5, 3), (16, 16, 4), (3, 9, 2)])
+def test_data_prep_save_equals_reference_axis_sequence(shape):
+    rng = np.random.default_rng(sum(shape))
+    stack = rng.random((shape[2], shape[0], shape[1], 1)).astype(np.float32)
+    got = preproc.data_prep_save(stack)
+    assert got.shape == shape and np.array_equal(got, _ref_save_axes(stack))
+    assert np.array_equal(preproc.data_prep(got), stack)              # and it inverts data_prep exactly
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint8, np.int16])
+@pytest.mark.parametrize("rng_out,p", [((0, 1), 0), ((-1, 1), 0), ((0, 255), 2), ((0.5, 2.5), 10)])
+def test_map_image_to_intensity_range_matches_formula(dtype, rng_out, p):
+    rng = np.random.default_rng(11)
+    img = (rng.random((9, 8, 5)) * 200).astype(dtype)
+    if np.dtype(dtype).kind == "u" and rng_out[0] < 0:
+        with pytest.raises(AssertionError):
+            preproc.map_image_to_intensity_range(img, rng_out[0], rng_out[1], p)
+        return
+    got = preproc.map_image_to_intensity_range(img, rng_out[0], rng_out[1], p)
+    want = _ref_intensity_map(img, rng_out[0], rng_out[1], p)
+    assert got.dtype == want.dtype and got.shape == img.shape
+    assert np.array_equal(got, want)
+    assert got.min() >= rng_out[0] and got.max() <= rng_out[1]
+    if p == 0:                                                          # min-max scaling reaches both ends
+        assert got.min() == rng_out[0] and np.isclose(got.max(), rng_out[1])
+    # monotone: the map never swaps the order of two voxels
+    order = np.argsort(img.reshape(-1), kind="stable")
+    assert np.all(np.diff(got.reshape(-1)[order]) >= 0)
+
+
+def test_map_image_to_intensity_range_edge_cases():
+    with pytest.raises(AssertionError):
+        preproc.map_image_to_intensity_range(np.zeros((2, 2), np.uint8), 0, 300)
+    img = np.full((3, 3), 7.0, np.float32)                              # constant image: 0/0, NaN like the reference
+    assert np.isnan(preproc.map_image_to_intensity_range(img, 0, 1)).all()
+    src = np.arange(6, dtype=np.float32).reshape(2, 3)
+    keep = src.copy()
+    preproc.map_image_to_intensity_range(src, 0, 1)
+    assert np.array_equal(src, keep)                                    # the input is not modified
+
+
 def test_prepare_subject_dem_and_uresnet():
     rng = np.random.default_rng(2)
     X, Y, Z = 8, 8, 3
