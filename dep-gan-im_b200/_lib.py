@@ -72,6 +72,7 @@ SIGNATURES = {
     "depgan_op_wgrad_csum": (_I, [_P, _P, _I, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "depgan_op_pack_weights": (_I, [_P, _P, _I, _I, _I, _P]),
     "depgan_op_f32_to_bf16": (_I, [_P, _P, _LL, _P]),
+    "depgan_op_f32_to_f16": (_I, [_P, _P, _LL, _P]),
     "depgan_op_bf16_to_f32": (_I, [_P, _P, _LL, _P]),
 }
 

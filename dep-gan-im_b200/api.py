@@ -28,6 +28,14 @@ def _torch():
     return torch
 
 
+def _warn_once(obj, key, msg):
+    import warnings
+    seen = obj.__dict__.setdefault("_warned", set())
+    if key not in seen:
+        seen.add(key)
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
+
 def _stream(torch):
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -290,12 +298,23 @@ class Gen_UNet2D(_Net):
             tot, cnt = 0.0, 0
             for i in range(0, n, bs):
                 idx = order[i:i + bs]
+                if dp is not None and len(idx) % world:
+                    # remainder batch under data parallelism: every rank needs the same number of rows for the
+                    # synchronised statistics, so the tail that does not divide evenly is left out (at most
+                    # world - 1 samples per epoch); Keras on one device trains on all of them
+                    cut = len(idx) - len(idx) % world
+                    _warn_once(self, "fit_dp_tail", "fit: %d sample(s) of the last batch dropped per epoch (batch not "
+                               "divisible by the %d data-parallel ranks)" % (len(idx) - cut, world))
+                    idx = idx[:cut]
                 if len(idx) < 2 * world:
-                    continue  # batch statistics need at least two samples (per rank)
+                    # training-phase BatchNorm cannot normalise a single sample per rank (its variance is 0): the one
+                    # deviation from Keras Model.fit, which would train on it
+                    if len(idx):
+                        _warn_once(self, "fit_single", "fit: a final batch of %d sample(s) is skipped (batch "
+                                   "statistics need two samples per rank)" % len(idx))
+                    continue
                 keep = (rng.uniform(size=(len(idx), self.cfg.H // 4, self.cfg.W // 4, 96)) >= 0.25).astype(np.uint8)
                 if dp is not None:  # every rank draws the same global batch and mask and takes its contiguous shard
-                    if len(idx) % world:
-                        continue
                     per = len(idx) // world
                     if per > self.cfg.max_batch:
                         raise ValueError("batch_size / world exceeds max_batch")
@@ -317,35 +336,49 @@ class Gen_UNet2D(_Net):
         h.history = hist
         return h
 
-    def predict(self, inputs, batch_size=32, verbose=0):
-        """Keras ``model.predict([x, z])`` (EG:621, EU:558): numpy in, numpy float32 out, inference mode."""
+    def cast_output(self, src, dst):
+        """float32 CUDA tensor -> float16 / bfloat16 CUDA tensor of the same shape on the current stream (our cast
+        kernel; the opt-in narrow ``predict`` output)."""
+        torch = self._torch
+        if src.dtype != torch.float32 or src.numel() != dst.numel() or not (src.is_contiguous() and dst.is_contiguous()):
+            raise ValueError("cast_output needs contiguous tensors of equal size, float32 source")
+        L = _lib.lib()
+        fn = {torch.bfloat16: L.depgan_op_f32_to_bf16, torch.float16: L.depgan_op_f32_to_f16}.get(dst.dtype)
+        if fn is None:
+            raise ValueError("cast_output: destination must be float16 or bfloat16")
+        with torch.cuda.device(self.device):
+            _lib.check(fn(src.data_ptr(), dst.data_ptr(), src.numel(), _stream(torch)), "cast_output")
+        return dst
+
+    def predict(self, inputs, batch_size=32, verbose=0, out_dtype=None):
+        """Keras ``model.predict([x, z])`` (EG:621, EU:558): numpy in, numpy float32 out, inference mode.
+
+        Batches of ``batch_size`` (clamped to ``max_batch``) run through a persistent :class:`InferencePipeline` with
+        pinned staging buffers owned by the model: no per-call pinning, copies overlap the kernels, and results do not
+        depend on the batching (slices are independent in inference mode).  ``out_dtype=np.float16`` is an opt-in
+        extension: the maps cross PCIe as float16 (half the device->host bytes) and are returned as float16."""
         torch = self._torch
         x, z = inputs
         x = np.ascontiguousarray(x, np.float32)
         z = np.ascontiguousarray(z, np.float32)
         if x.shape[0] != z.shape[0]:
             raise ValueError("x and z must have the same number of samples")
+        if tuple(x.shape[1:]) != self.input_shape or tuple(z.shape[1:]) != self.noiseZ_shape:
+            raise ValueError("bad input shapes %s %s" % (x.shape, z.shape))
         n = x.shape[0]
         bs = max(1, min(int(batch_size), self.cfg.max_batch))
-        out = np.empty((n, self.cfg.H, self.cfg.W, self.nc_out), np.float32)
-        if n > bs:  # several batches: overlap copies and kernels (results are identical, per-slice independent)
-            if getattr(self, "_pipe", None) is None:
-                self._pipe = InferencePipeline(self)
-            outs = []
-            for i in range(0, n, bs):
-                xh = torch.from_numpy(x[i:i + bs]).pin_memory()
-                zh = torch.from_numpy(z[i:i + bs]).pin_memory()
-                oh = torch.empty((xh.shape[0], self.cfg.H, self.cfg.W, self.nc_out), dtype=torch.float32).pin_memory()
-                self._pipe.submit(xh, zh, oh)
-                outs.append((i, oh))
-            self._pipe.flush()
-            for i, oh in outs:
-                out[i:i + oh.shape[0]] = oh.numpy()
-            return out
+        np_dt = np.dtype(out_dtype or np.float32)
+        if np_dt not in (np.dtype(np.float32), np.dtype(np.float16)):
+            raise ValueError("out_dtype must be float32 or float16")
+        t_dt = torch.float32 if np_dt == np.float32 else torch.float16
+        pipes = self.__dict__.setdefault("_pipes", {})
+        pipe = pipes.get(t_dt)
+        if pipe is None:
+            pipe = pipes[t_dt] = InferencePipeline(self, depth=2, out_dtype=t_dt, staging=True)
+        out = np.empty((n, self.cfg.H, self.cfg.W, self.nc_out), np_dt)
         for i in range(0, n, bs):
-            xb = torch.from_numpy(x[i:i + bs]).to(self.device, non_blocking=False)
-            zb = torch.from_numpy(z[i:i + bs]).to(self.device, non_blocking=False)
-            out[i:i + bs] = self.forward_device(xb, zb).cpu().numpy()
+            pipe.submit_numpy(x[i:i + bs], z[i:i + bs], out[i:i + bs])
+        pipe.flush()
         return out
 
 
@@ -358,28 +391,66 @@ class InferencePipeline:
         for xh, zh, oh in batches:            # pinned host tensors; oh receives the prediction
             pipe.submit(xh, zh, oh)
         pipe.flush()                          # all outputs are complete in host memory
-    """
 
-    def __init__(self, net, depth=2):
+    The pipeline's streams are ordered after whatever the caller's current stream had enqueued at the first
+    ``submit`` of a cycle (``load_weights`` / ``set_weights`` / ``adam_step`` re-pack the weights there), and
+    ``flush`` makes the caller's stream wait for the last copy.
+
+    ``out_dtype``: ``torch.float32`` (the Keras ``predict`` contract) or ``torch.float16`` / ``torch.bfloat16`` -- an
+    opt-in narrower device->host transfer (the network output is converted on the device by our cast kernel; half the
+    PCIe bytes per slice).  ``staging=True`` adds persistent pinned host buffers so that pageable NumPy arrays can be
+    fed with ``submit_numpy`` without a ``pin_memory()`` allocation per batch."""
+
+    def __init__(self, net, depth=2, out_dtype=None, staging=False):
         torch = net._torch
         self.net, self.torch, self.depth = net, torch, depth
         dev, cfg = net.device, net.cfg
         B = cfg.max_batch
+        self.out_dtype = out_dtype or torch.float32
+        if self.out_dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise ValueError("out_dtype must be float32, float16 or bfloat16")
         with torch.cuda.device(dev):
             self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
             self.x = [torch.empty((B, cfg.H, cfg.W, cfg.nicg), dtype=torch.float32, device=dev) for _ in range(depth)]
             self.z = [torch.empty((B, cfg.noise_len, 1), dtype=torch.float32, device=dev) for _ in range(depth)]
             self.o = [torch.empty((B, cfg.H, cfg.W, net.nc_out), dtype=torch.float32, device=dev) for _ in range(depth)]
+            self.o_lp = None
+            if self.out_dtype != torch.float32:
+                self.o_lp = [torch.empty((B, cfg.H, cfg.W, net.nc_out), dtype=self.out_dtype, device=dev)
+                             for _ in range(depth)]
             self.ev_in = [torch.cuda.Event() for _ in range(depth)]
             self.ev_run = [torch.cuda.Event() for _ in range(depth)]
             self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_entry = torch.cuda.Event()
         self.i = 0
+        self._open = False  # a submit/flush cycle is in progress
+        self.hx = self.hz = self.ho = None
+        if staging:
+            self.hx = [torch.empty((B, cfg.H, cfg.W, cfg.nicg), dtype=torch.float32).pin_memory() for _ in range(depth)]
+            self.hz = [torch.empty((B, cfg.noise_len, 1), dtype=torch.float32).pin_memory() for _ in range(depth)]
+            self.ho = [torch.empty((B, cfg.H, cfg.W, net.nc_out), dtype=self.out_dtype).pin_memory()
+                       for _ in range(depth)]
+            self._pending = [None] * depth  # (destination numpy array, n) whose D2H copy into ho[k] is in flight
+
+    def _enter(self):
+        # first submit of a cycle: everything the caller's stream has enqueued so far (weight fold / pack kernels of
+        # depgan_net_prepare in particular) happens before the pipeline touches the network
+        if not self._open:
+            torch = self.torch
+            cur = torch.cuda.current_stream(self.net.device)
+            self.ev_entry.record(cur)
+            for s in (self.s_in, self.s_run, self.s_out):
+                s.wait_event(self.ev_entry)
+            self._open = True
 
     def submit(self, xh, zh, oh):
         torch = self.torch
         k = self.i % self.depth
         n = int(xh.shape[0])
+        if oh.dtype != self.out_dtype:
+            raise ValueError("output buffer dtype %s does not match the pipeline's %s" % (oh.dtype, self.out_dtype))
         with torch.cuda.device(self.net.device):
+            self._enter()
             with torch.cuda.stream(self.s_in):
                 if self.i >= self.depth:
                     self.s_in.wait_event(self.ev_run[k])   # the kernels that last read these input buffers
@@ -391,16 +462,57 @@ class InferencePipeline:
                 if self.i >= self.depth:
                     self.s_run.wait_event(self.ev_out[k])  # the D2H copy that last read this output buffer
                 self.net.forward_device(self.x[k][:n], self.z[k][:n], self.o[k][:n])
+                src = self.o[k]
+                if self.o_lp is not None:                  # opt-in narrow output: converted on the device
+                    self.net.cast_output(self.o[k][:n], self.o_lp[k][:n])
+                    src = self.o_lp[k]
                 self.ev_run[k].record(self.s_run)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_run[k])
-                oh.copy_(self.o[k][:n], non_blocking=True)
+                oh.copy_(src[:n], non_blocking=True)
                 self.ev_out[k].record(self.s_out)
         self.i += 1
 
+    def _drain(self, k):
+        """Persistent-staging mode: wait for the D2H copy into ho[k] and move it to its NumPy destination."""
+        if self._pending[k] is not None:
+            dst, n = self._pending[k]
+            self.ev_out[k].synchronize()
+            if self.out_dtype == self.torch.bfloat16:
+                dst[...] = self.ho[k][:n].float().numpy()
+            else:
+                np.copyto(dst, self.ho[k][:n].numpy(), casting="same_kind")
+            self._pending[k] = None
+
+    def submit_numpy(self, x, z, out):
+        """Pageable NumPy in / out through the persistent pinned staging buffers (``staging=True``): ``x``/``z`` are
+        copied into pinned slot k (host memcpy), ``out`` (a NumPy view) is filled once the slot's D2H copy has
+        completed -- at the latest in ``flush``."""
+        if self.hx is None:
+            raise RuntimeError("create the pipeline with staging=True to use submit_numpy")
+        k = self.i % self.depth
+        n = int(x.shape[0])
+        self._drain(k)                    # the slot's previous result must have left ho[k]
+        if self.i >= self.depth:
+            self.ev_in[k].synchronize()   # the H2D copy that last read hx[k] / hz[k]
+        self.hx[k][:n].numpy()[...] = x
+        self.hz[k][:n].numpy()[...] = z
+        self.submit(self.hx[k][:n], self.hz[k][:n], self.ho[k][:n])
+        self._pending[k] = (out, n)
+
     def flush(self):
+        torch = self.torch
         for s in (self.s_in, self.s_run, self.s_out):
             s.synchronize()
+        if self.hx is not None:
+            for k in range(self.depth):
+                self._drain(k)
+        # later work on the caller's stream (e.g. a weight update) is ordered after the pipeline's last kernel / copy
+        with torch.cuda.device(self.net.device):
+            cur = torch.cuda.current_stream(self.net.device)
+            cur.wait_stream(self.s_run)
+            cur.wait_stream(self.s_out)
+        self._open = False
 
 
 class Dis_C2D_FCN1(_Net):

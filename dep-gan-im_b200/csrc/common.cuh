@@ -75,6 +75,30 @@ inline cudaError_t dg_launch_pdl(K kern, dim3 grid, dim3 block, size_t smem, cud
     if (_r != 0) return _r;    \
   } while (0)
 
+// Per-device one-time set-up.  cudaFuncSetAttribute (shared-memory opt-in, carve-out) and the SM count belong to a
+// device, not to the process: a site keeps one DgPerDevice and runs its set-up once for every device it is called on.
+struct DgPerDevice {
+  unsigned long long done = 0;  // bit d: device d has been set up at this site
+  int sms[64] = {};
+  int val[64] = {};             // site-specific cached value (e.g. resident CTAs per SM)
+};
+// 0 on success; *dev = current device, *first = true when this site has not run its set-up on it yet (the caller
+// then does the set-up and calls dg_device_mark).  Devices >= 64 are always treated as "first" (never cached).
+inline int dg_device_enter(DgPerDevice& s, int* dev, bool* first) {
+  if (cudaGetDevice(dev) != cudaSuccess) { depgan_set_error("cudaGetDevice failed"); return -1; }
+  *first = *dev >= 64 || !((s.done >> *dev) & 1ull);
+  if (*first) {
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, *dev) != cudaSuccess) {
+      depgan_set_error("cudaDeviceGetAttribute(multiProcessorCount) failed");
+      return -1;
+    }
+    if (*dev < 64) s.sms[*dev] = n;
+  }
+  return 0;
+}
+inline void dg_device_mark(DgPerDevice& s, int dev) { if (dev < 64) s.done |= 1ull << dev; }
+
 enum DType { DT_F32 = 0, DT_BF16 = 1 };
 static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 

@@ -12,6 +12,7 @@
 #include <cuda.h>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -445,23 +446,30 @@ template <int KS, int CIN, int COUT>
 int launch_wgrad_first_tc(const WgradArgs& a, cudaStream_t st) {
   typedef FirstGeom<KS, CIN> GEO;
   constexpr uint32_t smem = 1024 + 256 * GEO::ROWB + 1024 + 256 * COUT * 2 + GEO::HT * GEO::HT * CIN * 4 + 16 + 32;
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_tc_kernel<KS, CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_tc_kernel<KS, CIN, COUT>,
-                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    cudaFuncAttributes fa;
-    DG_CHECK_CUDA(cudaFuncGetAttributes(&fa, wgrad_first_tc_kernel<KS, CIN, COUT>));
-    int occ = (int)((216u * 1024u) / (smem + 1024u));
-    const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * 256);
-    if (occ > by_regs) occ = by_regs;
-    if (occ > 8) occ = 8;
-    per_sm = occ < 1 ? 1 : occ;
+  static DgPerDevice site;  // function attributes and occupancy are set up once per device
+  static std::mutex mu;
+  int dev = 0, sms = 148, per_sm = 1;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    bool first = false;
+    DG_TRY(dg_device_enter(site, &dev, &first));
+    if (first) {
+      DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_tc_kernel<KS, CIN, COUT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_first_tc_kernel<KS, CIN, COUT>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      cudaFuncAttributes fa;
+      DG_CHECK_CUDA(cudaFuncGetAttributes(&fa, wgrad_first_tc_kernel<KS, CIN, COUT>));
+      int occ = (int)((216u * 1024u) / (smem + 1024u));
+      const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * 256);
+      if (occ > by_regs) occ = by_regs;
+      if (occ > 8) occ = 8;
+      if (dev < 64) site.val[dev] = occ < 1 ? 1 : occ;
+      dg_device_mark(site, dev);
+    }
+    if (dev < 64) { sms = site.sms[dev]; per_sm = site.val[dev]; }
+    else DG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  int dev = 0, sms = 148;
-  DG_CHECK_CUDA(cudaGetDevice(&dev));
-  DG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int n_tiles = (a.W / 16) * (a.H / 16) * a.N;
   const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
   wgrad_first_tc_kernel<KS, CIN, COUT><<<grid, 256, smem, st>>>((const float*)a.x0, (const bf16*)a.dy, a.dw, a.N, a.H,
@@ -477,24 +485,31 @@ int launch_first_tc(const ConvArgs& a, cudaStream_t st) {
   constexpr uint32_t smem = 1024 + A_BYTES + B_BYTES + (GEO::HT * GEO::HT * CIN + 2 * COUT) * 4 + 16 + 32;
   // several CTAs per SM overlap one tile's load / build / MMA / store phases; the grid must not exceed what is
   // resident at once (persistent loop), and TMEM gives each CTA 2*COUT of the SM's 512 columns
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    DG_CHECK_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<KS, CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    DG_CHECK_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<KS, CIN, COUT>,
-                                       cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    cudaFuncAttributes fa;
-    DG_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_first_tc_kernel<KS, CIN, COUT>));
-    int occ = (int)((216u * 1024u) / (smem + 1024u));          // shared memory (1 KB reserved per CTA)
-    const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * 256);
-    if (occ > by_regs) occ = by_regs;
-    if (occ > 512 / (2 * COUT)) occ = 512 / (2 * COUT);      // tensor memory columns
-    if (occ > 8) occ = 8;
-    per_sm = occ < 1 ? 1 : occ;
+  static DgPerDevice site;  // function attributes and occupancy are set up once per device
+  static std::mutex mu;
+  int dev = 0, sms = 148, per_sm = 1;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    bool first = false;
+    DG_TRY(dg_device_enter(site, &dev, &first));
+    if (first) {
+      DG_CHECK_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<KS, CIN, COUT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DG_CHECK_CUDA(cudaFuncSetAttribute(conv_first_tc_kernel<KS, CIN, COUT>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      cudaFuncAttributes fa;
+      DG_CHECK_CUDA(cudaFuncGetAttributes(&fa, conv_first_tc_kernel<KS, CIN, COUT>));
+      int occ = (int)((216u * 1024u) / (smem + 1024u));          // shared memory (1 KB reserved per CTA)
+      const int by_regs = 65536 / (((fa.numRegs + 7) / 8 * 8) * 256);
+      if (occ > by_regs) occ = by_regs;
+      if (occ > 512 / (2 * COUT)) occ = 512 / (2 * COUT);      // tensor memory columns
+      if (occ > 8) occ = 8;
+      if (dev < 64) site.val[dev] = occ < 1 ? 1 : occ;
+      dg_device_mark(site, dev);
+    }
+    if (dev < 64) { sms = site.sms[dev]; per_sm = site.val[dev]; }
+    else DG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  int dev = 0, sms = 148;
-  DG_CHECK_CUDA(cudaGetDevice(&dev));
-  DG_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int n_tiles = (a.W / 16) * (a.H / 16) * a.N;
   const int grid = n_tiles < sms * per_sm ? n_tiles : sms * per_sm;
   conv_first_tc_kernel<KS, CIN, COUT><<<grid, 256, smem, st>>>((const float*)a.in0, a.w, a.scale, a.shift, (bf16*)a.out,

@@ -2,6 +2,7 @@
 // maps and dispatch to the kernel instantiations of conv_tc_k{1,3,5}.cu.  The kernel itself is conv_tc_kernel.cuh.
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "conv_tc_kernel.cuh"
 
@@ -12,8 +13,9 @@ namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-int g_num_sms = 148;
+EncodeTiledFn g_encode = nullptr;   // driver entry point: process-global
+DgPerDevice g_dev;                  // shared-memory opt-in of every instantiation + SM count: per device
+thread_local int g_num_sms = 148;   // SM count of the device the last conv_tc_init() of this thread ran on
 
 CUtensorMapSwizzle swizzle_for(int kc) {  // kc bf16 channels = one swizzle span
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -156,21 +158,29 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
 }  // namespace
 
 int conv_tc_init() {
-  if (g_encode) return 0;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  DG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-  if (!fn || q != cudaDriverEntryPointSuccess) {
-    depgan_set_error("cuTensorMapEncodeTiled entry point not available");
-    return -1;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+      depgan_set_error("cuTensorMapEncodeTiled entry point not available");
+      return -1;
+    }
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   int dev = 0;
-  DG_CHECK_CUDA(cudaGetDevice(&dev));
-  DG_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  DG_TRY(set_attrs_ks1());
-  DG_TRY(set_attrs_ks3());
-  DG_TRY(set_attrs_ks5());
+  bool first = false;
+  DG_TRY(dg_device_enter(g_dev, &dev, &first));
+  if (first) {  // function attributes are per device: opt every instantiation in on each device we run on
+    DG_TRY(set_attrs_ks1());
+    DG_TRY(set_attrs_ks3());
+    DG_TRY(set_attrs_ks5());
+    dg_device_mark(g_dev, dev);
+  }
+  if (dev < 64) g_num_sms = g_dev.sms[dev];
+  else DG_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
   return 0;
 }
 

@@ -63,6 +63,7 @@ int k_uresnet_labels(const double* acc, double n_repeat, int chan, double* mean_
 int k_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t, float b1, float b2, float eps,
            float gscale, cudaStream_t st);
 
+int k_cast_narrow(const float* src, void* dst, long long n, int to_f16, cudaStream_t st);
 int k_copy_to_f32(const void* src, float* dst, long long n, int dt, cudaStream_t st);
 
 // ---- backward / loss kernels (kernels_bwd.cu) ------------------------------------------------------------

@@ -1,5 +1,7 @@
 // Forward-side non-convolution kernels: BN folding / weight packing, max-pool, k2s2 transposed conv,
 // 1x1 heads, the FiLM noise MLP, critic tail, inference accumulation and bit-exact DEM post-processing.
+#include <cuda_fp16.h>
+
 #include "kernels.cuh"
 
 namespace {
@@ -556,6 +558,47 @@ int k_convert_in(const float* src, void* dst, long long n, int dt, cudaStream_t 
   else
     convert_in_kernel<bf16><<<grid_for(n), 256, 0, st>>>(src, (bf16*)dst, n);
   DG_LAUNCH_CHECK();
+  return 0;
+}
+
+// float32 -> float16 / bfloat16, 8 elements (two 128-bit loads, one 128-bit store) per thread; the opt-in narrow
+// device->host output of predict().  HBM-bound: 4 B read + 2 B written per element.
+template <typename H2, typename CVT>
+__global__ void cast_narrow_kernel(const float* __restrict__ src, uint4* __restrict__ dst, long long n8, CVT cvt) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+  H2 h[4] = {cvt(a.x, a.y), cvt(a.z, a.w), cvt(b.x, b.y), cvt(b.z, b.w)};
+  dst[i] = *reinterpret_cast<uint4*>(h);
+}
+__global__ void cast_f16_tail_kernel(const float* src, __half* dst, long long from, long long n) {
+  const long long i = from + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
+}
+__global__ void cast_bf16_tail_kernel(const float* src, bf16* dst, long long from, long long n) {
+  const long long i = from + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+struct CvtF16 { __device__ __half2 operator()(float x, float y) const { return __floats2half2_rn(x, y); } };
+struct CvtBf16 { __device__ __nv_bfloat162 operator()(float x, float y) const { return __floats2bfloat162_rn(x, y); } };
+
+int k_cast_narrow(const float* src, void* dst, long long n, int to_f16, cudaStream_t st) {
+  if (n <= 0) return 0;
+  DG_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+             "cast_narrow: buffers must be 16-byte aligned");
+  const long long n8 = n / 8;
+  if (n8 > 0) {
+    const unsigned grid = (unsigned)((n8 + 255) / 256);
+    if (to_f16) cast_narrow_kernel<__half2><<<grid, 256, 0, st>>>(src, (uint4*)dst, n8, CvtF16());
+    else cast_narrow_kernel<__nv_bfloat162><<<grid, 256, 0, st>>>(src, (uint4*)dst, n8, CvtBf16());
+    DG_LAUNCH_CHECK();
+  }
+  if (n8 * 8 < n) {
+    if (to_f16) cast_f16_tail_kernel<<<1, 8, 0, st>>>(src, (__half*)dst, n8 * 8, n);
+    else cast_bf16_tail_kernel<<<1, 8, 0, st>>>(src, (bf16*)dst, n8 * 8, n);
+    DG_LAUNCH_CHECK();
+  }
   return 0;
 }
 

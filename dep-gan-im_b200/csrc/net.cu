@@ -11,6 +11,8 @@ long long g_launch_count = 0;
 static thread_local std::string g_err;
 void depgan_set_error(const std::string& msg) { g_err = msg; }
 
+depgan_net::~depgan_net() { delete tr; }  // the Train bookkeeping object of train_alloc(); device memory is the caller's
+
 // =========================================================================================================
 // manifest
 // =========================================================================================================
@@ -720,6 +722,9 @@ int depgan_op_pack_weights(const float* w_f32_dev, void* w_bf16_dev, int taps, i
 }
 int depgan_op_f32_to_bf16(const float* src_dev, void* dst_dev, long long n, void* stream) {
   return k_convert_in(src_dev, dst_dev, n, DT_BF16, (cudaStream_t)stream);
+}
+int depgan_op_f32_to_f16(const float* src_dev, void* dst_dev, long long n, void* stream) {
+  return k_cast_narrow(src_dev, dst_dev, n, 1, (cudaStream_t)stream);
 }
 int depgan_op_bf16_to_f32(const void* src_dev, float* dst_dev, long long n, void* stream) {
   return k_copy_to_f32(src_dev, dst_dev, n, DT_BF16, (cudaStream_t)stream);

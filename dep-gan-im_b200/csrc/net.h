@@ -100,8 +100,12 @@ struct depgan_net {
   void* c_pool[4] = {};   // pooled outputs (after convs 1,3,5,7)
   float* c_out = nullptr;  // (max_batch) critic scores
 
-  // ---- training scratch (net_train.cu) ----
+  // ---- training scratch (net_train.cu); owned by the handle ----
   struct Train* tr = nullptr;
+  depgan_net() = default;
+  depgan_net(const depgan_net&) = delete;
+  depgan_net& operator=(const depgan_net&) = delete;
+  ~depgan_net();  // net.cu (Train is complete there)
 
   int lvl_h(int lvl) const { return cfg.H >> lvl; }
   int lvl_w(int lvl) const { return cfg.W >> lvl; }

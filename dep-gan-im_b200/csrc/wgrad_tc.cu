@@ -20,6 +20,8 @@
 // ceil(ks / (128/C)) dx groups x (ks * nb) columns in TMEM.
 #include <cuda.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace {
@@ -27,8 +29,9 @@ namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode_w = nullptr;
-int g_sms_w = 148;
+EncodeTiledFn g_encode_w = nullptr;  // driver entry point: process-global
+DgPerDevice g_dev_w;                 // shared-memory opt-in + SM count: per device
+thread_local int g_sms_w = 148;      // SM count of the device of this thread's last wgrad_tc_init()
 
 constexpr int WG_THREADS = 192;  // warp 0 producer, warp 1 MMA, warps 2..5 final flush
 constexpr int R = 8;             // tile rows per stage (128 pixels)
@@ -377,24 +380,32 @@ bool wgrad_tc_supported(const WgradArgs& a) {
 }
 
 int wgrad_tc_init() {
-  if (g_encode_w) return 0;
-  void* fn = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  DG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-  if (!fn || q != cudaDriverEntryPointSuccess) {
-    depgan_set_error("cuTensorMapEncodeTiled entry point not available");
-    return -1;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!g_encode_w) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    DG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+      depgan_set_error("cuTensorMapEncodeTiled entry point not available");
+      return -1;
+    }
+    g_encode_w = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  g_encode_w = reinterpret_cast<EncodeTiledFn>(fn);
   int dev = 0;
-  DG_CHECK_CUDA(cudaGetDevice(&dev));
-  DG_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms_w, cudaDevAttrMultiProcessorCount, dev));
+  bool first = false;
+  DG_TRY(dg_device_enter(g_dev_w, &dev, &first));
+  if (first) {  // function attributes are per device
 #define DG_WG_ATTR(KS_, C_) \
   DG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<KS_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  DG_WG_ATTR(1, 16) DG_WG_ATTR(1, 32) DG_WG_ATTR(1, 64)
-  DG_WG_ATTR(3, 16) DG_WG_ATTR(3, 32) DG_WG_ATTR(3, 64)
-  DG_WG_ATTR(5, 16) DG_WG_ATTR(5, 32) DG_WG_ATTR(5, 64)
+    DG_WG_ATTR(1, 16) DG_WG_ATTR(1, 32) DG_WG_ATTR(1, 64)
+    DG_WG_ATTR(3, 16) DG_WG_ATTR(3, 32) DG_WG_ATTR(3, 64)
+    DG_WG_ATTR(5, 16) DG_WG_ATTR(5, 32) DG_WG_ATTR(5, 64)
 #undef DG_WG_ATTR
+    dg_device_mark(g_dev_w, dev);
+  }
+  if (dev < 64) g_sms_w = g_dev_w.sms[dev];
+  else DG_CHECK_CUDA(cudaDeviceGetAttribute(&g_sms_w, cudaDevAttrMultiProcessorCount, dev));
   return 0;
 }
 

@@ -15,10 +15,10 @@ import zlib
 
 import numpy as np
 
-from . import postproc
-from .api import _torch
+from . import _lib, postproc
+from .api import _stream, _torch
 
-__all__ = ["shard_range", "shard_items", "predict_subject_dem", "predict_subject_uresnet", "evaluate_subject",
+__all__ = ["shard_range", "shard_items", "SubjectEngine", "predict_subject_dem", "predict_subject_uresnet", "evaluate_subject",
            "save_subject_outputs", "cohort_sweep"]
 
 
@@ -50,50 +50,198 @@ def _forward_volume(net, xd, zd, out):
     return out
 
 
-def predict_subject_dem(netG, vol_1tp, mask_2tp, thr, n_repeat=10, seed=0, noises=None):
+class SubjectEngine:
+    """Per-GPU engine behind ``predict_subject_dem`` / ``predict_subject_uresnet`` / ``cohort_sweep``: the 10-repeat
+    loop of the testing scripts (EG:616-628, EU:553-564) and the post-processing (EG:673-741, EU:570, 597-600) for a
+    stream of subjects, double-buffered so that the upload of subject s+1 and the download of subject s-1 overlap the
+    kernels of subject s (three CUDA streams, pinned host staging, no per-subject allocation).
+
+    * Several noise repeats share one generator pass when they fit ``max_batch`` (the volume is replicated on the
+      device); the float64 accumulation still adds repeat 0, 1, 2, ... in order, so results are bit-identical to the
+      one-repeat-per-pass loop.
+    * ``outputs`` selects what travels back to the host: any of ``"dem"``, ``"fake2"`` (float64 (Z,H,W) maps),
+      ``"labels"`` (uint8) for DEP-GAN, ``"prob_mean"`` (float64 (Z,H,W,C)), ``"labels"`` for DEP-UResNet; the WMH voxel
+      count always does.  The testing scripts save all of them per subject; a sweep that only needs volumes / label
+      maps moves 64 KB instead of 1 MB+ per slice.
+    """
+
+    def __init__(self, net, kind="dem", z_max=48, n_repeat=10, outputs=None, depth=2):
+        torch = _torch()
+        self.torch, self.net, self.kind = torch, net, kind
+        if kind not in ("dem", "uresnet"):
+            raise ValueError("kind must be 'dem' or 'uresnet'")
+        all_out = ("dem", "fake2", "labels") if kind == "dem" else ("prob_mean", "labels")
+        self.outputs = tuple(all_out if outputs is None else outputs)
+        for o in self.outputs:
+            if o not in all_out:
+                raise ValueError("unknown output %r for kind %r" % (o, kind))
+        cfg, dev = net.cfg, net.device
+        self.dev, self.Z, self.R, self.depth = dev, int(z_max), int(n_repeat), int(depth)
+        H, W, nc = cfg.H, cfg.W, net.nc_out
+        self.rpp = max(1, min(self.R, cfg.max_batch // max(1, self.Z)))   # repeats per generator pass
+        self.rows = self.rpp * self.Z
+        mshape = (self.Z, H, W) if kind == "dem" else (self.Z, H, W, nc)
+        with torch.cuda.device(dev):
+            self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+            d = lambda shape, dt: [torch.empty(shape, dtype=dt, device=dev) for _ in range(depth)]  # noqa: E731
+            self.x = d((self.rows, H, W, cfg.nicg), torch.float32)
+            self.m = d((self.Z, H, W), torch.float32)
+            self.z = d((self.R * self.Z, cfg.noise_len, 1), torch.float32)
+            self.acc = d(mshape, torch.float64)
+            self.o_a = d(mshape, torch.float64)          # dem / prob_mean
+            self.o_b = d(mshape, torch.float64) if kind == "dem" else None   # fake2
+            self.lab = d((self.Z, H, W), torch.uint8)
+            self.cnt = d((1,), torch.int64)
+            self.out = torch.empty((self.rows, H, W, nc), dtype=torch.float32, device=dev)
+            self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+            self.ev_entry = torch.cuda.Event()
+        p = lambda shape, dt: [torch.empty(shape, dtype=dt).pin_memory() for _ in range(depth)]  # noqa: E731
+        self.hx = p((self.Z, H, W, cfg.nicg), torch.float32)
+        self.hm = p((self.Z, H, W), torch.float32)
+        self.hz = p((self.R * self.Z, cfg.noise_len, 1), torch.float32)
+        self.h_a = p(mshape, torch.float64) if (("dem" in self.outputs) or ("prob_mean" in self.outputs)) else None
+        self.h_b = p(mshape, torch.float64) if "fake2" in self.outputs else None
+        self.h_lab = p((self.Z, H, W), torch.uint8) if "labels" in self.outputs else None
+        self.h_cnt = p((1,), torch.int64)
+        self.pending = [None] * depth
+        self.i = 0
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    # ---- one subject in, (possibly) one finished subject out -------------------------------------------------
+    def submit(self, tag, vol, mask, thr=None, seed=0, noises=None):
+        """Enqueues one subject (vol (Z,H,W,nicg), mask (Z,H,W), Z <= z_max).  Returns the finished result of the
+        subject that previously used this slot (``(tag, dict)``) or None."""
+        torch = self.torch
+        net, cfg = self.net, self.net.cfg
+        k = self.i % self.depth
+        done = self._collect(k)
+        vol = np.asarray(vol)
+        Z = int(vol.shape[0])
+        if Z > self.Z or Z < 1:
+            raise ValueError("subject has %d slices, engine was built for at most %d" % (Z, self.Z))
+        if self.i >= self.depth:
+            self.ev_in[k].synchronize()                      # the H2D copies that last read these pinned buffers
+        self.hx[k][:Z].numpy()[...] = vol
+        self.hm[k][:Z].numpy()[...] = mask
+        rng = np.random.default_rng(seed)
+        hz = self.hz[k].numpy()
+        for rep in range(self.R):                            # one fresh N(0,1) draw per repeat (EG:620 / EU:557)
+            hz[rep * Z:(rep + 1) * Z] = _noise(rng, noises, rep, (Z, cfg.noise_len, 1))
+        rpp = max(1, min(self.R, cfg.max_batch // Z, self.rows // Z))   # repeats sharing one generator pass
+        with torch.cuda.device(self.dev):
+            if self.i == 0 or not any(self.pending):
+                self.ev_entry.record(torch.cuda.current_stream(self.dev))   # after the caller's weight updates
+                for st in (self.s_in, self.s_run, self.s_out):
+                    st.wait_event(self.ev_entry)
+            with torch.cuda.stream(self.s_in):
+                if self.i >= self.depth:
+                    self.s_in.wait_event(self.ev_run[k])
+                self.x[k][:Z].copy_(self.hx[k][:Z], non_blocking=True)
+                self.m[k][:Z].copy_(self.hm[k][:Z], non_blocking=True)
+                self.z[k][:self.R * Z].copy_(self.hz[k][:self.R * Z], non_blocking=True)
+                self.ev_in[k].record(self.s_in)
+            self.h2d_bytes += 4 * (self.hx[k][:Z].numel() + self.hm[k][:Z].numel() + self.R * Z * cfg.noise_len)
+            with torch.cuda.stream(self.s_run):
+                self.s_run.wait_event(self.ev_in[k])
+                if self.i >= self.depth:
+                    self.s_run.wait_event(self.ev_out[k])
+                self._run(k, Z, rpp, thr)
+                self.ev_run[k].record(self.s_run)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[k])
+                if self.h_a is not None:
+                    self.h_a[k][:Z].copy_(self.o_a[k][:Z], non_blocking=True)
+                    self.d2h_bytes += 8 * self.o_a[k][:Z].numel()
+                if self.h_b is not None:
+                    self.h_b[k][:Z].copy_(self.o_b[k][:Z], non_blocking=True)
+                    self.d2h_bytes += 8 * self.o_b[k][:Z].numel()
+                if self.h_lab is not None:
+                    self.h_lab[k][:Z].copy_(self.lab[k][:Z], non_blocking=True)
+                    self.d2h_bytes += self.lab[k][:Z].numel()
+                self.h_cnt[k].copy_(self.cnt[k], non_blocking=True)
+                self.d2h_bytes += 8
+                self.ev_out[k].record(self.s_out)
+        self.pending[k] = (tag, Z)
+        self.i += 1
+        return done
+
+    def _run(self, k, Z, rpp, thr):
+        """The kernels of one subject on the current (run) stream."""
+        torch = self.torch
+        net = self.net
+        x, m, acc = self.x[k], self.m[k][:Z], self.acc[k][:Z]
+        for r in range(1, rpp):                              # replicate the volume for multi-repeat passes
+            x[r * Z:(r + 1) * Z].copy_(x[:Z])
+        acc.zero_()
+        accu = postproc.DemAccumulator.wrap(acc)
+        rep = 0
+        while rep < self.R:
+            r_now = min(rpp, self.R - rep)
+            rows = r_now * Z
+            _forward_volume(net, x[:rows], self.z[k][rep * Z:rep * Z + rows], self.out[:rows])
+            for j in range(r_now):                           # EG:622-624: repeat order preserved
+                accu.add(self.out[j * Z:(j + 1) * Z], m)
+            rep += r_now
+        self.cnt[k].zero_()
+        L = _lib.lib()
+        with torch.cuda.device(self.dev):
+            if self.kind == "dem":
+                _lib.check(L.depgan_dem_postproc(x.data_ptr(), int(net.cfg.nicg), acc.data_ptr(), float(self.R),
+                                                 m.data_ptr(), float(thr), self.o_a[k].data_ptr(),
+                                                 self.o_b[k].data_ptr(), self.lab[k].data_ptr(),
+                                                 self.cnt[k].data_ptr(), acc.numel(), _stream(torch)), "dem_postproc")
+            else:
+                _lib.check(L.depgan_uresnet_labels(acc.data_ptr(), float(self.R), int(net.nc_out),
+                                                   self.o_a[k].data_ptr(), self.lab[k].data_ptr(),
+                                                   self.cnt[k].data_ptr(), m.numel(), _stream(torch)), "uresnet_labels")
+
+    def _collect(self, k):
+        if self.pending[k] is None:
+            return None
+        tag, Z = self.pending[k]
+        self.ev_out[k].synchronize()
+        res = {"wmh_voxels": int(self.h_cnt[k].item())}
+        first = "dem" if self.kind == "dem" else "prob_mean"
+        if first in self.outputs:
+            res[first] = self.h_a[k][:Z].numpy().copy()
+        if "fake2" in self.outputs:
+            res["fake2"] = self.h_b[k][:Z].numpy().copy()
+        if "labels" in self.outputs:
+            res["labels"] = self.h_lab[k][:Z].numpy().copy()
+        self.pending[k] = None
+        return tag, res
+
+    def flush(self):
+        """Finishes every subject in flight; returns their ``(tag, dict)`` results in submission order."""
+        out = []
+        for j in range(self.depth):
+            r = self._collect((self.i + j) % self.depth)
+            if r is not None:
+                out.append(r)
+        torch = self.torch
+        with torch.cuda.device(self.dev):
+            cur = torch.cuda.current_stream(self.dev)
+            cur.wait_stream(self.s_run)
+            cur.wait_stream(self.s_out)
+        return out
+
+
+def predict_subject_dem(netG, vol_1tp, mask_2tp, thr, n_repeat=10, seed=0, noises=None, outputs=None):
     """vol_1tp (Z,H,W,nicg) f32, mask_2tp (Z,H,W) f32 -> dict(dem f64, fake2 f64, labels u8, wmh_voxels int)."""
-    torch = _torch()
-    dev = netG.device
-    x = torch.from_numpy(np.ascontiguousarray(vol_1tp, np.float32)).to(dev)
-    m = torch.from_numpy(np.ascontiguousarray(mask_2tp, np.float32)).to(dev)
-    Z = x.shape[0]
-    acc = postproc.DemAccumulator((Z, netG.cfg.H, netG.cfg.W), dev)
-    out = torch.empty((Z, netG.cfg.H, netG.cfg.W, 1), dtype=torch.float32, device=dev)
-    rng = np.random.default_rng(seed)
-    for rep in range(n_repeat):
-        z = torch.from_numpy(_noise(rng, noises, rep, (Z, netG.cfg.noise_len, 1))).to(dev)
-        _forward_volume(netG, x, z, out)
-        acc.add(out, m)                                                    # EG:622-624
-    dem, fake2, labels, count = postproc.dem_postproc_device(x, netG.cfg.nicg, acc.acc, float(n_repeat), m, thr)
-    return {"dem": dem.cpu().numpy(), "fake2": fake2.cpu().numpy(), "labels": labels.cpu().numpy(),
-            "wmh_voxels": int(count.item())}
+    eng = SubjectEngine(netG, "dem", z_max=int(np.shape(vol_1tp)[0]), n_repeat=n_repeat, outputs=outputs, depth=1)
+    eng.submit(0, np.ascontiguousarray(vol_1tp, np.float32), np.ascontiguousarray(mask_2tp, np.float32), thr,
+               seed=seed, noises=noises)
+    return eng.flush()[0][1]
 
 
-def predict_subject_uresnet(net, vol, mask, n_repeat=10, seed=0, noises=None):
+def predict_subject_uresnet(net, vol, mask, n_repeat=10, seed=0, noises=None, outputs=None):
     """vol (Z,H,W,1) z-scored FLAIR, mask (Z,H,W) -> dict(prob_mean f64 (Z,H,W,4), labels u8, wmh_voxels int)."""
-    import ctypes as C  # noqa: F401
-    from . import _lib
-    from .api import _stream
-    torch = _torch()
-    dev = net.device
-    x = torch.from_numpy(np.ascontiguousarray(vol, np.float32)).to(dev)
-    m = torch.from_numpy(np.ascontiguousarray(mask, np.float32)).to(dev)
-    Z, nc = x.shape[0], net.nc_out
-    acc = postproc.DemAccumulator((Z, net.cfg.H, net.cfg.W, nc), dev)
-    out = torch.empty((Z, net.cfg.H, net.cfg.W, nc), dtype=torch.float32, device=dev)
-    rng = np.random.default_rng(seed)
-    for rep in range(n_repeat):
-        z = torch.from_numpy(_noise(rng, noises, rep, (Z, net.cfg.noise_len, 1))).to(dev)
-        _forward_volume(net, x, z, out)
-        acc.add(out, m)                                                    # EU:559-560
-    mean = torch.empty_like(acc.acc)
-    labels = torch.empty(m.shape, dtype=torch.uint8, device=dev)
-    count = torch.zeros(1, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().depgan_uresnet_labels(acc.acc.data_ptr(), float(n_repeat), nc, mean.data_ptr(),
-                                                    labels.data_ptr(), count.data_ptr(), m.numel(), _stream(torch)),
-                   "uresnet_labels")
-    return {"prob_mean": mean.cpu().numpy(), "labels": labels.cpu().numpy(), "wmh_voxels": int(count.item())}
+    eng = SubjectEngine(net, "uresnet", z_max=int(np.shape(vol)[0]), n_repeat=n_repeat, outputs=outputs, depth=1)
+    eng.submit(0, np.ascontiguousarray(vol, np.float32), np.ascontiguousarray(mask, np.float32), seed=seed,
+               noises=noises)
+    return eng.flush()[0][1]
 
 
 def evaluate_subject(result, real_labels, vol_1tp_ml, vol_2tp_ml, voxel_mm3, device="cuda:0"):
@@ -120,21 +268,44 @@ def save_subject_outputs(result, affine, out_dir, name):
     return paths
 
 
-def cohort_sweep(net, subjects, thr, rank=0, world=1, n_repeat=10, kind="dem"):
+def cohort_sweep(net, subjects, thr, rank=0, world=1, n_repeat=10, kind="dem", outputs=None, sink=None, engine=None):
     """subjects: list of (subject_id, vol, mask) or (subject_id, vol, mask, truth) with truth = dict(labels,
-    vol_1tp_ml, vol_2tp_ml, voxel_mm3).  Each rank processes its contiguous shard; returns {subject_id: result dict}
-    (with "eval_row" when truth is given).  No collective: gather the dictionaries on the host if a global table is
-    wanted."""
+    vol_1tp_ml, vol_2tp_ml, voxel_mm3).  Each rank processes its contiguous shard through one double-buffered
+    :class:`SubjectEngine`; returns {subject_id: result dict} (with "eval_row" when truth is given), or -- when
+    ``sink(subject_id, result)`` is given -- hands every finished subject to the callback and returns the number of
+    subjects processed (a whole cohort of float64 maps does not have to sit in host memory).  No collective: gather
+    the dictionaries on the host if a global table is wanted."""
+    mine = shard_items(subjects, rank, world)
     res = {}
-    for item in shard_items(subjects, rank, world):
+    if not mine:
+        return res if sink is None else 0
+    kind_e = "dem" if kind == "dem" else "uresnet"
+    if engine is None:
+        z_max = max(int(np.shape(it[1])[0]) for it in mine)
+        engine = SubjectEngine(net, kind_e, z_max=z_max, n_repeat=n_repeat, outputs=outputs)
+    truths = {}
+
+    def finish(done):
+        if done is None:
+            return
+        sid, r = done
+        t = truths.pop(sid, None)
+        if t is not None:
+            if "labels" not in r:
+                raise ValueError("evaluation rows need the 'labels' output")
+            r["eval_row"] = evaluate_subject(r, t["labels"], t["vol_1tp_ml"], t["vol_2tp_ml"], t["voxel_mm3"],
+                                             device=str(net.device))
+        if sink is None:
+            res[sid] = r
+        else:
+            sink(sid, r)
+
+    for item in mine:
         sid, vol, mask = item[0], item[1], item[2]
         seed = zlib.crc32(str(sid).encode()) & 0x7FFFFFFF  # per-subject noise stream, the same in every process
-        if kind == "dem":
-            res[sid] = predict_subject_dem(net, vol, mask, thr, n_repeat=n_repeat, seed=seed)
-        else:
-            res[sid] = predict_subject_uresnet(net, vol, mask, n_repeat=n_repeat, seed=seed)
         if len(item) > 3 and item[3] is not None:
-            t = item[3]
-            res[sid]["eval_row"] = evaluate_subject(res[sid], t["labels"], t["vol_1tp_ml"], t["vol_2tp_ml"],
-                                                    t["voxel_mm3"], device=str(net.device))
-    return res
+            truths[sid] = item[3]
+        finish(engine.submit(sid, vol, mask, thr, seed=seed))
+    for done in engine.flush():
+        finish(done)
+    return res if sink is None else len(mine)

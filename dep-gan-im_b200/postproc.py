@@ -23,6 +23,13 @@ class DemAccumulator:
         self.acc = torch.zeros(self.shape, dtype=torch.float64, device=self.device)
         self.n = 0
 
+    @classmethod
+    def wrap(cls, acc):
+        """Accumulator over an existing (already zeroed) float64 CUDA tensor."""
+        self = cls.__new__(cls)
+        self.torch, self.device, self.shape, self.acc, self.n = _torch(), acc.device, tuple(acc.shape), acc, 0
+        return self
+
     def add(self, pred, mask):
         """pred (Z,H,W[,C]) float32 CUDA tensor, mask (Z,H,W) float32 CUDA tensor."""
         torch = self.torch

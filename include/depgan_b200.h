@@ -194,6 +194,9 @@ int depgan_op_wgrad_csum(const void* x0, const void* x1, int C0, int C1, const v
                          int H, int W, int Cout, int ks, void* stream);
 int depgan_op_pack_weights(const float* w_f32_dev, void* w_bf16_dev, int taps, int cin, int cout, void* stream);
 int depgan_op_f32_to_bf16(const float* src_dev, void* dst_dev, long long n, void* stream);
+/* float32 -> IEEE float16 (round to nearest even), 16-byte aligned buffers: the opt-in narrow device->host output of
+ * predict() (an extension; the Keras contract, EG:621 / EU:558, returns float32 and stays the default). */
+int depgan_op_f32_to_f16(const float* src_dev, void* dst_dev, long long n, void* stream);
 int depgan_op_bf16_to_f32(const void* src_dev, float* dst_dev, long long n, void* stream);
 
 #ifdef __cplusplus
