@@ -4,7 +4,12 @@
 Workloads (BASELINE.json configs):
   uresnet_infer   (default, configs[1]) DEP-UResNet inference, 256x256, batch 64 per GPU, bf16 tcgen05 path
   depgan_infer    (configs[0])          DEP-GAN generator inference, 256x256 IM slices, batch 16
-  depgan_train    (configs[2])          DEP-GAN two-critic generator iteration, batch 32 (when built)
+  depgan_train    (configs[2])          DEP-GAN two-critic generator iteration (IM), batch 32 per GPU
+  depgan_train_pf (configs[3])          PROB+FLAIR two-critic training, GLOBAL batch 256 split over the GPUs (strong scaling)
+  cohort          (configs[4])          whole-cohort 4-fold test sweep, 156 synthetic 48-slice subjects x 10 repeats
+
+The default run prints ONE JSON line for configs[1] and carries the other four configs as sub-records under
+"configs" (each with its own value / unit / ms, measured in the same process right after the headline leg).
 
 One "step" = one pass of the hot path over one batch of synthetic slices.  `value` = slices/s with inputs
 resident in HBM; `e2e` = the same through the Keras-like public call with pinned host buffers (H2D + D2H inside
@@ -152,7 +157,9 @@ def run_reference(args, w, rank):
     line = {"impl": "reference", "metric": "256x256 slices/sec (gen inference)", "value": val, "unit": "slices/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["desc"], "batch_per_step_sample": sample},
+            "config": {"workload": w["desc"], "batch_per_step_sample": sample,
+                       "note": "per-slice rate of the same graph on %d-slice batches (a bounded sample of the batch-64 "
+                               "workload; the CPU rate does not depend on the batch size beyond 8)" % sample},
             "cpu_baseline": {"value": val, "unit": "slices/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "%d-slice batches x %d steps of the torch-CPU fp32 oracle "
                                        "(Keras reference not runnable here)" % (sample, args.steps)},
@@ -288,12 +295,26 @@ def run_gpu(args, w, rank, world, local_rank):
             except Exception:
                 pass
 
-    # ---- second headline metric: DEP-GAN train steps/s (configs[2]; data parallel when world > 1) ----
-    train = None
-    if not args.no_train:
-        del g, out, xd, zd
+    # ---- the drop-in call itself on NumPy arrays, then the other BASELINE configs as sub-records ----
+    extra = {}
+    if not args.no_extra:
+        extra["predict_numpy"] = measure_predict_numpy(args, w, g, rank, world, dev, B)
+    del g, out, xd, zd, pipe
+    torch.cuda.empty_cache()
+    if not args.no_extra:
+        extra["configs[0]"] = measure_config0(args, rank, world, dev)
         torch.cuda.empty_cache()
-        train = measure_train(args, rank, world, dev, steps=3, warmup=1)
+        extra["configs[4]"] = measure_cohort(args, rank, world, dev)
+        torch.cuda.empty_cache()
+
+    # ---- second headline metric: DEP-GAN train steps/s (configs[2] weak scaling at 32 slices per GPU; configs[3]
+    # PROB+FLAIR at a fixed global batch of 256; data parallel when world > 1) ----
+    train = train_pf = None
+    if not args.no_train:
+        train = measure_train(args, rank, world, dev, steps=10, warmup=2)
+        if not args.no_extra:
+            train_pf = measure_train(args, rank, world, dev, steps=max(2, min(8, 2 * world)), warmup=1,
+                                     workload="depgan_train_pf", global_batch=args.global_batch)
 
     if rank != 0:
         if world > 1:
@@ -325,22 +346,236 @@ def run_gpu(args, w, rank, world, local_rank):
         "e2e": {"value": slices / (ms_e2e * 1e-3), "unit": "slices/s",
                 "h2d_bytes_per_step": int(xh.numel() * 4 + zh.numel() * 4), "d2h_bytes_per_step": int(oh.numel() * 4)},
         "roofline": roof, "cpu_baseline": cpu, "train": train,
+        "configs": {"configs[0]": extra.get("configs[0]"),
+                    "configs[1]": "this line (value / e2e / roofline); predict(numpy) below",
+                    "configs[2]": "the 'train' record of this line (IM, 32 slices per GPU, weak scaling)",
+                    "configs[3]": train_pf, "configs[4]": extra.get("configs[4]")},
+        "predict_numpy": extra.get("predict_numpy"),
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"):
+def _barrier(torch, dist, dev, world):
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+
+
+def measure_config0(args, rank, world, dev):
+    """BASELINE configs[0]: DEP-GAN generator (tanh head, IM input) inference at batch 16: device-resident rate and the
+    rate of the public ``Gen_UNet2D.predict([x, z])`` call on pageable NumPy arrays (host copies inside the timing)."""
+    import torch
+    import torch.distributed as dist
+    from depgan_b200 import Gen_UNet2D, launch_count
+    w = WORKLOADS["depgan_infer"]
+    B = w["batch"]
+    g = Gen_UNet2D((256, 256, 1), (32, 1), 32, 1, precision=args.precision, max_batch=B, device=str(dev))
+    g.set_weights(make_weights(w, g))
+    x, z = make_inputs(w, B, seed=300 + rank)
+    xd, zd = torch.from_numpy(x).to(dev), torch.from_numpy(z).to(dev)
+    out = torch.empty((B, 256, 256, 1), dtype=torch.float32, device=dev)
+    steps = max(args.steps, 20)
+    for _ in range(5):
+        g.forward_device(xd, zd, out)
+    _barrier(torch, dist, dev, world)
+    l0 = launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g.forward_device(xd, zd, out)
+    e1.record()
+    _barrier(torch, dist, dev, world)
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+    # the drop-in call itself: predict() on NumPy arrays, 8 batches of 16 per call
+    nb = 8
+    xs, zs = np.concatenate([x] * nb), np.concatenate([z] * nb)
+    g.predict([xs, zs], batch_size=B)
+    g.predict([xs, zs], batch_size=B)
+    _barrier(torch, dist, dev, world)
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        y = g.predict([xs, zs], batch_size=B)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t = torch.tensor([ms, dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, dt = float(t[0]), float(t[1])
+    del g
+    if rank != 0:
+        return None
+    return {"workload": w["desc"], "metric": "256x256 slices/sec (gen inference)", "unit": "slices/s",
+            "value": B * steps * world / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "batch_per_gpu": B,
+            "n_gpus": world, "gpu_launches": int(launches), "tflops_effective": B * steps * world / (ms * 1e-3) * G_FLOP[(1, 1)] / 1e12,
+            "e2e": {"value": reps * xs.shape[0] * world / dt, "unit": "slices/s",
+                    "what": "Gen_UNet2D.predict([x, z], batch_size=16) on pageable NumPy arrays, %d slices per call, "
+                            "host wall clock (max over ranks)" % xs.shape[0],
+                    "h2d_bytes_per_step": int(x.nbytes + z.nbytes), "d2h_bytes_per_step": int(y.nbytes // nb)}}
+
+
+def measure_predict_numpy(args, w, g, rank, world, dev, B):
+    """The drop-in call of configs[1] itself: ``predict([x, z], batch_size=B)`` with NumPy in / NumPy out."""
+    import torch
+    import torch.distributed as dist
+    nb = 4
+    x, z = make_inputs(w, B, seed=400 + rank)
+    xs, zs = np.concatenate([x] * nb), np.concatenate([z] * nb)
+    res = {}
+    for name, dt_ in (("float32", None), ("float16_opt_in", np.float16)):
+        g.predict([xs, zs], batch_size=B, out_dtype=dt_)
+        _barrier(torch, dist, dev, world)
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            y = g.predict([xs, zs], batch_size=B, out_dtype=dt_)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res[name] = {"value": reps * xs.shape[0] * world / float(t[0]), "unit": "slices/s",
+                     "d2h_bytes_per_batch": int(y.nbytes // nb)}
+    res["what"] = "Gen_UNet2D.predict on pageable NumPy arrays (%d slices per call, batch_size %d), persistent pinned " \
+                  "staging inside the model, host wall clock, max over ranks" % (xs.shape[0], B)
+    return res if rank == 0 else None
+
+
+def measure_cohort(args, rank, world, dev):
+    """BASELINE configs[4]: the whole-cohort 4-fold test sweep (EG:378, 484, 616-741): 4 folds x 39 subjects of 48
+    synthetic 256x256 slices, 10 noise repeats per subject, float64 mean, DEM post-processing (labels + WMH voxel count),
+    subjects sharded over the ranks with no collective, one weight set per fold loaded through the Keras-h5 layout.
+    Wall clock from the first subject to the last result on the host, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from depgan_b200 import Gen_UNet2D, h5lite, launch_count, synth
+    from depgan_b200.infer import SubjectEngine, cohort_sweep
+    Z, folds, per_fold, R = 48, 4, 39, 10
+    thr = 0.178
+    w = WORKLOADS["depgan_infer"]
+    g = Gen_UNet2D((256, 256, 1), (32, 1), 32, 1, precision=args.precision, max_batch=2 * Z, device=str(dev))
+    man3 = [(n.split("/")[0], n.split("/")[1], s_) for n, s_, _, _ in g.manifest]
+    paths = []
+    for f in range(folds):  # four seeded weight sets, stored as the reference's per-fold .h5 files would be
+        pth = "/tmp/depgan_cohort_fold%d_rank%d.h5" % (f, rank)
+        h5lite.save_keras_weights(pth, synth.init_weights(man3, seed=40 + f, trained_like=True),
+                                  [n for n, _, _, _ in g.manifest])
+        paths.append(pth)
+    # a small pool of distinct synthetic volumes stands in for the 39 subjects of a fold (the arithmetic does not depend
+    # on the content; every subject still gets its own noise stream, upload, kernels, post-processing and download)
+    pool = [synth.make_im_pair(Z, 256, 256, thr=thr, seed=900 + i) for i in range(3)]
+    out = {}
+    for mode, outputs in (("full_outputs", ("dem", "fake2", "labels")), ("labels_only", ("labels",))):
+        eng = SubjectEngine(g, "dem", z_max=Z, n_repeat=R, outputs=outputs)
+        voxels = [0]
+
+        def sink(sid, r):
+            voxels[0] += r["wmh_voxels"]
+
+        def fold(f, n_subjects):
+            g.load_weights(paths[f])
+            subs = [("f%d_s%02d" % (f, i), pool[i % len(pool)][0], pool[i % len(pool)][2]) for i in range(n_subjects)]
+            return cohort_sweep(g, subs, thr, rank=rank, world=world, n_repeat=R, sink=sink, engine=eng)
+
+        fold(0, 2 * world)  # warm-up: two subjects per rank
+        _barrier(torch, dist, dev, world)
+        eng.h2d_bytes = eng.d2h_bytes = 0
+        l0 = launch_count()
+        t0 = time.perf_counter()
+        mine = 0
+        for f in range(folds):
+            mine += fold(f, per_fold)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        launches = launch_count() - l0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t[0])
+        n_sub = folds * per_fold
+        out[mode] = {"wall_s": dt, "subjects_per_s": n_sub / dt, "slice_forwards_per_s": n_sub * Z * R / dt,
+                     "outputs_to_host": list(outputs) + ["wmh_voxels"], "subjects_this_rank": mine,
+                     "h2d_bytes_per_subject": eng.h2d_bytes // max(mine, 1),
+                     "d2h_bytes_per_subject": eng.d2h_bytes // max(mine, 1), "gpu_launches_this_rank": int(launches)}
+        del eng
+    del g
+    if rank != 0:
+        return None
+    return {"workload": "whole-cohort 4-fold test sweep: 4 x 39 synthetic subjects x 48 slices x 10 noise repeats "
+                        "(74 880 slice-forwards) + DEM post-processing, subjects sharded over %d GPU(s), no collective "
+                        "(BASELINE configs[4])" % world,
+            "metric": "256x256 slices/sec (gen inference)", "unit": "slices/s", "n_gpus": world,
+            "value": out["full_outputs"]["slice_forwards_per_s"], "scaling": "strong",
+            "what": "host wall clock incl. weight loading per fold, uploads, kernels, float64 mean, post-processing and "
+                    "the download of every subject's maps (max over ranks); 'full_outputs' returns what the testing "
+                    "script saves per subject (DEM, predicted follow-up map, label map), 'labels_only' the label map "
+                    "and the voxel count", **out}
+
+
+def dp_self_check(tr, G, D1, D2, rank, world, dev, nicg, thr, cap):
+    """Data-parallel correctness inside the bench run (the 2-GPU pytest cases are skipped on one-GPU boxes): every rank
+    feeds its shard of ONE fixed global batch through the data-parallel critic / generator gradient calls (NCCL
+    all-reduce of the flat bucket and of the loss partial sums); rank 0 then runs the same batch unsharded through a
+    non-distributed trainer on the same weights and reports the relative differences."""
+    import torch
+    from depgan_b200 import synth
+    from depgan_b200.trainer import DepGanTrainer
+    Bg = max(world, (min(cap, 32) // world) * world)  # global check batch, divisible by world, fits rank 0 unsharded
+    per = Bg // world
+    x1, y2, _ = synth.make_im_pair(Bg, 256, 256, nicg=nicg, thr=thr, seed=4242)
+    z, ep = synth.make_noise(Bg, seed=4243), synth.make_eps(Bg, seed=4244).reshape(-1)
+    full = [torch.from_numpy(a).to(dev) for a in (y2, x1, z, ep)]
+    sl = slice(rank * per, (rank + 1) * per)
+    mine = [t[sl].contiguous() for t in full]
+    res = {}
+    # data-parallel pass (all ranks)
+    c_dp = tr.critic_grads_device(0, *mine).clone()
+    gD_dp = D1.grads.clone()
+    g_dp = tr.gen_device(mine[1], mine[0], mine[2], True).clone()
+    gG_dp = G.grads.clone()
+    torch.cuda.synchronize(dev)
+    if rank == 0:
+        solo = DepGanTrainer(G, D1, D2, thr, distributed=False)
+        c_1 = solo.critic_grads_device(0, *full).clone()
+        gD_1 = D1.grads.clone()
+        g_1 = solo.gen_device(full[1], full[0], full[2], True).clone()
+        gG_1 = G.grads.clone()
+        torch.cuda.synchronize(dev)
+
+        def rel(a, b):
+            return float((a.double() - b.double()).norm() / (b.double().norm() + 1e-30))
+        res = {"global_batch": Bg, "per_rank": per,
+               "critic_loss_rel_err": rel(c_dp, c_1), "critic_grad_rel_err": rel(gD_dp, gD_1),
+               "gen_loss_rel_err": rel(g_dp, g_1), "gen_grad_rel_err": rel(gG_dp, gG_1),
+               "what": "||dp - single|| / ||single|| over the 4 critic loss terms / the flat critic gradient / the 6 "
+                       "generator loss terms / the flat generator gradient (bf16 activations: the two runs differ only "
+                       "in summation order)"}
+    if world > 1:
+        torch.distributed.barrier()
+    return res
+
+
+def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train", global_batch=None):
     """BASELINE configs[2]/[3]: DEP-GAN two-critic training, one step = one generator iteration of the reference
     schedule (5 Y2-critic + 5 DEM-critic updates, 10 noise evaluations, 1 generator update; TG:796-878).
+    ``global_batch``: strong scaling -- the global batch is fixed and split evenly over the ranks (configs[3]);
+    otherwise every rank runs ``--train-batch`` slices (weak scaling).
     Returns the result dict on rank 0 (None elsewhere).  The process group must already exist for world > 1."""
     import torch
     import torch.distributed as dist
     from depgan_b200 import Dis_C2D_FCN1, Gen_UNet2D, launch_count, synth
     from depgan_b200.trainer import DepGanTrainer
 
-    B = args.train_batch
+    if global_batch:
+        if global_batch % world:
+            raise ValueError("global batch %d is not divisible by %d ranks" % (global_batch, world))
+        B = global_batch // world
+    else:
+        B = args.train_batch
     nicg = 2 if workload == "depgan_train_pf" else 1
     thr = 0.5 if nicg == 2 else 0.178
     G = Gen_UNet2D((256, 256, nicg), (32, 1), 32, 1, precision=args.precision, max_batch=B, device=str(dev),
@@ -370,6 +605,9 @@ def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    dp_check = None
+    if world > 1:  # before any update: all ranks hold identical weights (same seeds)
+        dp_check = dp_self_check(tr, G, D1, D2, rank, world, dev, nicg, thr, B)
     for i in range(warmup):
         step(i)
     barrier()
@@ -405,25 +643,30 @@ def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
+    last = [float(v) for v in out.cpu().numpy()]
+    del tr, G, D1, D2, batches, noises
+    torch.cuda.empty_cache()
     if rank != 0:
         return None
     flop_per_slice = 1013.3e9  # 10 critic updates + 10 evals + 1 G update
+    pk = peaks()
+    tf = steps * B * world * flop_per_slice / (ms * 1e-3) / 1e12
     return {
         "metric": "DEP-GAN train steps/sec (generator iterations: 5+5 critic updates, 10 noise evals, 1 G update)",
         "value": steps / (ms * 1e-3), "unit": "gen-iterations/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
-        "data": "synthetic",
+        "scaling": "strong" if global_batch else "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "DEP-GAN %s two-critic training, random init, batch %d per GPU, global batch %d "
-                               "(BASELINE configs[%s])" % ("PROB+FLAIR" if nicg == 2 else "IM", B, B * world,
-                                                           "3" if nicg == 2 else "2"),
+                               "(BASELINE configs[%s])" % ("PROB+FLAIR (nicg=2, T=0.5)" if nicg == 2 else "IM", B,
+                                                           B * world, "3" if nicg == 2 else "2"),
                    "precision": args.precision,
                    "parallelism": "data parallel over %d GPU(s): NCCL all-reduce of the flat gradient bucket + "
                                   "loss partial sums" % world,
                    "l2": "per-step working set >> 126 MB L2; no explicit flush"},
         "slices_per_s": steps * B * world / (ms * 1e-3),
-        "tflops_effective": steps * B * world * flop_per_slice / (ms * 1e-3) / 1e12,
-        "last_losses": [float(v) for v in out.cpu().numpy()],
+        "tflops_effective": tf, "frac_of_sustained_bf16_peak_per_gpu": tf / world / pk["tf_sust"],
+        "last_losses": last, "dp_check": dp_check,
         "clocks": clocks, "gpu_launches": int(launches), "conv_time_per_iteration": prof,
     }
 
@@ -435,7 +678,8 @@ def run_train(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    line = measure_train(args, rank, world, dev, args.steps, args.warmup, args.workload)
+    gb = args.global_batch if args.workload == "depgan_train_pf" and not args.batch else None
+    line = measure_train(args, rank, world, dev, args.steps, args.warmup, args.workload, global_batch=gb)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -458,6 +702,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the DEP-GAN train-step leg of the default run")
     ap.add_argument("--train-batch", type=int, default=32, help="per-GPU batch of the train-step leg")
+    ap.add_argument("--global-batch", type=int, default=256,
+                    help="global batch of the PROB+FLAIR strong-scaling leg (BASELINE configs[3])")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the sub-records of configs[0], [3], [4] and the predict(numpy) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
