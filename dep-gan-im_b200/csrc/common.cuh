@@ -154,6 +154,9 @@ int conv_first_tc_try(const ConvArgs& a, cudaStream_t st);  // tcgen05 first lay
 bool conv_tc_supported(const ConvArgs& a);
 bool conv_tc_plan_query(const ConvArgs& a, int* plan16);  // host-only: the planner's geometry for a supported layer
 int conv_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
+// row-streaming tcgen05 kernel for the 3x3, 32-output-channel layers at full width (conv_row.cu); conv_fwd_tc routes to it
+bool conv_row_supported(const ConvArgs& a);
+int conv_fwd_row(const ConvArgs& a, cudaStream_t st);
 
 // wgrad: dw[tap][ci][co] += alpha * sum_p x[p+off(tap)][ci] * dy[p][co]  (fp32 accumulate, atomics)
 struct WgradArgs {

@@ -157,6 +157,8 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
 
 }  // namespace
 
+static bool tile_kernel_supported(const ConvArgs& a);
+
 int conv_tc_init() {
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
@@ -185,6 +187,10 @@ int conv_tc_init() {
 }
 
 bool conv_tc_supported(const ConvArgs& a) {
+  return conv_row_supported(a) || tile_kernel_supported(a);  // conv_row.cu takes the 32-channel full-width 3x3 layers
+}
+
+static bool tile_kernel_supported(const ConvArgs& a) {
   if (a.in_dt != DT_BF16 || a.out_dt != DT_BF16) return false;
   if (a.ks != 1 && a.ks != 3 && a.ks != 5) return false;
   if (a.deconv && a.ks != 1) return false;
@@ -208,7 +214,7 @@ bool conv_tc_supported(const ConvArgs& a) {
 bool conv_tc_plan_query(const ConvArgs& a, int* o) {
   TcGeom g;
   uint32_t smem;
-  if (!conv_tc_supported(a) || !plan(a, &g, &smem)) return false;
+  if (!tile_kernel_supported(a) || !plan(a, &g, &smem)) return false;
   const int v[16] = {g.kc, g.ncta, g.nchunk0 + g.nchunk1, g.na, g.nb, g.b_tps, g.b_resident, g.acc_stages, g.n_issuers,
                      g.ch, g.n_side, g.tmem_cols, (int)smem, g.pool, g.stage_out, g.ncols_total / g.ncta};
   for (int i = 0; i < 16; ++i) o[i] = v[i];
@@ -217,10 +223,11 @@ bool conv_tc_plan_query(const ConvArgs& a, int* o) {
 
 int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   if (a.N <= 0) return 0;
+  if (conv_row_supported(a)) return conv_fwd_row(a, st);
   DG_TRY(conv_tc_init());
   TcGeom g;
   uint32_t smem;
-  DG_REQUIRE(conv_tc_supported(a) && plan(a, &g, &smem), "conv_fwd_tc: unsupported shape");
+  DG_REQUIRE(tile_kernel_supported(a) && plan(a, &g, &smem), "conv_fwd_tc: unsupported shape");
   const int ht = 16 + a.ks - 1;
   TcMaps tm;
   DG_TRY(make_act_map(&tm.a0, a.in0, a.C0, a.W, a.H, a.N, g.kc, ht));
