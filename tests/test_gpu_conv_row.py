@@ -11,9 +11,10 @@ from tests.test_gpu_conv import _bf, _rand, ref_conv
 
 pytestmark = pytest.mark.gpu
 
-ROW_CASES = [  # N, H, W, c0, c1
-    (2, 32, 128, 32, 0), (1, 16, 256, 32, 0), (3, 64, 128, 32, 0), (2, 48, 256, 32, 0),
-    (2, 32, 128, 64, 32), (1, 32, 256, 64, 32), (2, 32, 128, 32, 32), (1, 16, 128, 96, 0),
+ROW_CASES = [  # N, H, W, c0, c1   (W a multiple of 256; odd heights and tiny segments exercise the edge paths)
+    (2, 32, 256, 32, 0), (1, 16, 512, 32, 0), (3, 64, 256, 32, 0), (2, 48, 256, 32, 0), (5, 7, 256, 32, 0),
+    (2, 32, 256, 64, 32), (1, 33, 512, 64, 32), (2, 32, 256, 32, 32), (1, 16, 256, 96, 0), (3, 1, 256, 32, 0),
+    (2, 2, 256, 32, 0), (1, 3, 256, 64, 32),
 ]
 
 
@@ -48,7 +49,7 @@ def test_row_kernel_is_exact_on_integer_data():
     assert torch.equal(got, want)
 
 
-@pytest.mark.parametrize("N,H,W", [(2, 32, 128), (1, 32, 256), (3, 16, 128)])
+@pytest.mark.parametrize("N,H,W", [(2, 32, 256), (1, 32, 512), (3, 17, 256)])
 def test_row_kernel_film_residual(N, H, W):
     from depgan_b200 import conv2d_op
     c = 32
@@ -64,7 +65,7 @@ def test_row_kernel_film_residual(N, H, W):
 
 def test_row_kernel_add_and_mask():
     from depgan_b200 import conv2d_op
-    N, H, W, c = 2, 32, 128, 32
+    N, H, W, c = 2, 31, 256, 32
     x, w = _bf(_rand((N, H, W, c), 1)), _bf(_rand((3, 3, c, c), 2, 0.08))
     add, mask = _bf(_rand((N, H, W, c), 6)), _bf(_rand((N, H, W, c), 7))
     for kw in ({"add": add}, {"mask": mask}, {"add": add, "mask": mask}):
@@ -79,7 +80,7 @@ def test_row_kernel_fused_head(nc, act):
     """conv2d_gen_17 + gen_segmentation (1x1, tanh / softmax) fused: the head is computed from the fp32 values before
     the bf16 rounding of the stored tensor."""
     from depgan_b200 import conv2d_op
-    N, H, W, c = 2, 32, 128, 32
+    N, H, W, c = 2, 33, 256, 32
     x, w = _bf(_rand((N, H, W, c), 1)), _bf(_rand((3, 3, c, c), 2, 0.08))
     sc, sh = 1 + 0.1 * _rand((c,), 6), 0.1 * _rand((c,), 7)
     hw, hb = 0.3 * _rand((c, nc), 8), 0.1 * _rand((nc,), 9)
@@ -92,8 +93,8 @@ def test_row_kernel_fused_head(nc, act):
 
 
 def test_row_kernel_many_bands_per_cta_match_first_pass():
-    """More work items than SMs (N = 40 slices x 2 column blocks x 8 bands = 640 items): every CTA loops over several
-    bands, wrapping all rings; slices are independent, so slice k of the batch equals slice k computed alone."""
+    """40 slices x 256 rows: every CTA walks ~70 rows across image borders, wrapping all rings many times; slices are
+    independent, so slice k of the batch equals slice k computed alone (a different split of the rows over CTAs)."""
     from depgan_b200 import conv2d_op
     H, W, c = 256, 256, 32
     x = _bf(_rand((40, H, W, c), 1))
