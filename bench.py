@@ -288,10 +288,16 @@ def run_gpu(args, w, rank, world, local_rank):
                                          "achieved": (arr_fl[0] + arr_fl[6]) / ((arr_ms[0] + arr_ms[6]) * 1e-3) / 1e12,
                                          "frac": (arr_fl[0] + arr_fl[6]) / ((arr_ms[0] + arr_ms[6]) * 1e-3) / 1e12
                                                  / pk["tf_sust"]}}
-        prof_path = ROOT / "profiles" / "ncu_traffic_r01.json"
+        # DRAM traffic per launch of the same kernel class: from the committed ncu --set full capture of this step
+        # (scripts/r2_run4.sh -> scripts/summarize_profiles.py r02); the record names the commit it was taken at
+        prof_path = ROOT / "profiles" / "ncu_traffic_r02.json"
         if roof and prof_path.exists():
             try:
-                roof["traffic"] = json.loads(prof_path.read_text()).get("dram_bytes_per_launch")
+                pj = json.loads(prof_path.read_text())
+                roof["traffic"] = pj.get("dram_bytes_per_launch")
+                roof["traffic_source"] = "profiles/ncu_traffic_r02.json (ncu --set full at commit %s)" % pj.get("commit")
+                roof["algorithmic_bytes_per_launch"] = arr_by[k] / arr_n[k]
+                roof["ncu_tensor_pipe_pct_time_weighted"] = pj.get("time_weighted_tensor_pipe_pct_batch64_cold")
             except Exception:
                 pass
 

@@ -44,12 +44,12 @@ def full_summary(src, dst, traffic_json, batch, bench_batch, alg_bytes_b16):
     name_i, dur_i = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
     rd_i, wr_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     tp_i = hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
-    k3 = [d for d in data if "conv_tc_kernel<3" in d[name_i]]
+    k3 = [d for d in data if "conv_tc_kernel<3" in d[name_i] or "conv_row_kernel" in d[name_i]]
     dur = sum(float(d[dur_i]) for d in k3)
     dram = sum(float(d[rd_i]) + float(d[wr_i]) for d in k3) * 1e6
     tens = sum(float(d[tp_i]) * float(d[dur_i]) for d in k3) / dur
     json.dump({
-        "source": "ncu --set full --clock-control none, conv_tc_kernel<3,*,*,*>, the %d launches of one DEP-UResNet "
+        "source": "ncu --set full --clock-control none, conv_tc_kernel<3,*,*,*> + conv_row_kernel, the %d launches of one DEP-UResNet "
                   "forward at batch %d (profiles/%s)" % (len(k3), batch, dst.name),
         "launches": len(k3), "dram_bytes_total_batch%d" % batch: dram,
         "algorithmic_bytes_total_batch%d" % batch: alg_bytes_b16,
@@ -62,7 +62,26 @@ def full_summary(src, dst, traffic_json, batch, bench_batch, alg_bytes_b16):
     }, open(traffic_json, "w"), indent=1)
 
 
+def round2(tag="r02", commit=None):
+    """Round 2: launch list of one batch-64 forward and --set full on every convolution launch of it (scripts/r2_run4.sh)."""
+    t = launch_table(SRC / "r02_infer_launches_b64_raw.csv", OUT / ("%s_infer_launches_b64.csv" % tag))
+    print("inference forward b64: %.1f us over all launches (cold, serialised)" % t)
+    full_summary(SRC / "r02_conv_full_raw_b64.csv", OUT / ("%s_conv_ncu_full_summary_b64.csv" % tag),
+                 OUT / "ncu_traffic_r02.json", 64, 64, 64 * 100597760.0)
+    d = json.load(open(OUT / "ncu_traffic_r02.json"))
+    d["commit"] = commit
+    d["algorithmic_bytes_definition"] = (
+        "every input / output / FiLM-residual tensor of the 20 3x3 launches moved once, bf16 (fp32 for the 4-channel head "
+        "output): 100 597 760 B per slice = the figure depgan_profile_end reports to bench.py (6.44 GB per 64-slice step); "
+        "round 1's 8.92 GB counted the decoder inputs once per source AND once concatenated")
+    json.dump(d, open(OUT / "ncu_traffic_r02.json", "w"), indent=1)
+
+
 if __name__ == "__main__":
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "r02":
+        round2("r02" if len(sys.argv) < 4 else sys.argv[3], sys.argv[2] if len(sys.argv) > 2 else None)
+        sys.exit(0)
     # final build of round 1 (programmatic dependent launch): launch list and --set full, both at the bench batch of 64
     t = launch_table(SRC / "infer_launches_b64_final.csv", OUT / "r01_final_infer_launches_b64.csv")
     print("inference forward b64: %.1f us over all launches (cold, serialised)" % t)

@@ -98,5 +98,7 @@ int main() {
   run<128, 1, 0, 0, 1, 0>(d);  run<128, 2, 0, 128, 1, 0>(d); run<128, 2, 0, 256, 1, 0>(d);
   run<192, 1, 0, 0, 1, 0>(d);  run<192, 2, 0, 256, 1, 0>(d);
   run<256, 1, 0, 0, 1, 0>(d);  run<256, 2, 0, 256, 1, 0>(d);
+  run<16, 1, 0, 0, 1, 0>(d);   run<16, 1, 0, 0, 1, 2>(d);    run<48, 1, 0, 0, 1, 0>(d);    run<80, 1, 0, 0, 1, 0>(d);   run<80, 1, 0, 0, 1, 2>(d);
+  run<160, 1, 0, 0, 1, 0>(d);  run<160, 1, 0, 0, 1, 4>(d);   run<192, 1, 0, 0, 1, 4>(d);   run<192, 1, 0, 0, 1, 8>(d);
   return 0;
 }
