@@ -341,7 +341,8 @@ def run_gpu(args, w, rank, world, local_rank):
     line = {
         "metric": "256x256 slices/sec (gen inference)", "value": value, "unit": "slices/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": {"bf16": "bf16", "f16": "f16", "fp32": "f32"}[args.precision],
         "data": "synthetic",
         "config": {"workload": w["desc"], "batch_per_gpu": B, "precision": args.precision,
                    "weights": "synthetic (seeded), round-tripped through the Keras-h5 layout",
@@ -584,10 +585,10 @@ def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"
         B = args.train_batch
     nicg = 2 if workload == "depgan_train_pf" else 1
     thr = 0.5 if nicg == 2 else 0.178
-    G = Gen_UNet2D((256, 256, nicg), (32, 1), 32, 1, precision=args.precision, max_batch=B, device=str(dev),
+    G = Gen_UNet2D((256, 256, nicg), (32, 1), 32, 1, precision=args.train_precision, max_batch=B, device=str(dev),
                    training=True, seed=0)
-    D1 = Dis_C2D_FCN1((256, 256, 1), precision=args.precision, max_batch=3 * B, device=str(dev), training=True, seed=1)
-    D2 = Dis_C2D_FCN1((256, 256, 1), precision=args.precision, max_batch=3 * B, device=str(dev), training=True, seed=2)
+    D1 = Dis_C2D_FCN1((256, 256, 1), precision=args.train_precision, max_batch=3 * B, device=str(dev), training=True, seed=1)
+    D2 = Dis_C2D_FCN1((256, 256, 1), precision=args.train_precision, max_batch=3 * B, device=str(dev), training=True, seed=2)
     tr = DepGanTrainer(G, D1, D2, thr)
 
     def batch(seed):
@@ -662,11 +663,11 @@ def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"
         "value": steps / (ms * 1e-3), "unit": "gen-iterations/s", "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
         "scaling": "strong" if global_batch else "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": "bf16" if args.train_precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "DEP-GAN %s two-critic training, random init, batch %d per GPU, global batch %d "
                                "(BASELINE configs[%s])" % ("PROB+FLAIR (nicg=2, T=0.5)" if nicg == 2 else "IM", B,
                                                            B * world, "3" if nicg == 2 else "2"),
-                   "precision": args.precision,
+                   "precision": args.train_precision,
                    "parallelism": "data parallel over %d GPU(s): NCCL all-reduce of the flat gradient bucket + "
                                   "loss partial sums" % world,
                    "l2": "per-step working set >> 126 MB L2; no explicit flush"},
@@ -703,7 +704,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="uresnet_infer",
                     choices=sorted(WORKLOADS) + ["depgan_train", "depgan_train_pf"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    # inference legs: 'f16' (default) and 'bf16' run the same tcgen05 kernels at the same rate, f16 = IEEE-half storage
+    # (DEM error ~7x smaller); the training legs keep bf16 (gradient range) unless fp32 is asked for
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-train", action="store_true", help="skip the DEP-GAN train-step leg of the default run")
@@ -713,6 +716,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true",
                     help="skip the sub-records of configs[0], [3], [4] and the predict(numpy) leg")
     args = ap.parse_args()
+    args.train_precision = "fp32" if args.precision == "fp32" else "bf16"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -159,11 +159,48 @@ class _Net:
         from . import h5lite
         self.set_weights(h5lite.load_keras_weights(path, [(n, s) for n, s, _, _ in self.manifest]))
 
-    def save(self, path):
+    def _keras_description(self):
+        raise NotImplementedError  # Gen_UNet2D / Dis_C2D_FCN1 name their graph
+
+    def save(self, path, include_optimizer=True):
+        """`model.save(path)` (TG:892, TU:622): a Keras 2.x full-model HDF5 file -- /model_weights in Keras' own layer order
+        (weight-less layers included), the `model_config` JSON, and for a compiled model that has trained (`fit`) the
+        `training_config` + /optimizer_weights (iterations, first and second moments, the unused amsgrad slots) in the
+        order of `optimizer.weights`.  See keras_config.py for what is and is not verified about the JSON."""
+        from . import h5lite, keras_config
+        d = self._keras_description()
+        w = self.get_weights()
+        training_config = opt = None
+        if include_optimizer and self.cfg.training == 2 and self.adam_m is not None:
+            training_config = keras_config.adam_training_config()
+            m, v = self.adam_m.detach().cpu().numpy(), self.adam_v.detach().cpu().numpy()
+            offs = {n: (o, s) for n, s, o, tr in self.manifest if tr}
+            tw = ["%s/%s" % (ln, wn) for ln in d["layer_names"] for wn in d["weights"][ln] if "%s/%s" % (ln, wn) in offs]
+            opt, k = [("Adam/iterations:0", np.array(self.iterations, np.int64))], 0
+
+            def var(arr):
+                nonlocal k
+                name = "training/Adam/Variable%s:0" % ("" if k == 0 else "_%d" % k)
+                k += 1
+                opt.append((name, arr))
+
+            for buf in (m, v):
+                for n in tw:
+                    o, shp = offs[n]
+                    var(buf[o:o + int(np.prod(shp))].reshape(shp).copy())
+            for _ in tw:  # vhats of amsgrad=False: K.zeros(1) each
+                var(np.zeros((1,), np.float32))
+        h5lite.save_keras_model(path, w, d["layer_names"], d["weights"], d["model_config"], training_config, opt)
+
+    def to_json(self):
+        """`model.to_json()` (TU:623)."""
+        return self._keras_description()["model_config"]
+
+    def save_weights(self, path):
+        """Weights only, under /model_weights in manifest order (readable by `load_weights` here and, by layer name, by
+        Keras' `load_weights(by_name=True)`)."""
         from . import h5lite
         h5lite.save_keras_weights(path, self.get_weights(), [n for n, _, _, _ in self.manifest])
-
-    save_weights = save
 
 
 def _prec(precision):
@@ -171,15 +208,18 @@ def _prec(precision):
         return _lib.PREC_BF16
     if precision in ("fp32", "f32", _lib.PREC_FP32):
         return _lib.PREC_FP32
-    raise ValueError("precision must be 'bf16' or 'fp32'")
+    if precision in ("f16", "fp16", _lib.PREC_F16):
+        return _lib.PREC_F16
+    raise ValueError("precision must be 'bf16', 'f16' (generator inference) or 'fp32'")
 
 
 class Gen_UNet2D(_Net):
     """Drop-in for ``Gen_UNet2D(input_shape, noiseZ_shape, first_fm, nc_out)`` (TG:349-498, TU:291-428).
 
     nc_out == 1 -> tanh head (DEP-GAN generator); nc_out == 4 -> softmax head (DEP-UResNet).
-    Extra keyword arguments choose the arithmetic ('bf16' tcgen05 path, 'fp32' CUDA-core path), the
-    workspace batch, the device and the synthetic-initialisation seed.
+    Extra keyword arguments choose the arithmetic ('bf16' tcgen05 path; 'f16' = the same kernels with IEEE-half
+    activations and weights, inference handles only, ~7x smaller DEM error at the same speed; 'fp32' CUDA-core path),
+    the workspace batch, the device and the synthetic-initialisation seed.
     """
 
     def __init__(self, input_shape=(256, 256, 1), noiseZ_shape=(32, 1), first_fm=32, nc_out=1, *, precision="bf16",
@@ -194,6 +234,10 @@ class Gen_UNet2D(_Net):
                        tmode)
         self.input_shape, self.noiseZ_shape, self.nc_out = tuple(input_shape), tuple(noiseZ_shape), int(nc_out)
         super().__init__(_lib.MODEL_GEN, cfg, device, seed)
+
+    def _keras_description(self):
+        from . import keras_config
+        return keras_config.describe("generator", self.input_shape, self.noiseZ_shape[0], self.nc_out)
 
     def forward_device(self, x, z, out=None):
         """x (n,H,W,nicg), z (n,L,1) float32 CUDA tensors -> (n,H,W,nc_out) float32 CUDA tensor (async)."""
@@ -526,6 +570,10 @@ class Dis_C2D_FCN1(_Net):
         cfg = _lib.Cfg(int(h), int(w), 1, 1, 32, int(max_batch), _prec(precision), int(bool(training)))
         self.input_shape = tuple(input_shape)
         super().__init__(_lib.MODEL_CRITIC, cfg, device, seed)
+
+    def _keras_description(self):
+        from . import keras_config
+        return keras_config.describe("critic", self.input_shape)
 
     def forward_device(self, x, out=None):
         torch = self._torch

@@ -1,6 +1,7 @@
 // Shared declarations for the depgan_b200 CUDA sources (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -99,14 +100,41 @@ inline int dg_device_enter(DgPerDevice& s, int* dev, bool* first) {
 }
 inline void dg_device_mark(DgPerDevice& s, int dev) { if (dev < 64) s.done |= 1ull << dev; }
 
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
+// DT_F16: IEEE half storage of the inference-only generator handles (DEPGAN_PREC_F16): same tcgen05 kind::f16 rate and
+// the same kernels as bf16 (the 16-bit format is a run-time flag of the pack / unpack points), 3 more mantissa bits
+// per stored activation -- DEM max-abs error ~1.5e-3 instead of ~1e-2 with un-normalised (freshly initialised) weights.
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+static inline bool dt_is_half(int dt) { return dt == DT_BF16 || dt == DT_F16; }
 
 // ---- typed load/store helpers ----
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ float ldf(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void stf(__half* p, float v) { *p = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
+
+// ---- two 16-bit floats in one word; `f16` (warp-uniform) selects IEEE half, else bfloat16.  Low half = first value. ----
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, bool f16) {
+  uint32_t r;
+  if (f16) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_h2(uint32_t w, bool f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+// element-wise max of two packed pairs (2x2 max-pool on the stored values)
+__device__ __forceinline__ uint32_t max_h2(uint32_t a, uint32_t b, bool f16) {
+  if (f16) {
+    const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&m);
+  }
+  const __nv_bfloat162 m = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&m);
+}
 
 // ---- convolution argument block (SIMT and tcgen05 paths share it) ----
 // acc = conv(in0 || in1, w)  ('same' padding, stride 1, ks in {1,3,5});  then per output element (n,h,w,c):
@@ -157,6 +185,9 @@ int conv_tc_init();  // resolves cuTensorMapEncodeTiled, sets smem attributes
 // row-streaming tcgen05 kernel for the 3x3, 32-output-channel layers at full width (conv_row.cu); conv_fwd_tc routes to it
 bool conv_row_supported(const ConvArgs& a);
 int conv_fwd_row(const ConvArgs& a, cudaStream_t st);
+// generic row-streaming kernel (conv_rowg.cu): 5x5 critic layers, 64-output-channel 3x3 layers; width a multiple of 128
+bool conv_rowg_supported(const ConvArgs& a);
+int conv_fwd_rowg(const ConvArgs& a, cudaStream_t st);
 
 // wgrad: dw[tap][ci][co] += alpha * sum_p x[p+off(tap)][ci] * dy[p][co]  (fp32 accumulate, atomics)
 struct WgradArgs {

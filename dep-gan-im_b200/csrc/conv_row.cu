@@ -142,7 +142,8 @@ struct SegIter {
 // ---------------------------------------------------------------------------------------------------------
 // EPI bit 0: FiLM residual side row; bit 1: add / mask side rows.  HEAD: fused 1x1 head on the 32 outputs.
 // ---------------------------------------------------------------------------------------------------------
-template <int EPI, bool HEAD>
+// F16: IEEE-half storage of activations / weights instead of bfloat16 (compile time: see conv_tc_kernel.cuh).
+template <int EPI, bool HEAD, bool F16 = false>
 __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_constant__ RowMaps tm, const ConvArgs a,
                                                                  const RowGeom g) {
   extern __shared__ uint8_t smem_raw[];
@@ -252,6 +253,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
       // works through the queued instructions. =====
       const uint32_t hi = ((uint32_t)(8 * 64) >> 4) | (1u << 14) | (4u << 29);  // SBO 512 B, 64-byte swizzle
       constexpr uint32_t LBO1 = 1u << 16;
+      constexpr bool f16_in = F16;
       mbar_wait(fullB, 0);
       tc_fence_after();
       const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | LBO1;
@@ -282,8 +284,8 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
         s.n1 = blk0 + nblk > (uint32_t)NBLK ? (uint32_t)NBLK - blk0 : nblk;
         s.n2 = nblk - s.n1;
         s.d1 = tmem_base + blk0 * 32u;
-        s.idesc1 = make_idesc((int)(32u * s.n1));
-        s.idesc2 = make_idesc((int)(32u * (s.n2 ? s.n2 : 1u)));
+        s.idesc1 = make_idesc((int)(32u * s.n1), f16_in);
+        s.idesc2 = make_idesc((int)(32u * (s.n2 ? s.n2 : 1u)), f16_in);
         s.q = q; s.c = c;
         s.stage = ra.idx; s.phase = ra.phase;
         ra.advance(g.na);
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
     const bool has_mask = E_AM && a.mask_src != nullptr;
     const bool stage_out = g.stage_out != 0;
     const bool side = EPI != 0 && g.n_side > 0;
+    constexpr bool f16 = F16;  // 16-bit storage format (bf16 otherwise)
     const int head_nc = HEAD ? a.head_nc : 0;
     float* tab = s_tab + warp * 128;  // [2 buffers][scale 32 | shift 32]
     // staging: this warp's NSLOT slots of [2 rows][32 pixels][64 B], 16-byte units XOR-swizzled like the TMA (64-byte mode)
@@ -476,8 +479,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
                   const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    v[8 * uu + 2 * e] = fmaxf(v[8 * uu + 2 * e], 0.f) + __uint_as_float(wv[e] << 16);
-                    v[8 * uu + 2 * e + 1] = fmaxf(v[8 * uu + 2 * e + 1], 0.f) + __uint_as_float(wv[e] & 0xFFFF0000u);
+                    const float2 rv = unpack_h2(wv[e], f16);
+                    v[8 * uu + 2 * e] = fmaxf(v[8 * uu + 2 * e], 0.f) + rv.x;
+                    v[8 * uu + 2 * e + 1] = fmaxf(v[8 * uu + 2 * e + 1], 0.f) + rv.y;
                   }
                 }
               }
@@ -488,8 +492,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
                   const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    v[8 * uu + 2 * e] += __uint_as_float(wv[e] << 16);
-                    v[8 * uu + 2 * e + 1] += __uint_as_float(wv[e] & 0xFFFF0000u);
+                    const float2 rv = unpack_h2(wv[e], f16);
+                    v[8 * uu + 2 * e] += rv.x;
+                    v[8 * uu + 2 * e + 1] += rv.y;
                   }
                 }
               }
@@ -500,8 +505,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
                   const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
-                    v[8 * uu + 2 * e] = __uint_as_float(wv[e] << 16) > 0.f ? v[8 * uu + 2 * e] : 0.f;
-                    v[8 * uu + 2 * e + 1] = __uint_as_float(wv[e] & 0xFFFF0000u) > 0.f ? v[8 * uu + 2 * e + 1] : 0.f;
+                    // sign test on the raw 16-bit patterns: valid for bf16 and IEEE half alike (x > 0 <=> int16(x) > 0)
+                    v[8 * uu + 2 * e] = (int)(wv[e] << 16) > 0 ? v[8 * uu + 2 * e] : 0.f;
+                    v[8 * uu + 2 * e + 1] = (int)(wv[e] & 0xFFFF0000u) > 0 ? v[8 * uu + 2 * e + 1] : 0.f;
                   }
                 }
               }
@@ -517,9 +523,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
 #pragma unroll
               for (int uu = 0; uu < 4; ++uu) {
                 uint4 pk;
-                __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(&pk);
+                uint32_t* hp = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) hp[e] = __floats2bfloat162_rn(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1]);
+                for (int e = 0; e < 4; ++e) hp[e] = pack_h2(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16);
                 *reinterpret_cast<uint4*>(ogen + (((uint32_t)uu ^ p_xor) << 4)) = pk;
               }
             }
@@ -655,9 +661,9 @@ bool plan_row(const ConvArgs& a, RowGeom* g, uint32_t* smem) {
   return true;
 }
 
-template <int EPI, bool HEAD>
+template <int EPI, bool HEAD, bool F16 = false>
 int set_attr_row() {
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_row_kernel<EPI, HEAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_row_kernel<EPI, HEAD, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return 0;
 }
 
@@ -682,6 +688,9 @@ int conv_row_init() {
     DG_TRY((set_attr_row<0, true>()));
     DG_TRY((set_attr_row<1, false>()));
     DG_TRY((set_attr_row<2, false>()));
+    DG_TRY((set_attr_row<0, false, true>()));
+    DG_TRY((set_attr_row<0, true, true>()));
+    DG_TRY((set_attr_row<1, false, true>()));
     dg_device_mark(g_dev_r, dev);
   }
   if (dev < 64) g_sms_r = g_dev_r.sms[dev];
@@ -695,7 +704,8 @@ int conv_row_init() {
 bool conv_row_supported(const ConvArgs& a) {
   static const bool off = getenv("DEPGAN_NO_ROW") != nullptr;  // A/B switch: every layer through conv_tc_kernel
   if (off) return false;
-  if (a.in_dt != DT_BF16 || a.out_dt != DT_BF16) return false;
+  if (!dt_is_half(a.in_dt) || a.out_dt != a.in_dt) return false;
+  if (a.in_dt == DT_F16 && (a.add_src || a.mask_src)) return false;  // IEEE half: the inference epilogues only
   if (a.ks != 3 || a.deconv || a.Cout != 32) return false;
   if (a.W % (2 * BW) || a.H < 1) return false;
   if (a.C0 % 32 || a.C1 % 32 || a.C0 < 32 || (a.C0 + a.C1) > 96) return false;
@@ -739,7 +749,11 @@ int conv_fwd_row(const ConvArgs& a, cudaStream_t st) {
   const int grid = want < g_sms_r ? (int)(want < 1 ? 1 : want) : g_sms_r;
   const int epi = a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : 0);
   cudaError_t e;
-  if (a.head_w) e = dg_launch_pdl(conv_row_kernel<0, true>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);
+  if (a.in_dt == DT_F16) {
+    if (a.head_w) e = dg_launch_pdl(conv_row_kernel<0, true, true>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);
+    else if (epi == 1) e = dg_launch_pdl(conv_row_kernel<1, false, true>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);
+    else e = dg_launch_pdl(conv_row_kernel<0, false, true>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);
+  } else if (a.head_w) e = dg_launch_pdl(conv_row_kernel<0, true>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);
   else if (epi == 1) e = dg_launch_pdl(conv_row_kernel<1, false>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);
   else if (epi == 2) e = dg_launch_pdl(conv_row_kernel<2, false>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);
   else e = dg_launch_pdl(conv_row_kernel<0, false>, dim3(grid), dim3(RW_THREADS), smem, st, tm, a, g);

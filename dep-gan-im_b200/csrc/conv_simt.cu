@@ -164,6 +164,13 @@ struct VecIO<2> {
   static __device__ __forceinline__ void store(float* p, const float (&v)[2]) {
     *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
   }
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[2]) {
+    const float2 a = unpack_h2(__ldg(reinterpret_cast<const uint32_t*>(p)), true);
+    v[0] = a.x; v[1] = a.y;
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[2]) {
+    *reinterpret_cast<uint32_t*>(p) = pack_h2(v[0], v[1], true);
+  }
 };
 template <>
 struct VecIO<4> {
@@ -186,6 +193,14 @@ struct VecIO<4> {
   }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[4]) {
+    const uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = unpack_h2(q.x, true), b = unpack_h2(q.y, true);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_h2(v[0], v[1], true), pack_h2(v[2], v[3], true));
   }
 };
 template <>
@@ -217,6 +232,19 @@ struct VecIO<8> {
     float4* q = reinterpret_cast<float4*>(p);
     q[0] = make_float4(v[0], v[1], v[2], v[3]);
     q[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_h2(w[i], true);
+      v[2 * i] = f.x; v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_h2(v[0], v[1], true), pack_h2(v[2], v[3], true),
+                                              pack_h2(v[4], v[5], true), pack_h2(v[6], v[7], true));
   }
 };
 
@@ -677,11 +705,17 @@ int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
       const int r0 = conv_first_tc_try(a, st);
       if (r0 != 0) return r0 < 0 ? r0 : 0;
     }
-    const int r = a.out_dt == DT_BF16 ? try_first<bf16>(a, st) : try_first<float>(a, st);
+    const int r = a.out_dt == DT_BF16 ? try_first<bf16>(a, st)
+                  : a.out_dt == DT_F16 ? try_first<__half>(a, st) : try_first<float>(a, st);
     if (r != 0) return r < 0 ? r : 0;
-    const int r2 = a.in_dt == DT_BF16 ? try_last<bf16>(a, st) : try_last<float>(a, st);
-    if (r2 != 0) return r2 < 0 ? r2 : 0;
+    if (a.in_dt != DT_F16) {
+      const int r2 = a.in_dt == DT_BF16 ? try_last<bf16>(a, st) : try_last<float>(a, st);
+      if (r2 != 0) return r2 < 0 ? r2 : 0;
+    }
   }
+  // IEEE-half handles (generator inference): first layer (fp32 image in) and the levels below 16x16
+  if (a.in_dt == DT_F32 && a.out_dt == DT_F16) return launch_fwd<float, __half>(a, st);
+  if (a.in_dt == DT_F16 && a.out_dt == DT_F16) return launch_fwd<__half, __half>(a, st);
   if (a.in_dt == DT_F32 && a.out_dt == DT_F32) return launch_fwd<float, float>(a, st);
   if (a.in_dt == DT_F32 && a.out_dt == DT_BF16) return launch_fwd<float, bf16>(a, st);
   if (a.in_dt == DT_BF16 && a.out_dt == DT_BF16) return launch_fwd<bf16, bf16>(a, st);

@@ -187,11 +187,15 @@ int conv_tc_init() {
 }
 
 bool conv_tc_supported(const ConvArgs& a) {
-  return conv_row_supported(a) || tile_kernel_supported(a);  // conv_row.cu takes the 32-channel full-width 3x3 layers
+  // conv_row.cu takes the 32-channel full-width 3x3 layers, conv_rowg.cu the critics' 5x5 and the 64-channel 3x3 layers
+  return conv_row_supported(a) || conv_rowg_supported(a) || tile_kernel_supported(a);
 }
 
 static bool tile_kernel_supported(const ConvArgs& a) {
-  if (a.in_dt != DT_BF16 || a.out_dt != DT_BF16) return false;
+  if (!dt_is_half(a.in_dt) || a.out_dt != a.in_dt) return false;
+  // IEEE-half storage is instantiated for what generator inference runs: plain / FiLM 3x3 layers and the transposed conv
+  if (a.in_dt == DT_F16 && (a.add_src || a.mask_src || a.pool_out || a.out_pre || !(a.ks == 3 || (a.ks == 1 && !a.film_g))))
+    return false;
   if (a.ks != 1 && a.ks != 3 && a.ks != 5) return false;
   if (a.deconv && a.ks != 1) return false;
   if (a.H % 16 || a.W % 16 || a.H < 16 || a.W < 16) return false;
@@ -224,6 +228,7 @@ bool conv_tc_plan_query(const ConvArgs& a, int* o) {
 int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   if (a.N <= 0) return 0;
   if (conv_row_supported(a)) return conv_fwd_row(a, st);
+  if (conv_rowg_supported(a)) return conv_fwd_rowg(a, st);
   DG_TRY(conv_tc_init());
   TcGeom g;
   uint32_t smem;
@@ -253,7 +258,7 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   const int n_items = g.tiles_w * g.tiles_h * a.N * (g.ncols_total / g.ncta);
   const int grid = n_items < g_num_sms ? n_items : g_num_sms;
   // side inputs the epilogue has to stream (selects the EPI instantiation): 1 FiLM residual, 2 add / mask
-  const int need = a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : (a.pool_out ? 4 : 0));
+  const int need = (a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : (a.pool_out ? 4 : 0))) + (a.in_dt == DT_F16 ? 8 : 0);
   int rc;
   switch (a.ks) {
     case 1: rc = launch_ks1(grid, smem, st, tm, a, g, need); break;

@@ -8,6 +8,7 @@ int launch_ks1(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const
   switch (epi * 100 + (g.kc / 16) * 10 + (g.b_resident ? 1 : 0)) {
     DG_TC_CASES(1, 0)
     DG_TC_CASES(1, 2)
+    DG_TC_CASES_F16(1, 0)
     default: depgan_set_error("conv_fwd_tc: no kernel for this (ks, kc, epi)"); return -2;
   }
 }
@@ -15,6 +16,7 @@ int launch_ks1(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const
 int set_attrs_ks1() {
   DG_TC_ATTRS(1, 0)
   DG_TC_ATTRS(1, 2)
+  DG_TC_ATTRS_F16(1, 0)
   return 0;
 }
 

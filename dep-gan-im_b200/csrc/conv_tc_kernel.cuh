@@ -182,13 +182,29 @@ __device__ __forceinline__ void tc_ld_wait4(uint32_t (&r)[4][16]) {
                     "+r"(r[3][12]), "+r"(r[3][13]), "+r"(r[3][14]), "+r"(r[3][15]) :: "memory");
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16 (format 1) or IEEE half (format 0), both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc(int n, bool f16 = false) {
+  const uint32_t ab = f16 ? 0u : ((1u << 7) | (1u << 10));
+  return (1u << 4) | ab | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-struct Packed16 {  // 16 bf16 values as loaded (two 128-bit words)
+struct Packed16 {  // 16 half-precision values as loaded (two 128-bit words); get() decodes bf16, unpack() either format
   uint4 q[2];
+  __device__ __forceinline__ void unpack(float (&s)[16], bool f16) const {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(q);
+    if (f16) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        s[2 * i] = f.x; s[2 * i + 1] = f.y;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[2 * i] = __uint_as_float(w[i] << 16); s[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+      }
+    }
+  }
   __device__ __forceinline__ void load(const void* base, size_t elem_off) {
     const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + elem_off);
     q[0] = __ldg(p);
@@ -199,15 +215,15 @@ struct Packed16 {  // 16 bf16 values as loaded (two 128-bit words)
     return __uint_as_float((i & 1) ? (w & 0xFFFF0000u) : (w << 16));
   }
 };
-__device__ __forceinline__ void st16_bf16(void* base, size_t elem_off, const float (&v)[16]) {
+__device__ __forceinline__ void st16_bf16(void* base, size_t elem_off, const float (&v)[16], bool f16 = false) {
 #ifdef DG_DBG_NOSTORE  // timing experiment only: keeps the values alive without a global store
   if (v[0] == 1.2345e-30f && v[7] == 5.4321e-30f) reinterpret_cast<float*>(base)[0] = v[3];
   return;
 #endif
   uint4 q[2];
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(q);
+  uint32_t* h = reinterpret_cast<uint32_t*>(q);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  for (int i = 0; i < 8; ++i) h[i] = pack_h2(v[2 * i], v[2 * i + 1], f16);
   uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + elem_off);
   p[0] = q[0];
   p[1] = q[1];
@@ -300,7 +316,9 @@ __device__ __forceinline__ bool elect_one() {
 //   epilogue warps 0..7 (warp w reads TMEM lane quarter w%4 of strip w/4), running with the registers the control
 //     warpgroup gave up.
 // ---------------------------------------------------------------------------------------------------------
-template <int KS, int KSTEPS, bool RES, int EPI>
+// F16: the 16-bit storage format of activations and weights is IEEE half instead of bfloat16 (generator inference handles,
+// DEPGAN_PREC_F16); a template parameter, because a run-time flag doubles the pack / unpack instructions of the epilogue.
+template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps tm, const ConvArgs a,
                                                                 const TcGeom g) {
   constexpr int PAD = KS / 2, HT = 16 + KS - 1, TAPS = KS * KS;
@@ -460,7 +478,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int m = warp == CTRL_W0 + 1 ? 0 : 1;
     const int nI = g.n_issuers;
     if (m < nI) {
-    const uint32_t idesc = make_idesc(g.ncta);
+    const uint32_t idesc = make_idesc(g.ncta, F16);
     const uint32_t hiA = ((uint32_t)(HT * rowb) >> 4) | (1u << 14) | (g.layout << 29);
     const uint32_t hiB = ((uint32_t)(8 * rowb) >> 4) | (1u << 14) | (g.layout << 29);
     constexpr uint32_t LBO1 = 1u << 16;
@@ -567,6 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const bool side = EPI != 0 && g.n_side > 0;
     const bool stage_out = g.stage_out != 0;
     const bool t0 = threadIdx.x == EPI_W0 * 32;  // issues the TMA stores
+    constexpr bool f16 = F16;                    // 16-bit storage format of the activations (bf16 otherwise)
     // this thread's pixel in a staging tile [16 rows][16 cols][ch] whose 16-byte units are XOR-swizzled like the TMA
     // (unit j of the pixel at byte offset o lives at o + ((j ^ ((o >> 7) & (units-1))) << 4)): conflict-free 128-bit
     // accesses for 8 neighbouring pixels
@@ -646,19 +665,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             float vp[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) vp[i] = fmaf(v[i], s_scale[col + i], s_shift[col + i]);
-            st16_bf16(a.out_pre, pix0 * Cout + col, vp);
+            st16_bf16(a.out_pre, pix0 * Cout + col, vp, f16);
           }
           Packed16 rs16;
           rs16.q[0] = *reinterpret_cast<const uint4*>(sgen + u0);
           rs16.q[1] = *reinterpret_cast<const uint4*>(sgen + u1);
+          float rsv[16];
+          rs16.unpack(rsv, f16);
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
             const float4 sc = reinterpret_cast<const float4*>(sF + gi * 16)[i4];
             const float4 sh = reinterpret_cast<const float4*>(sF + g.ncta + gi * 16)[i4];
-            v[4 * i4 + 0] = fmaxf(fmaf(v[4 * i4 + 0], sc.x, sh.x), 0.f) + rs16.get(4 * i4 + 0);
-            v[4 * i4 + 1] = fmaxf(fmaf(v[4 * i4 + 1], sc.y, sh.y), 0.f) + rs16.get(4 * i4 + 1);
-            v[4 * i4 + 2] = fmaxf(fmaf(v[4 * i4 + 2], sc.z, sh.z), 0.f) + rs16.get(4 * i4 + 2);
-            v[4 * i4 + 3] = fmaxf(fmaf(v[4 * i4 + 3], sc.w, sh.w), 0.f) + rs16.get(4 * i4 + 3);
+            v[4 * i4 + 0] = fmaxf(fmaf(v[4 * i4 + 0], sc.x, sh.x), 0.f) + rsv[4 * i4 + 0];
+            v[4 * i4 + 1] = fmaxf(fmaf(v[4 * i4 + 1], sc.y, sh.y), 0.f) + rsv[4 * i4 + 1];
+            v[4 * i4 + 2] = fmaxf(fmaf(v[4 * i4 + 2], sc.z, sh.z), 0.f) + rsv[4 * i4 + 2];
+            v[4 * i4 + 3] = fmaxf(fmaf(v[4 * i4 + 3], sc.w, sh.w), 0.f) + rsv[4 * i4 + 3];
           }
         } else {
 #pragma unroll
@@ -670,21 +691,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
             v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
           }
-          if (a.out_pre) st16_bf16(a.out_pre, pix0 * Cout + col, v);
+          if (a.out_pre) st16_bf16(a.out_pre, pix0 * Cout + col, v, f16);
         }
         if (has_add) {
           Packed16 ad;
           ad.q[0] = *reinterpret_cast<const uint4*>(sgen + add_slot + u0);
           ad.q[1] = *reinterpret_cast<const uint4*>(sgen + add_slot + u1);
+          float adv[16];
+          ad.unpack(adv, f16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += ad.get(i);
+          for (int i = 0; i < 16; ++i) v[i] += adv[i];
         }
         if (has_mask) {
           Packed16 mk;
           mk.q[0] = *reinterpret_cast<const uint4*>(sgen + mask_slot + u0);
           mk.q[1] = *reinterpret_cast<const uint4*>(sgen + mask_slot + u1);
+          float mkv[16];
+          mk.unpack(mkv, f16);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = mk.get(i) > 0.f ? v[i] : 0.f;
+          for (int i = 0; i < 16; ++i) v[i] = mkv[i] > 0.f ? v[i] : 0.f;
         }
         if (a.relu) {
 #pragma unroll
@@ -692,9 +717,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         if (stage_out) {
           uint4 pk[2];
-          __nv_bfloat162* hp = reinterpret_cast<__nv_bfloat162*>(pk);
+          uint32_t* hp = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) hp[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+          for (int i = 0; i < 8; ++i) hp[i] = pack_h2(v[2 * i], v[2 * i + 1], f16);
           uint8_t* ogen = smem_raw + (o_base + oslot * g.slot_bytes - raw);
           *reinterpret_cast<uint4*>(ogen + u0) = pk[0];
           *reinterpret_cast<uint4*>(ogen + u1) = pk[1];
@@ -705,11 +730,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               uint32_t o = __shfl_xor_sync(0xffffffffu, w8[i], 1);
-              __nv_bfloat162 m = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w8[i]), *reinterpret_cast<__nv_bfloat162*>(&o));
-              uint32_t mw = *reinterpret_cast<uint32_t*>(&m);
+              const uint32_t mw = max_h2(w8[i], o, f16);
               o = __shfl_xor_sync(0xffffffffu, mw, 8);
-              m = __hmax2(m, *reinterpret_cast<__nv_bfloat162*>(&o));
-              w8[i] = *reinterpret_cast<uint32_t*>(&m);
+              w8[i] = max_h2(mw, o, f16);
             }
             if ((lane & 9) == 0) {
               const uint32_t pp = (uint32_t)((ty >> 1) * 8 + (tx >> 1)) * (uint32_t)(g.ch * 2);
@@ -847,15 +870,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 }
 
 // ---- instantiation helpers used by conv_tc_k{1,3,5}.cu ----
-template <int KS, int KSTEPS, bool RES, int EPI>
+template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false>
 int launch_one(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g) {
-  DG_CHECK_CUDA(dg_launch_pdl(conv_tc_kernel<KS, KSTEPS, RES, EPI>, dim3(grid), dim3(TC_THREADS), smem, st, tm, a, g));
+  DG_CHECK_CUDA(dg_launch_pdl(conv_tc_kernel<KS, KSTEPS, RES, EPI, F16>, dim3(grid), dim3(TC_THREADS), smem, st, tm, a, g));
   DG_LAUNCH_CHECK();
   return 0;
 }
-template <int KS, int KSTEPS, bool RES, int EPI>
+template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false>
 int set_attr_one() {
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, KSTEPS, RES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, KSTEPS, RES, EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024 - DG_TRACE_SMEM));
   return 0;
 }
@@ -875,6 +898,21 @@ int set_attr_one() {
   DG_TRY((set_attr_one<KS_, 2, true, EPI_>()));       \
   DG_TRY((set_attr_one<KS_, 4, false, EPI_>()));      \
   DG_TRY((set_attr_one<KS_, 4, true, EPI_>()));
+// IEEE-half instantiations (generator inference: plain and FiLM 3x3 layers, transposed conv): key = epi + 8
+#define DG_TC_CASES_F16(KS_, EPI_)                                                                 \
+  case (EPI_ + 8) * 100 + 10: return launch_one<KS_, 1, false, EPI_, true>(grid, smem, st, tm, a, g); \
+  case (EPI_ + 8) * 100 + 11: return launch_one<KS_, 1, true, EPI_, true>(grid, smem, st, tm, a, g);  \
+  case (EPI_ + 8) * 100 + 20: return launch_one<KS_, 2, false, EPI_, true>(grid, smem, st, tm, a, g); \
+  case (EPI_ + 8) * 100 + 21: return launch_one<KS_, 2, true, EPI_, true>(grid, smem, st, tm, a, g);  \
+  case (EPI_ + 8) * 100 + 40: return launch_one<KS_, 4, false, EPI_, true>(grid, smem, st, tm, a, g); \
+  case (EPI_ + 8) * 100 + 41: return launch_one<KS_, 4, true, EPI_, true>(grid, smem, st, tm, a, g);
+#define DG_TC_ATTRS_F16(KS_, EPI_)                          \
+  DG_TRY((set_attr_one<KS_, 1, false, EPI_, true>()));      \
+  DG_TRY((set_attr_one<KS_, 1, true, EPI_, true>()));       \
+  DG_TRY((set_attr_one<KS_, 2, false, EPI_, true>()));      \
+  DG_TRY((set_attr_one<KS_, 2, true, EPI_, true>()));       \
+  DG_TRY((set_attr_one<KS_, 4, false, EPI_, true>()));      \
+  DG_TRY((set_attr_one<KS_, 4, true, EPI_, true>()));
 #endif  // __CUDACC__
 
 }  // namespace convtc

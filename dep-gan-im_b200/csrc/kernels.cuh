@@ -9,7 +9,7 @@ int k_fold_bn(const float* bias, const float* gamma, const float* beta, const fl
 // dst_tc[tap][co][ci] (bf16) and dst_dgrad[flip(tap)][co][ci] (fp32) from src HWIO [tap][ci][co]
 // (dgrad variants: taps flipped, multiplied by scale[co] when scale != nullptr)
 int k_pack_conv_weights(const float* src, const float* scale, bf16* dst_tc, float* dst_dgrad, bf16* dst_tc_dgrad,
-                        int taps, int Cin, int Cout, cudaStream_t st);
+                        int taps, int Cin, int Cout, cudaStream_t st, int f16 = 0);  // f16: IEEE half in the 16-bit slots
 
 // ---- forward -----------------------------------------------------------------------------------------
 int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt, cudaStream_t st);

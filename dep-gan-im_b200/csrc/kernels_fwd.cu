@@ -35,21 +35,27 @@ __global__ void fold_bn_kernel(const float* bias, const float* gamma, const floa
   }
 }
 
+__device__ __forceinline__ bf16 w16(float v, bool f16) {  // weight in the handle's 16-bit format, carried in a bf16 slot
+  if (!f16) return __float2bfloat16_rn(v);
+  const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  return *reinterpret_cast<const bf16*>(&h);
+}
+
 __global__ void pack_conv_kernel(const float* src, const float* scale, bf16* dst_tc, float* dst_dgrad,
-                                 bf16* dst_tc_dgrad, int taps, int Cin, int Cout) {
+                                 bf16* dst_tc_dgrad, int taps, int Cin, int Cout, int f16) {
   size_t total = (size_t)taps * Cin * Cout;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int co = i % Cout;
     int ci = (i / Cout) % Cin;
     int tap = i / ((size_t)Cout * Cin);
     float v = src[i];
-    if (dst_tc) dst_tc[((size_t)tap * Cout + co) * Cin + ci] = __float2bfloat16_rn(v);
+    if (dst_tc) dst_tc[((size_t)tap * Cout + co) * Cin + ci] = w16(v, f16 != 0);
     // data-gradient operands: spatially flipped taps, in/out channels swapped, BN scale of the forward
     // output channel folded in (it multiplies dy before the contraction)
     int ft = taps - 1 - tap;
     const float vs = scale ? v * scale[co] : v;
     if (dst_dgrad) dst_dgrad[((size_t)ft * Cout + co) * Cin + ci] = vs;
-    if (dst_tc_dgrad) dst_tc_dgrad[((size_t)ft * Cin + ci) * Cout + co] = __float2bfloat16_rn(vs);
+    if (dst_tc_dgrad) dst_tc_dgrad[((size_t)ft * Cin + ci) * Cout + co] = w16(vs, f16 != 0);
   }
 }
 
@@ -104,7 +110,8 @@ __global__ void maxpool_fwd_kernel(const T* in, T* out, int N, int H, int W, int
   }
 }
 
-// bf16 max-pool, 8 channels (128 bits) per thread: 4 vector loads, 1 vector store
+// bf16 / fp16 max-pool, 8 channels (128 bits) per thread: 4 vector loads, 1 vector store
+template <typename H2>
 __global__ void maxpool_fwd_bf16x8_kernel(const uint4* in, uint4* out, int N, int H, int W, int C8) {
   const int Ho = H / 2, Wo = W / 2;
   const size_t total = (size_t)N * Ho * Wo * C8;
@@ -116,13 +123,13 @@ __global__ void maxpool_fwd_bf16x8_kernel(const uint4* in, uint4* out, int N, in
     const uint4* b = in + (((size_t)n * H + 2 * ho) * W + 2 * wo) * C8 + c;
     uint4 q[4] = {__ldg(b), __ldg(b + C8), __ldg(b + (size_t)W * C8), __ldg(b + (size_t)W * C8 + C8)};
     uint4 r;
-    __nv_bfloat162* rr = reinterpret_cast<__nv_bfloat162*>(&r);
+    H2* rr = reinterpret_cast<H2*>(&r);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat162 a0 = reinterpret_cast<const __nv_bfloat162*>(&q[0])[k];
-      const __nv_bfloat162 a1 = reinterpret_cast<const __nv_bfloat162*>(&q[1])[k];
-      const __nv_bfloat162 a2 = reinterpret_cast<const __nv_bfloat162*>(&q[2])[k];
-      const __nv_bfloat162 a3 = reinterpret_cast<const __nv_bfloat162*>(&q[3])[k];
+      const H2 a0 = reinterpret_cast<const H2*>(&q[0])[k];
+      const H2 a1 = reinterpret_cast<const H2*>(&q[1])[k];
+      const H2 a2 = reinterpret_cast<const H2*>(&q[2])[k];
+      const H2 a3 = reinterpret_cast<const H2*>(&q[3])[k];
       rr[k] = __hmax2(__hmax2(a0, a1), __hmax2(a2, a3));
     }
     out[i] = r;
@@ -466,10 +473,10 @@ int k_fold_bn(const float* bias, const float* gamma, const float* beta, const fl
 }
 
 int k_pack_conv_weights(const float* src, const float* scale, bf16* dst_tc, float* dst_dgrad, bf16* dst_tc_dgrad,
-                        int taps, int Cin, int Cout, cudaStream_t st) {
+                        int taps, int Cin, int Cout, cudaStream_t st, int f16) {
   if (!dst_tc && !dst_dgrad && !dst_tc_dgrad) return 0;
   pack_conv_kernel<<<grid_for((long long)taps * Cin * Cout), 256, 0, st>>>(src, scale, dst_tc, dst_dgrad, dst_tc_dgrad,
-                                                                         taps, Cin, Cout);
+                                                                         taps, Cin, Cout, f16);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -488,9 +495,14 @@ int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt,
   if (total == 0) return 0;
   if (dt == DT_F32)
     maxpool_fwd_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)in, (float*)out, N, H, W, C);
+  else if (C % 8 == 0 && dt == DT_F16)
+    maxpool_fwd_bf16x8_kernel<__half2><<<grid_for(total / 8, 256, 148 * 32), 256, 0, st>>>((const uint4*)in, (uint4*)out,
+                                                                                          N, H, W, C / 8);
   else if (C % 8 == 0)
-    maxpool_fwd_bf16x8_kernel<<<grid_for(total / 8, 256, 148 * 32), 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W,
-                                                                                 C / 8);
+    maxpool_fwd_bf16x8_kernel<__nv_bfloat162><<<grid_for(total / 8, 256, 148 * 32), 256, 0, st>>>(
+        (const uint4*)in, (uint4*)out, N, H, W, C / 8);
+  else if (dt == DT_F16)
+    maxpool_fwd_kernel<__half><<<grid_for(total), 256, 0, st>>>((const __half*)in, (__half*)out, N, H, W, C);
   else
     maxpool_fwd_kernel<bf16><<<grid_for(total), 256, 0, st>>>((const bf16*)in, (bf16*)out, N, H, W, C);
   DG_LAUNCH_CHECK();
@@ -506,6 +518,9 @@ int k_deconv_fwd(const void* in, const float* w, const float* scale, const float
   if (dt == DT_F32)
     deconv_fwd_kernel<float><<<grid, 128, smem, st>>>((const float*)in, w, scale, shift, (float*)out, N, H, W, Cin, Cout,
                                                       relu);
+  else if (dt == DT_F16)
+    deconv_fwd_kernel<__half><<<grid, 128, smem, st>>>((const __half*)in, w, scale, shift, (__half*)out, N, H, W, Cin,
+                                                       Cout, relu);
   else
     deconv_fwd_kernel<bf16><<<grid, 128, smem, st>>>((const bf16*)in, w, scale, shift, (bf16*)out, N, H, W, Cin, Cout,
                                                      relu);
@@ -520,6 +535,8 @@ int k_head_fwd(const void* in, const float* w, const float* b, float* out, long 
   int grid = (int)((npix + 127) / 128);
   if (dt == DT_F32)
     head_fwd_kernel<float><<<grid, 128, 0, st>>>((const float*)in, w, b, out, npix, Cin, nc_out, head);
+  else if (dt == DT_F16)
+    head_fwd_kernel<__half><<<grid, 128, 0, st>>>((const __half*)in, w, b, out, npix, Cin, nc_out, head);
   else
     head_fwd_kernel<bf16><<<grid, 128, 0, st>>>((const bf16*)in, w, b, out, npix, Cin, nc_out, head);
   DG_LAUNCH_CHECK();
@@ -555,6 +572,8 @@ int k_convert_in(const float* src, void* dst, long long n, int dt, cudaStream_t 
   if (n == 0) return 0;
   if (dt == DT_F32)
     convert_in_kernel<float><<<grid_for(n), 256, 0, st>>>(src, (float*)dst, n);
+  else if (dt == DT_F16)
+    convert_in_kernel<__half><<<grid_for(n), 256, 0, st>>>(src, (__half*)dst, n);
   else
     convert_in_kernel<bf16><<<grid_for(n), 256, 0, st>>>(src, (bf16*)dst, n);
   DG_LAUNCH_CHECK();

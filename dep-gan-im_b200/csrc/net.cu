@@ -114,7 +114,10 @@ int check_cfg(int model, const depgan_cfg* cfg) {
   DG_REQUIRE(model == DEPGAN_MODEL_GEN || model == DEPGAN_MODEL_CRITIC, "unknown model id");
   DG_REQUIRE(cfg->H >= 16 && cfg->W >= 16 && cfg->H % 16 == 0 && cfg->W % 16 == 0, "H, W must be multiples of 16");
   DG_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
-  DG_REQUIRE(cfg->precision == DEPGAN_PREC_FP32 || cfg->precision == DEPGAN_PREC_BF16, "unknown precision");
+  DG_REQUIRE(cfg->precision == DEPGAN_PREC_FP32 || cfg->precision == DEPGAN_PREC_BF16 ||
+                 cfg->precision == DEPGAN_PREC_F16, "unknown precision");
+  DG_REQUIRE(cfg->precision != DEPGAN_PREC_F16 || (model == DEPGAN_MODEL_GEN && cfg->training == 0),
+             "DEPGAN_PREC_F16 is the inference format of the generator (training handles keep the bf16 range)");
   if (model == DEPGAN_MODEL_GEN) {
     DG_REQUIRE(cfg->nicg >= 1 && cfg->nicg <= 8, "nicg must be 1..8");
     DG_REQUIRE(cfg->nc_out >= 1 && cfg->nc_out <= 4, "nc_out must be 1..4");
@@ -150,7 +153,7 @@ void alloc_conv_derived(depgan_net* h, ConvL& L, Bump& b) {
   L.scale = b.arr<float>(L.cout);
   L.shift = b.arr<float>(L.cout);
   const size_t nw = (size_t)L.taps() * L.cin * L.cout;
-  if (h->act_dt == DT_BF16) L.w_tc = b.arr<bf16>(nw);
+  if (dt_is_half(h->act_dt)) L.w_tc = b.arr<bf16>(nw);  // 16-bit slots: bf16, or IEEE half for DT_F16 handles
   if (h->cfg.training) {
     L.inv_std = b.arr<float>(L.cout);
     L.w_dg = b.arr<float>(nw);
@@ -253,13 +256,13 @@ int fold_conv(depgan_net* h, ConvL& L, cudaStream_t st) {
   DG_TRY(k_fold_bn(h->P(L.b_off), h->P(L.g_off), h->P(L.be_off), h->P(L.mu_off), h->P(L.var_off), L.scale, L.shift,
                    L.inv_std, L.cout, st));
   if (L.deconv) {
-    if (L.w_tc) DG_TRY(k_convert_in(h->P(L.k_off), L.w_tc, (long long)4 * L.cin * L.cout, DT_BF16, st));
+    if (L.w_tc) DG_TRY(k_convert_in(h->P(L.k_off), L.w_tc, (long long)4 * L.cin * L.cout, h->act_dt, st));
     DG_TRY(k_pack_deconv_dgrad(h->P(L.k_off), h->cfg.training == 2 ? nullptr : L.scale, L.w_dg, L.w_dg_tc, L.cin,
                                L.cout, st));
   } else {
     // training == 2 (Keras training phase): BN is applied after the raw convolution, so dgrad weights stay unscaled
     DG_TRY(k_pack_conv_weights(h->P(L.k_off), h->cfg.training == 2 ? nullptr : L.scale, L.w_tc, L.w_dg, L.w_dg_tc,
-                               L.ks * L.ks, L.cin, L.cout, st));
+                               L.ks * L.ks, L.cin, L.cout, st, h->act_dt == DT_F16));
   }
   return 0;
 }
@@ -320,13 +323,13 @@ int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void*
   a.shift = L.shift;
   a.N = n; a.H = h->lvl_h(L.lvl); a.W = h->lvl_w(L.lvl); a.Cout = L.cout; a.ks = L.ks;
   a.in_dt = in_dt; a.out_dt = h->act_dt;
-  if (a.pool_out && !(h->act_dt == DT_BF16 && conv_tc_supported(a))) {  // unfused fallback: conv, then the pool
+  if (a.pool_out && !(dt_is_half(h->act_dt) && conv_tc_supported(a))) {  // unfused fallback: conv, then the pool
     void* pool_out = a.pool_out;
     a.pool_out = nullptr;
     DG_TRY(net_conv(h, L, in0, C0, in1, C1, in_dt, a, n, st));
     return k_maxpool_fwd(a.out, pool_out, n, a.H, a.W, a.Cout, h->act_dt, st);
   }
-  const bool tc = h->act_dt == DT_BF16 && conv_tc_supported(a);
+  const bool tc = dt_is_half(h->act_dt) && conv_tc_supported(a);
   ProfScope prof(a, tc, st);
   if (tc) return conv_fwd_tc(a, st);
   if (a.head_w) {  // unfused fallback: conv, then the 1x1 head
@@ -341,10 +344,10 @@ int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void*
 
 static int net_deconv(depgan_net* h, const ConvL& L, const void* in, void* out, int n, cudaStream_t st) {
   const int H = h->lvl_h(L.lvl), W = h->lvl_w(L.lvl);
-  if (h->act_dt == DT_BF16) {
+  if (dt_is_half(h->act_dt)) {
     ConvArgs a{};
     a.in0 = in; a.C0 = L.cin; a.w_tc = L.w_tc; a.scale = L.scale; a.shift = L.shift; a.out = out; a.relu = 1;
-    a.deconv = 1; a.N = n; a.H = H; a.W = W; a.Cout = L.cout; a.ks = 1; a.in_dt = DT_BF16; a.out_dt = DT_BF16;
+    a.deconv = 1; a.N = n; a.H = H; a.W = W; a.Cout = L.cout; a.ks = 1; a.in_dt = h->act_dt; a.out_dt = h->act_dt;
     if (conv_tc_supported(a)) {
       ProfScope prof(a, true, st);
       return conv_fwd_tc(a, st);
@@ -387,7 +390,7 @@ int gen_forward_impl(depgan_net* g, const float* x, const float* z, float* out, 
     if (bi == 6) {                                                       // + gen_segmentation 1x1 + tanh/softmax
       e.head_w = g->P(g->g_seg.k_off); e.head_b = g->P(g->g_seg.b_off); e.head_out = out;
       e.head_nc = c.nc_out; e.head_act = c.nc_out == 1 ? 0 : 1;
-      if (!keep && g->act_dt == DT_BF16) e.out = nullptr;                // inference: gen_17 never leaves the SM
+      if (!keep && dt_is_half(g->act_dt)) e.out = nullptr;                // inference: gen_17 never leaves the SM
     }
     // MaxPooling2D (TG:409): fused into the epilogue of the block's last conv for training handles (the per-launch
     // profile counts those launches as their own class, 6, with the pooled bytes included).  Inference handles keep
@@ -463,7 +466,7 @@ long long depgan_workspace_bytes(int model, const depgan_cfg* cfg) {
   if (check_cfg(model, cfg)) return -2;
   depgan_net h;
   h.model = model; h.cfg = *cfg; h.man = build_manifest(model, *cfg);
-  h.act_dt = cfg->precision == DEPGAN_PREC_BF16 ? DT_BF16 : DT_F32;
+  h.act_dt = cfg->precision == DEPGAN_PREC_BF16 ? DT_BF16 : cfg->precision == DEPGAN_PREC_F16 ? DT_F16 : DT_F32;
   h.es = dt_size(h.act_dt);
   Bump b;
   if (layout_net(&h, b)) return -2;
@@ -483,7 +486,7 @@ depgan_net* depgan_net_create(int model, const depgan_cfg* cfg, float* params_de
   depgan_net* h = new depgan_net();
   h->model = model; h->cfg = *cfg; h->man = build_manifest(model, *cfg);
   h->params = params_dev; h->grads = grads_dev;
-  h->act_dt = cfg->precision == DEPGAN_PREC_BF16 ? DT_BF16 : DT_F32;
+  h->act_dt = cfg->precision == DEPGAN_PREC_BF16 ? DT_BF16 : cfg->precision == DEPGAN_PREC_F16 ? DT_F16 : DT_F32;
   h->es = dt_size(h->act_dt);
   Bump b;
   b.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));
@@ -493,7 +496,7 @@ depgan_net* depgan_net_create(int model, const depgan_cfg* cfg, float* params_de
     delete h;
     return nullptr;
   }
-  if (h->act_dt == DT_BF16 && conv_tc_init()) { delete h; return nullptr; }
+  if (dt_is_half(h->act_dt) && conv_tc_init()) { delete h; return nullptr; }
   return h;
 }
 

@@ -95,7 +95,7 @@ class _Obj:
             try:
                 out[name] = self.f._decode(dt, sp, d[pos:])
             except H5Error:
-                out[name] = None  # e.g. variable-length model_config: not needed for loading weights
+                out[name] = None  # a datatype outside the subset: not needed for loading weights
         return out
 
     # ---- datasets ----
@@ -243,12 +243,37 @@ class File(_Obj):
             return np.dtype("%s%s%d" % ("<", "i" if dt[1] & 8 else "u", size)), None
         if cls == 3:
             return np.dtype("S%d" % size), None
+        if cls == 9 and (bits0 & 0x0F) == 1:
+            return np.dtype("V16"), "vlen_str"  # (length u32, global heap address u64, object index u32)
         raise H5Error("datatype class %d is not supported" % cls)
+
+    def _global_heap_object(self, addr, index):
+        """Object `index` of the global heap collection at `addr` (variable-length data: Keras' model_config /
+        training_config, which h5py stores as H5T_VARIABLE strings)."""
+        b = self.buf
+        if b[addr:addr + 4] != b"GCOL":
+            raise H5Error("bad global heap collection")
+        (size,) = struct.unpack_from("<Q", b, addr + 8)
+        pos, end = addr + 16, addr + size
+        while pos + 16 <= end:
+            idx, _, osize = struct.unpack_from("<HH4xQ", b, pos)
+            if idx == 0:
+                break  # free space: no further objects
+            if idx == index:
+                return b[pos + 16:pos + 16 + osize]
+            pos += 16 + ((osize + 7) & ~7)
+        raise H5Error("global heap object %d not found" % index)
 
     def _decode(self, dt, sp, data):
         shape = self._shape(sp)
-        dtype, _ = self._dtype(dt)
+        dtype, kind = self._dtype(dt)
         n = int(np.prod(shape, dtype=np.int64)) if shape else 1
+        if kind == "vlen_str":
+            vals = []
+            for i in range(n):
+                ln, gaddr, gidx = struct.unpack_from("<IQI", data, 16 * i)
+                vals.append(b"" if ln == 0 else self._global_heap_object(gaddr, gidx)[:ln])
+            return np.array(vals, dtype=object).reshape(shape) if shape else vals[0]
         arr = np.frombuffer(data[:n * dtype.itemsize], dtype=dtype)
         return arr.reshape(shape).copy() if shape else arr[0]
 
@@ -279,6 +304,23 @@ def read_keras_file(path):
         wn = _names_attr(lg.attrs(), "weight_names")
         out[ln] = [(w, lg[w].read()) for w in wn]
     return layers, out
+
+
+def read_keras_configs(path):
+    """-> (model_config, training_config) of a Keras full-model file as parsed JSON (None when absent): the attributes
+    `model.save` writes next to /model_weights (TG:892, TU:622) and `keras.models.load_model` reads back."""
+    import json
+    attrs = File(path).attrs()
+    out = []
+    for key in ("model_config", "training_config"):
+        v = attrs.get(key)
+        if v is None:
+            out.append(None)
+            continue
+        if isinstance(v, np.ndarray):
+            v = v.ravel()[0]
+        out.append(json.loads(v.decode("utf8") if isinstance(v, (bytes, np.bytes_)) else str(v)))
+    return tuple(out)
 
 
 def load_keras_weights(path, wanted):
@@ -330,8 +372,28 @@ def _space(shape):
     return struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", int(s)) for s in shape)
 
 
-def _attr_msg(name, value):
-    if isinstance(value, (bytes, str)):
+class VLenStr:
+    """Marks an attribute value to be stored as a scalar variable-length string (what h5py does with Python bytes / str:
+    Keras' keras_version, backend, model_config, training_config)."""
+
+    def __init__(self, text):
+        self.raw = text.encode("utf8") if isinstance(text, str) else bytes(text)
+
+
+def _dt_vlen_str():
+    # class 9 (variable length) version 1, type = string, null-terminated, ASCII; base type: 1-byte fixed string
+    return struct.pack("<BBBBI", 0x19, 0x01, 0x00, 0x00, 16) + _dt_string(1)
+
+
+def _dt_int64():
+    return struct.pack("<BBBBI", 0x10, 0x08, 0x00, 0x00, 8) + struct.pack("<HH", 0, 64)
+
+
+def _attr_msg(name, value, writer=None):
+    if isinstance(value, VLenStr):
+        gaddr = writer.global_heap(value.raw)
+        dt, sp, data = _dt_vlen_str(), _space(()), struct.pack("<IQI", len(value.raw), gaddr, 1)
+    elif isinstance(value, (bytes, str)):
         raw = value.encode("utf8") if isinstance(value, str) else value
         dt, sp, data = _dt_string(max(1, len(raw))), _space(()), raw or b"\0"
     else:
@@ -363,10 +425,24 @@ class _Writer:
         body = b"".join(msgs)
         return self.alloc(struct.pack("<BxHII4x", 1, len(msgs), 1, len(body)) + body)
 
+    def global_heap(self, blob):
+        """A global heap collection holding one object (index 1) + the free-space object; returns its address."""
+        body = struct.pack("<HH4xQ", 1, 1, len(blob)) + _pad8(blob)
+        size = max(4096, (16 + len(body) + 16 + 4095) & ~4095)
+        free = size - 16 - len(body)
+        body += struct.pack("<HH4xQ", 0, 0, free) + b"\0" * (free - 16)
+        return self.alloc(b"GCOL" + struct.pack("<B3xQ", 1, size) + body)
+
     def dataset(self, arr):
-        arr = np.ascontiguousarray(arr, "<f4")
+        arr = np.asarray(arr)
+        if arr.dtype.kind in "iu":  # the optimizer's iteration counter
+            arr = np.asarray(arr, "<i8", order="C")
+            dtmsg = _dt_int64()
+        else:
+            arr = np.asarray(arr, "<f4", order="C")
+            dtmsg = _dt_float32()
         addr = self.alloc(arr.tobytes()) if arr.size else UNDEF
-        msgs = [_msg(0x0001, _space(arr.shape)), _msg(0x0003, _dt_float32(), flags=1),
+        msgs = [_msg(0x0001, _space(arr.shape)), _msg(0x0003, dtmsg, flags=1),
                 _msg(0x0005, struct.pack("<BBBBI", 2, 2, 0, 1, 0)),
                 _msg(0x0008, struct.pack("<BBQQ", 3, 1, addr, arr.nbytes))]
         return self.header(msgs)
@@ -382,7 +458,8 @@ class _Writer:
         heap_data = self.alloc(bytes(heap) if len(heap) >= 8 else b"\0" * 8)
         heap_addr = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), 1, heap_data))
         K = self.K  # group leaf / internal K, also written into the superblock
-        assert len(names) <= 4 * K * K, "too many links for a single-level group B-tree"
+        if len(names) > 4 * K * K:
+            raise H5Error("too many links for a single-level group B-tree")
         chunks = [names[i:i + 2 * K] for i in range(0, len(names), 2 * K)]
         tree = bytearray(b"TREE" + struct.pack("<BBHQQ", 0, 0, len(chunks), UNDEF, UNDEF))
         tree += struct.pack("<Q", 0)  # key 0: the empty string at heap offset 0
@@ -394,7 +471,7 @@ class _Writer:
             tree += struct.pack("<QQ", self.alloc(bytes(snod)), offs[ch[-1]])
         tree += b"\0" * (24 + 8 + 16 * 2 * K - len(tree))
         tree_addr = self.alloc(bytes(tree))
-        msgs = [_msg(0x0011, struct.pack("<QQ", tree_addr, heap_addr))] + [_attr_msg(k, v) for k, v in attrs]
+        msgs = [_msg(0x0011, struct.pack("<QQ", tree_addr, heap_addr))] + [_attr_msg(k, v, self) for k, v in attrs]
         return self.header(msgs), tree_addr, heap_addr
 
     def finish(self, root):
@@ -440,3 +517,66 @@ def save_keras_weights(path, weights, order, extra_layers=(), tf_scope_suffix=""
     root = w.group({"model_weights": mw}, [("keras_version", b"2.2.4"), ("backend", b"tensorflow")])
     with open(path, "wb") as fh:
         fh.write(w.finish(root))
+
+
+def _nested_group(w, items):
+    """items: [('a/b/c:0', array)] -> object header address of a group tree whose leaves are datasets."""
+    here, sub = {}, {}
+    for name, arr in items:
+        head, _, rest = name.partition("/")
+        if rest:
+            sub.setdefault(head, []).append((rest, arr))
+        else:
+            here[head] = w.dataset(arr)
+    for head, rest in sub.items():
+        here[head] = _nested_group(w, rest)
+    return here
+
+
+def save_keras_model(path, weights, layer_names, layer_weights, model_config=None, training_config=None,
+                     optimizer_weights=None, tf_scope_suffix=""):
+    """Writes a Keras 2.x FULL-MODEL file (what `model.save` produces, TG:892 / TU:622):
+
+      /                      attrs keras_version, backend, model_config [, training_config]   (variable-length strings)
+      /model_weights         attrs layer_names (Keras' model.layers order, weight-less layers included; split into
+                             layer_names0.. above the 64 512-byte object-header limit like Keras does), backend,
+                             keras_version; one group per layer with attr weight_names and datasets <scope>/<weight>:0
+      /optimizer_weights     attr weight_names + nested datasets (compiled models only)
+
+    weights: {'layer/weight': array}; layer_weights: {layer: [weight names in Keras order]} (keras_config.describe)."""
+    w = _Writer()
+    layer_objs = {}
+    for ln in layer_names:
+        wn = list(layer_weights.get(ln, ()))
+        scope = ln + tf_scope_suffix
+        kids = {}
+        if wn:
+            ds = {n + ":0": w.dataset(weights["%s/%s" % (ln, n)]) for n in wn}
+            kids[scope] = w.group(ds)[0]
+        attr = _fixed_strings(["%s/%s:0" % (scope, n) for n in wn])
+        layer_objs[ln] = w.group(kids, [("weight_names", attr)])[0]
+    names = _fixed_strings(list(layer_names))
+    limit = 64512  # HDF5_OBJECT_HEADER_LIMIT of keras/engine/saving.py
+    if names.nbytes <= limit:
+        name_attrs = [("layer_names", names)]
+    else:
+        parts = int(np.ceil(names.nbytes / float(limit)))
+        name_attrs = [("layer_names%d" % i, c) for i, c in enumerate(np.array_split(names, parts))]
+    mw = w.group(layer_objs, name_attrs + [("backend", VLenStr("tensorflow")), ("keras_version", VLenStr("2.2.4"))])[0]
+    root = {"model_weights": mw}
+    if optimizer_weights:
+        tree = _nested_group(w, optimizer_weights)
+
+        def build(node):
+            return w.group({k: (build(v) if isinstance(v, dict) else v) for k, v in node.items()})[0]
+
+        ow_names = _fixed_strings([n for n, _ in optimizer_weights])
+        root["optimizer_weights"] = w.group({k: (build(v) if isinstance(v, dict) else v) for k, v in tree.items()},
+                                            [("weight_names", ow_names)])[0]
+    attrs = [("keras_version", VLenStr("2.2.4")), ("backend", VLenStr("tensorflow"))]
+    if model_config is not None:
+        attrs.append(("model_config", VLenStr(model_config)))
+    if training_config is not None:
+        attrs.append(("training_config", VLenStr(training_config)))
+    with open(path, "wb") as fh:
+        fh.write(w.finish(w.group(root, attrs)))

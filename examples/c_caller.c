@@ -78,7 +78,8 @@ int main(int argc, char** argv) {
   cfg.nc_out = atoi(argv[7]);
   cfg.noise_len = 32;
   cfg.max_batch = n;
-  cfg.precision = (argc > 8 && strcmp(argv[8], "fp32") == 0) ? DEPGAN_PREC_FP32 : DEPGAN_PREC_BF16;
+  cfg.precision = (argc > 8 && strcmp(argv[8], "fp32") == 0) ? DEPGAN_PREC_FP32
+                  : (argc > 8 && strcmp(argv[8], "f16") == 0) ? DEPGAN_PREC_F16 : DEPGAN_PREC_BF16;
   cfg.training = 0;
 
   n_par = depgan_manifest_floats(DEPGAN_MODEL_GEN, &cfg);
@@ -134,7 +135,7 @@ int main(int argc, char** argv) {
   }
   fclose(fo);
   printf("c_caller: %d slices of %dx%d, %s, %.3f ms per forward (%.0f slices/s), %lld kernel launches\n", n, cfg.H,
-         cfg.W, cfg.precision == DEPGAN_PREC_BF16 ? "bf16" : "fp32", ms / reps, 1e3 * n * reps / ms,
+         cfg.W, cfg.precision == DEPGAN_PREC_BF16 ? "bf16" : cfg.precision == DEPGAN_PREC_F16 ? "f16" : "fp32", ms / reps, 1e3 * n * reps / ms,
          depgan_launch_count());
 
   depgan_net_destroy(g);

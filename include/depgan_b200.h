@@ -25,6 +25,8 @@ extern "C" {
 
 #define DEPGAN_PREC_FP32 0 /* fp32 activations, fp32 CUDA-core implicit GEMM (the <=1e-4 variant) */
 #define DEPGAN_PREC_BF16 1 /* bf16 activations, tcgen05/TMEM implicit GEMM, fp32 accumulate (<=1e-2) */
+#define DEPGAN_PREC_F16 2  /* IEEE-half activations and weights, same tcgen05 kernels and rate (kind::f16), fp32 accumulate:
+                              generator inference handles only (training == 0); DEM error ~7x below the bf16 path */
 
 #define DEPGAN_HEAD_TANH 0    /* DEP-GAN generator TG:494-495 */
 #define DEPGAN_HEAD_SOFTMAX 1 /* DEP-UResNet TU:423-424 */

@@ -130,6 +130,11 @@ CASES = [
     lambda: conv_case("tc_5x5_16to16_N96", 96, 256, 256, 16, 16, 5),
     lambda: conv_case("tc_5x5_16to16_mask_N32", 32, 256, 256, 16, 16, 5, mask=True, relu=False),
     lambda: conv_case("tc_5x5_32to32_N96", 96, 128, 128, 32, 32, 5),
+    lambda: conv_case("tc_5x5_16to32_N96", 96, 128, 128, 16, 32, 5),
+    lambda: conv_case("tc_5x5_32to16_mask_N96", 96, 128, 128, 32, 16, 5, mask=True, relu=False),
+    lambda: conv_case("tc_5x5_32to32_mask_N96", 96, 128, 128, 32, 32, 5, mask=True, relu=False),
+    lambda: conv_case("tc_5x5_16to16_mask_N96", 96, 256, 256, 16, 16, 5, mask=True, relu=False),
+    lambda: conv_case("tc_3x3_32to64_N64", 64, 128, 128, 32, 64, 3),
     lambda: conv_case("tc_3x3_256to256_N96", 96, 16, 16, 256, 256, 3),
     lambda: wgrad_case("wgrad_tc_5x5_16to16_N64", 64, 256, 256, 16, 16, 5, 1),
     lambda: wgrad_case("wgrad_tc_3x3_32to32_N32", 32, 256, 256, 32, 32, 3, 1),

@@ -29,7 +29,7 @@ def test_c_caller_builds_and_fails_loudly_without_inputs(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("nicg,nc_out,precision", [(1, 1, "bf16"), (1, 4, "bf16"), (2, 1, "fp32")])
+@pytest.mark.parametrize("nicg,nc_out,precision", [(1, 1, "bf16"), (1, 4, "bf16"), (2, 1, "fp32"), (1, 4, "f16")])
 def test_c_caller_matches_python_surface(tmp_path, nicg, nc_out, precision):
     import torch
     from depgan_b200 import Gen_UNet2D, synth

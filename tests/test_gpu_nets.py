@@ -38,6 +38,24 @@ def test_generator_bf16_tcgen05_matches_oracle(nicg, nc_out, head):
     assert np.abs(got - want).max() <= 1e-2, np.abs(got - want).max()  # DEM tolerance of BASELINE.json
 
 
+@pytest.mark.parametrize("nicg,nc_out,head", [(1, 1, "tanh"), (2, 1, "tanh"), (1, 4, "softmax")])
+def test_generator_f16_tcgen05_matches_oracle(nicg, nc_out, head):
+    """precision='f16': the same tcgen05 kernels with IEEE-half activations / weights (inference handles).  64 x 64 also
+    walks the CUDA-core fallbacks of the 8 x 8 bottleneck in that format."""
+    from depgan_b200 import Gen_UNet2D
+    H = W = 64
+    P = util.gen_weights(nicg, nc_out, seed=3)
+    x, _, _ = synth.make_im_pair(3, H, W, nicg=nicg, seed=1)
+    z = synth.make_noise(3, seed=2)
+    g = Gen_UNet2D((H, W, nicg), (32, 1), 32, nc_out, precision="f16", max_batch=4)
+    g.set_weights(P)
+    got = g.predict([x, z])
+    want = util.oracle_gen(P, x, z, head)
+    assert np.abs(got - want).max() <= 2.5e-3, np.abs(got - want).max()
+    with pytest.raises(Exception):  # training handles keep the bf16 range
+        Gen_UNet2D((H, W, nicg), (32, 1), 32, nc_out, precision="f16", max_batch=4, training=True)
+
+
 def test_generator_intermediate_activations_fp32():
     from depgan_b200 import Gen_UNet2D
     from oracle import depgan_oracle as O
