@@ -30,7 +30,7 @@
 // 1 for CO = 64); warp w owns TMEM lane quarter w % 4 (32 pixels), stages its pixels in its own swizzled slots and
 // issues its own TMA stores -- no block- or group-wide barrier in the row loop.  Warp 8 TMA producer of the row tiles
 // (and, once, of the resident weights), warp 9 MMA issuer + TMEM owner, warp 10 TMA producer of the epilogue's side rows
-// (FiLM residual, add / mask sources).  EPI bit 2: 2x2 max-pool of the stored values (vertical max of the row pair in
+// (FiLM residual, add / mask sources), warp 11 scout (does the issuer's barrier waits and publishes "rows ready").  EPI bit 2: 2x2 max-pool of the stored values (vertical max of the row pair in
 // registers, horizontal max by one shuffle), staged and stored by a second TMA store.
 #include <cuda.h>
 
@@ -47,7 +47,29 @@ namespace {
 constexpr int RG_THREADS = 384;
 constexpr int BWG = 128;   // pixels per M block
 constexpr int NQG = 64;    // "input row done" barriers (ring)
+constexpr int NREC = 16;   // row records for the issuer (ring; more than the deepest row-tile ring)
 constexpr int NSIDEG = 4;  // side-row stages (one stage = one 128-pixel row of every side tensor)
+
+#ifdef DG_ROWG_TRACE  // timing experiment only: event clocks of CTA 0 (roles: 0 producer, 1 issuer, 2 epilogue warp 0, 3 warp 4)
+__device__ long long* g_rowg_trace = nullptr;  // [4 roles][64 rows][8 events], dumped from shared memory at exit
+#define GTRACE_DECL __shared__ uint32_t s_gtrace[4 * 64 * 8];
+#define GTRACE_SMEM 8192
+#define GTRACE(role_, row_, ev_)                                                                      \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (row_) < 64)                                    \
+      s_gtrace[((role_) * 64 + (row_)) * 8 + (ev_)] = (uint32_t)clock64();                            \
+  } while (0)
+#define GTRACE_DUMP                                                                                   \
+  do {                                                                                                \
+    if (blockIdx.x == 0 && g_rowg_trace)                                                              \
+      for (int i_ = threadIdx.x; i_ < 4 * 64 * 8; i_ += blockDim.x) g_rowg_trace[i_] = s_gtrace[i_];  \
+  } while (0)
+#else
+#define GTRACE_DECL
+#define GTRACE_SMEM 0
+#define GTRACE(role_, row_, ev_) do {} while (0)
+#define GTRACE_DUMP do {} while (0)
+#endif
 
 template <int KS, int CK, int CO>
 struct RG {
@@ -69,6 +91,7 @@ struct RG {
   static constexpr uint32_t SIDE_ROW = BWG * OSPAN;
   static constexpr int CW = CO < 32 ? CO : 32;                              // accumulator columns per epilogue pass
   static constexpr int NH = CO / CW;                                        // passes per row
+  static constexpr int NSIDE = CO == 64 ? 3 : NSIDEG;                       // side-row stages (shared memory is tight at 64)
   static_assert(NBLK >= KS + RP + 1, "TMEM ring too small for the taps in flight");
   static_assert(B_TILE % 256 == 0 && (CO * SPAN) % 256 == 0, "weight tiles must keep the swizzle phase");
 };
@@ -77,6 +100,7 @@ struct RowgGeom {
   int nchunk0, nchunk1;  // CK-channel chunks from in0 / in1
   int cblocks;           // 128-pixel column blocks per image row
   int na;                // row-tile ring depth
+  int batch;             // input rows the issuer issues per wait (<= na)
   int n_side;            // side tensors per output row (0..2)
   int pool;              // EPI bit 2 active
   long long rows_total;  // N * cblocks * H output rows (of 128 pixels)
@@ -127,6 +151,20 @@ __device__ __forceinline__ void tg_zero<32>(uint32_t taddr) {
       : "memory");
 }
 __device__ __forceinline__ void tg_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint2 ld_acquire_shared_v2(uint32_t addr) {  // one 64-bit access: both words are consistent
+  unsigned long long v;
+  asm volatile("ld.acquire.cta.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
+__device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_shared_v2(uint32_t addr, uint32_t x, uint32_t y) {
+  const unsigned long long v = (unsigned long long)x | ((unsigned long long)y << 32);
+  asm volatile("st.release.cta.shared::cta.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
 
 // The CTA's contiguous range of output rows (128 pixels wide), cut into segments at image borders.  A unit is one
 // (slice, column block); every role walks the same segments.  `even`: range borders fall on even rows (fused pool).
@@ -161,31 +199,47 @@ struct SegIterG {
 
 // ---------------------------------------------------------------------------------------------------------
 // EPI bit 0: FiLM residual side row; bit 1: add / mask side rows; bit 2: fused 2x2 max-pool.
+//
+// Indexing.  A segment of cnt output rows reads Q = cnt + KS - 1 input rows.  EVERY input row issues the same full-width
+// MMA (N = KS * CO): input row j of the segment accumulates into the KS blocks of "slots" j .. j + KS - 1, where slot
+// s = output row s - (KS - 1) of the segment.  Slots 0 .. KS-2 and cnt + KS - 1 .. cnt + 2 KS - 3 are phantoms (rows
+// above / below the segment): they collect partial sums nobody reads and are recycled (zeroed) by the epilogue like any
+// other block.  That keeps the issuer free of edge cases -- its per-row work is a handful of instructions, which is what
+// the kernel's speed hangs on: one warp issues dependent scalar instructions at ~4 clk each, an mbarrier poll costs
+// ~100 clk, and a row's MMAs are only 260 clk of tensor work for the 16 -> 16 layer (profiles/r02_rowg_role_trace.txt:
+// the first version spent 1000 clk per row in the issuer's bookkeeping).  Slot s is final after input row min(s, Q - 1).
 // ---------------------------------------------------------------------------------------------------------
 // F16: IEEE-half storage of activations / weights instead of bfloat16 (compile time: see conv_tc_kernel.cuh).
 template <int KS, int CK, int CO, int EPI, bool F16>
 __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_constant__ RowgMaps tm, const ConvArgs a,
                                                                   const RowgGeom g) {
   typedef RG<KS, CK, CO> G;
-  constexpr int NBLK = G::NBLK, RP = G::RP, NSLOT = G::NSLOT, CW = G::CW, NH = G::NH;
+  constexpr int NBLK = G::NBLK, RP = G::RP, NSLOT = G::NSLOT, CW = G::CW, NH = G::NH, NSD = G::NSIDE;
   constexpr bool E_RES = (EPI & 1) != 0, E_AM = (EPI & 2) != 0, E_POOL = (EPI & 4) != 0;
   static_assert(!E_POOL || RP == 2, "the fused pool works on row pairs");
+  static_assert((NBLK & (NBLK - 1)) == 0 && (NQG & (NQG - 1)) == 0, "ring sizes are powers of two");
   extern __shared__ uint8_t smem_raw[];
+  GTRACE_DECL
+#ifdef DG_ROWG_TRACE
+  for (int i_ = threadIdx.x; i_ < 4 * 64 * 8; i_ += blockDim.x) s_gtrace[i_] = 0;
+#endif
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   const int nchunks = g.nchunk0 + g.nchunk1;
+  const uint32_t a_stage = (uint32_t)nchunks * G::A_STAGE;                              // one input row, all chunks
   const uint32_t b_base = base;                                                         // weights: [dx][chunk] tiles
-  const uint32_t a_base = (b_base + (uint32_t)KS * nchunks * G::B_TILE + 1023u) & ~1023u;  // row-tile ring
-  const uint32_t o_base = a_base + (uint32_t)g.na * G::A_STAGE;                         // 8 warps x NSLOT slots
+  const uint32_t a_base = (b_base + (uint32_t)KS * nchunks * G::B_TILE + 1023u) & ~1023u;  // input-row ring
+  const uint32_t o_base = a_base + (uint32_t)g.na * a_stage;                            // 8 warps x NSLOT slots
   const uint32_t p_base = o_base + 8u * NSLOT * G::WSLOT;                               // pooled: 8 warps x NSLOT
-  const uint32_t s_base = p_base + (E_POOL ? 8u * NSLOT * G::PSLOT : 0u);               // NSIDEG stages x n_side rows
-  const uint32_t bar_base = s_base + (uint32_t)NSIDEG * g.n_side * G::SIDE_ROW;
-  const uint32_t fullA = bar_base, emptyA = fullA + 8 * g.na;
-  const uint32_t fullB = emptyA + 8 * g.na;
+  const uint32_t s_base = p_base + (E_POOL ? 8u * NSLOT * G::PSLOT : 0u);               // NSD stages x n_side rows
+  const uint32_t bar_base = s_base + (uint32_t)NSD * g.n_side * G::SIDE_ROW;
+  const uint32_t fullA = bar_base;
+  const uint32_t fullB = fullA + 8 * g.na;
   const uint32_t rowDone = fullB + 8, blkEmpty = rowDone + 8 * NQG;
-  const uint32_t sideFull = blkEmpty + 8 * NBLK, sideEmpty = sideFull + 8 * NSIDEG;
-  const uint32_t tmem_slot = sideEmpty + 8 * NSIDEG;
-  const uint32_t f_off = (tmem_slot + 16 + 15u) & ~15u;  // floats: scale, shift, per-warp tables
+  const uint32_t sideFull = blkEmpty + 8 * NBLK, sideEmpty = sideFull + 8 * NSD;
+  const uint32_t tmem_slot = sideEmpty + 8 * NSD;
+  const uint32_t rec_ring = tmem_slot + 16;              // NREC row records for the issuer (written by the scout warp)
+  const uint32_t f_off = (rec_ring + 8u * NREC + 15u) & ~15u;  // floats: scale, shift, per-warp tables
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - raw));
   float* s_scale = reinterpret_cast<float*>(smem_raw + (f_off - raw));
   float* s_shift = s_scale + CO;
@@ -194,11 +248,12 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < g.na; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
+    for (int i = 0; i < g.na; ++i) mbar_init(fullA + 8 * i, 1);
     mbar_init(fullB, 1);
+    for (int i = 0; i < NREC; ++i) st_release_shared_v2(rec_ring + 8u * i, 0u, 0u);
     for (int i = 0; i < NQG; ++i) mbar_init(rowDone + 8 * i, 1);
     for (int i = 0; i < NBLK; ++i) mbar_init(blkEmpty + 8 * i, 4);
-    for (int i = 0; i < NSIDEG; ++i) { mbar_init(sideFull + 8 * i, 1); mbar_init(sideEmpty + 8 * i, 4); }
+    for (int i = 0; i < NSD; ++i) { mbar_init(sideFull + 8 * i, 1); mbar_init(sideEmpty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == CTRL_W0 + 1) {
@@ -227,13 +282,13 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
   if (warp >= CTRL_W0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == CTRL_W0) {
-      // ===== TMA producer: resident weights once, then per input row and chunk one row tile =====
+      // ===== TMA producer: resident weights once, then one ring stage per input row (all its channel chunks) =====
       if (elect_one()) {
         mbar_expect_tx(fullB, (uint32_t)KS * nchunks * G::B_TILE);
         for (int dx = 0; dx < KS; ++dx)
           for (int c = 0; c < nchunks; ++c) {
             const int kglob = c < g.nchunk0 ? c * CK : a.C0 + (c - g.nchunk0) * CK;
-            for (int dy = 0; dy < KS; ++dy)  // rows stacked (dy = KS-1 .. 0): column block k of an MMA = output row j-KS+1+k
+            for (int dy = 0; dy < KS; ++dy)  // rows stacked (dy = KS-1 .. 0): column block k of an MMA = slot j + k
               tma_load_2d(b_base + (uint32_t)(dx * nchunks + c) * G::B_TILE + (uint32_t)(KS - 1 - dy) * CO * G::SPAN,
                           &tm.b, fullB, kglob, (dy * KS + dx) * CO);
           }
@@ -242,115 +297,135 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
       Ring ra;
       SegIterG si;
       si.init(g.rows_total, a.H, g.cblocks, E_POOL);
+      uint32_t pq = 0;  // input-row sequence number
       for (; si.valid(); si.next()) {
         const int x0 = si.cb * BWG - G::PAD, r0 = si.r0 - G::PAD;
-        for (int j = 0; j < si.cnt + KS - 1; ++j) {
-          for (int c = 0; c < nchunks; ++c) {
-            const bool first = c < g.nchunk0;
-            const int ch = (first ? c : c - g.nchunk0) * CK;
-            mbar_wait(emptyA + 8 * ra.idx, ra.phase ^ 1u);
-            if (elect_one()) {
-              mbar_expect_tx(fullA + 8 * ra.idx, G::A_TX);
-              tma_load_4d(a_base + ra.idx * G::A_STAGE, first ? &tm.a0 : &tm.a1, fullA + 8 * ra.idx, ch, x0, r0 + j, si.n);
-            }
-            __syncwarp();
-            ra.advance(g.na);
+        for (int j = 0; j < si.cnt + KS - 1; ++j, ++pq) {
+          GTRACE(0, (int)pq, 0);
+          // the stage is free once the row that used it last (na rows ago) has been multiplied: that row's "done"
+          // barrier (one commit per row serves the epilogue and this ring)
+          if (pq >= (uint32_t)g.na) {
+            const uint32_t qp = pq - (uint32_t)g.na;
+            mbar_wait(rowDone + 8 * (qp & (NQG - 1)), (qp / NQG) & 1u);
           }
-        }
-      }
-    } else if (warp == CTRL_W0 + 1) {
-      // ===== MMA issuer: per input row KS * KSTEPS * nchunks instructions of N = KS * CO (less at the segment edges).
-      // The MMA queue is shallow and an mbarrier poll costs ~100 clk, so the waits of the NEXT step (input row, chunk)
-      // are issued between the MMA groups of the current one. =====
-      const uint32_t hi = ((uint32_t)(8 * G::SPAN) >> 4) | (1u << 14) | (G::LAYOUT << 29);
-      constexpr uint32_t LBO1 = 1u << 16;
-      constexpr uint32_t BLK16 = (CO * G::SPAN) >> 4;  // one dy block of weight rows in descriptor units
-      constexpr bool f16_in = F16;
-      mbar_wait(fullB, 0);
-      tc_fence_after();
-      const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | LBO1;
-
-      struct Step {
-        uint32_t stage, phase;  // row-tile ring stage of this step
-        uint32_t d1, idesc1, idesc2, n1, n2, brow0;
-        uint32_t q, o_hi;
-        int c;
-        bool valid;
-      };
-      Ring ra;
-      SegIterG si;
-      si.init(g.rows_total, a.H, g.cblocks, E_POOL);
-      uint32_t o0 = 0, q = 0, acquired = 0;
-      int j = 0, c = 0;
-      auto make_step = [&]() -> Step {  // geometry of the step (si, j, c); advances the iteration state afterwards
-        Step s{};
-        s.valid = si.valid();
-        if (!s.valid) return s;
-        const int cnt = si.cnt;
-        const int i_lo = j >= KS - 1 ? j - (KS - 1) : 0, i_hi = j < cnt ? j : cnt - 1;
-        const uint32_t o_lo = o0 + (uint32_t)i_lo;
-        s.o_hi = o0 + (uint32_t)i_hi;
-        s.brow0 = (uint32_t)(i_lo - (j - (KS - 1)));
-        const uint32_t blk0 = o_lo % NBLK, nblk = s.o_hi - o_lo + 1u;
-        s.n1 = blk0 + nblk > (uint32_t)NBLK ? (uint32_t)NBLK - blk0 : nblk;
-        s.n2 = nblk - s.n1;
-        s.d1 = tmem_base + blk0 * CO;
-        s.idesc1 = make_idesc((int)(CO * s.n1), f16_in);
-        s.idesc2 = make_idesc((int)(CO * (s.n2 ? s.n2 : 1u)), f16_in);
-        s.q = q; s.c = c;
-        s.stage = ra.idx; s.phase = ra.phase;
-        ra.advance(g.na);
-        if (++c == nchunks) {
-          c = 0; ++q;
-          if (++j == cnt + KS - 1) { j = 0; o0 += (uint32_t)cnt; si.next(); }
-        }
-        return s;
-      };
-      // a block is acquired the first time an input row touches its output row: the previous owner (NBLK output rows
-      // earlier) must have been drained and zeroed by the four warps of its epilogue group
-      auto wait_blocks = [&](const Step& s) {
-        if (!s.valid) return;
-        while (acquired <= s.o_hi) {
-          if (acquired >= (uint32_t)NBLK) mbar_wait(blkEmpty + 8 * (acquired % NBLK), ((acquired / NBLK) & 1u) ^ 1u);
-          ++acquired;
-        }
-      };
-      auto wait_tiles = [&](const Step& s) {
-        if (s.valid) mbar_wait(fullA + 8 * s.stage, s.phase);
-      };
-      Step cur = make_step();
-      wait_blocks(cur);
-      wait_tiles(cur);
-      tc_fence_after();
-      while (cur.valid) {
-        const uint32_t a_lo0 = (((a_base + cur.stage * G::A_STAGE) & 0x3FFFFu) >> 4) | LBO1;
-        const uint32_t b_lo = b_lo0 + (uint32_t)cur.c * (G::B_TILE >> 4) + cur.brow0 * BLK16;
-        Step nxt{};
-#pragma unroll
-        for (int dx = 0; dx < KS; ++dx) {
+          GTRACE(0, (int)pq, 1);
           if (elect_one()) {
-            const uint32_t bt = b_lo + (uint32_t)dx * (uint32_t)nchunks * (G::B_TILE >> 4);
-#pragma unroll
-            for (int k = 0; k < G::KSTEPS; ++k) {
-              const uint64_t db = ((uint64_t)hi << 32) | (bt + 2 * k);
-              const uint64_t da = ((uint64_t)hi << 32) | (a_lo0 + (G::SPAN >> 4) * dx + 2 * k);
-              tc_mma(cur.d1, da, db, cur.idesc1, 1u);
-              if (cur.n2) {
-                const uint64_t db2 = ((uint64_t)hi << 32) | (bt + cur.n1 * BLK16 + 2 * k);
-                tc_mma(tmem_base, da, db2, cur.idesc2, 1u);
-              }
-            }
-            if (dx == KS - 1) {
-              tc_commit(emptyA + 8 * cur.stage);
-              if (cur.c == nchunks - 1) tc_commit(rowDone + 8 * (cur.q % NQG));
+            mbar_expect_tx(fullA + 8 * ra.idx, (uint32_t)nchunks * G::A_TX);
+            for (int c = 0; c < nchunks; ++c) {
+              const bool first = c < g.nchunk0;
+              tma_load_4d(a_base + ra.idx * a_stage + (uint32_t)c * G::A_STAGE, first ? &tm.a0 : &tm.a1,
+                          fullA + 8 * ra.idx, (first ? c : c - g.nchunk0) * CK, x0, r0 + j, si.n);
             }
           }
           __syncwarp();
-          // the next step's waits ride on the queued MMAs
-          if (dx == 0) { nxt = make_step(); wait_blocks(nxt); }
-          if (dx == 1) { wait_tiles(nxt); tc_fence_after(); }
+          ra.advance(g.na);
         }
-        cur = nxt;
+      }
+    } else if (warp == CTRL_W0 + 1) {
+      // ===== MMA issuer: per input row KS * KSTEPS * nchunks instructions of N = KS * CO into the blocks of slots
+      // s .. s + KS - 1 (two instructions each where the range wraps the ring), issued back to back by one elected lane
+      // with immediate descriptor offsets, then ONE commit ("row done": the epilogue's signal and the ring's stage-free
+      // signal).  The issuer polls no mbarrier and keeps no geometry: the scout warp (below) does the waiting and leaves
+      // one record per row (sequence tag, ring stage, first TMEM block) in shared memory; the record of the next row is
+      // read while this row's instructions are still queued on the tensor pipe.  Everything between two rows' MMAs has
+      // to fit the ~100 clk the two queued instructions last (profiles/r02_rowg_role_trace.txt). =====
+      const uint32_t hi = ((uint32_t)(8 * G::SPAN) >> 4) | (1u << 14) | (G::LAYOUT << 29);
+      constexpr uint32_t LBO1 = 1u << 16;
+      constexpr uint32_t BLK16 = (CO * G::SPAN) >> 4;  // one dy block of weight rows in descriptor units
+      constexpr uint32_t BT16 = G::B_TILE >> 4, AS16 = G::A_STAGE >> 4, SP16 = G::SPAN >> 4;
+      constexpr bool f16_in = F16;
+      const uint32_t idesc_full = make_idesc(KS * CO, f16_in);
+      mbar_wait(fullB, 0);
+      tc_fence_after();
+      const uint32_t b_lo0 = ((b_base & 0x3FFFFu) >> 4) | LBO1;
+      const uint32_t a_lo_base = ((a_base & 0x3FFFFu) >> 4) | LBO1;
+      const uint32_t as16 = a_stage >> 4;
+      const uint32_t dxb16 = (uint32_t)nchunks * BT16;  // weight tiles of consecutive dx are nchunks tiles apart
+
+      uint32_t rows_in = 0;  // input rows of this CTA (every role walks the same segments)
+      {
+        SegIterG si;
+        si.init(g.rows_total, a.H, g.cblocks, E_POOL);
+        for (; si.valid(); si.next()) rows_in += (uint32_t)(si.cnt + KS - 1);
+      }
+      // Rows are issued in batches of up to `batch` (<= ring depth): one wait, one elect and one warp sync per batch, so
+      // the per-row scalar work shrinks to what the elected lane does between two rows' instructions -- and that runs
+      // while the tensor pipe works through its queue.
+      const uint32_t batch = (uint32_t)g.batch;
+      for (uint32_t q = 0; q < rows_in;) {
+        const uint32_t nb = rows_in - q < batch ? rows_in - q : batch;
+        // record of row r: .x = r + 1 once the row's tiles have landed and its blocks are free, .y = stage | block << 8.
+        // The scout publishes in row order, so the batch is ready when its last record is.
+        const uint32_t last_addr = rec_ring + ((q + nb - 1u) & (NREC - 1)) * 8u;
+        uint2 rec_last = ld_acquire_shared_v2(last_addr);
+        while (rec_last.x != q + nb) rec_last = ld_acquire_shared_v2(last_addr);
+        tc_fence_after();
+        GTRACE(1, (int)q, 0);
+        if (elect_one()) {
+          for (uint32_t r = 0; r < nb; ++r) {
+            const uint32_t ry = r + 1u == nb ? rec_last.y : ld_shared_u32(rec_ring + ((q + r) & (NREC - 1)) * 8u + 4u);
+            const uint32_t stage = ry & 0xFFu, blk0 = ry >> 8;
+            const uint32_t d1 = tmem_base + blk0 * CO;
+            const uint32_t a_lo = a_lo_base + stage * as16;
+            if (blk0 + KS <= (uint32_t)NBLK) {
+              for (int c = 0; c < nchunks; ++c) {
+                const uint32_t ac = a_lo + (uint32_t)c * AS16, bc = b_lo0 + (uint32_t)c * BT16;
+#pragma unroll
+                for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+                  for (int k = 0; k < G::KSTEPS; ++k)
+                    tc_mma(d1, ((uint64_t)hi << 32) | (ac + SP16 * dx + 2 * k),
+                           ((uint64_t)hi << 32) | (bc + (uint32_t)dx * dxb16 + 2 * k), idesc_full, 1u);
+              }
+            } else {
+              const uint32_t n1 = (uint32_t)NBLK - blk0;  // blocks before the ring wraps
+              const uint32_t idesc1 = make_idesc((int)(CO * n1), f16_in), idesc2 = make_idesc((int)(CO * (KS - n1)), f16_in);
+              for (int c = 0; c < nchunks; ++c) {
+                const uint32_t ac = a_lo + (uint32_t)c * AS16, bc = b_lo0 + (uint32_t)c * BT16;
+#pragma unroll
+                for (int dx = 0; dx < KS; ++dx)
+#pragma unroll
+                  for (int k = 0; k < G::KSTEPS; ++k) {
+                    const uint64_t da = ((uint64_t)hi << 32) | (ac + SP16 * dx + 2 * k);
+                    tc_mma(d1, da, ((uint64_t)hi << 32) | (bc + (uint32_t)dx * dxb16 + 2 * k), idesc1, 1u);
+                    tc_mma(tmem_base, da, ((uint64_t)hi << 32) | (bc + (uint32_t)dx * dxb16 + n1 * BLK16 + 2 * k), idesc2, 1u);
+                  }
+              }
+            }
+            tc_commit(rowDone + 8 * ((q + r) & (NQG - 1)));
+            GTRACE(1, (int)(q + r), 1);
+          }
+        }
+        __syncwarp();
+        GTRACE(1, (int)q, 2);
+        q += nb;
+      }
+    } else if (warp == CTRL_W0 + 3) {
+      // ===== scout: waits, in row order, for the row's tiles (TMA) and for the blocks of its newest slots (drained and
+      // zeroed by the epilogue), then publishes the row's record for the issuer.  It runs as far ahead as the rings allow
+      // (at most na rows: a stage is refilled only after its row was multiplied), so NREC > na records never overlap. =====
+      SegIterG si;
+      si.init(g.rows_total, a.H, g.cblocks, E_POOL);
+      Ring ra;
+      uint32_t s0 = 0, acquired = 0, q = 0;
+      for (; si.valid(); si.next()) {
+        const int nin = si.cnt + KS - 1;
+        for (int j = 0; j < nin; ++j, ++q) {
+          mbar_wait(fullA + 8 * ra.idx, ra.phase);
+          const uint32_t top = s0 + (uint32_t)(KS - 1);
+          // a block is acquired the first time a row touches its slot: the previous owner (NBLK slots earlier) must have
+          // been drained and zeroed by the four warps of its epilogue group
+          while (acquired <= top) {
+            if (acquired >= (uint32_t)NBLK) mbar_wait(blkEmpty + 8 * (acquired & (NBLK - 1)), ((acquired / NBLK) & 1u) ^ 1u);
+            ++acquired;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0)
+            st_release_shared_v2(rec_ring + (q & (NREC - 1)) * 8u, q + 1u, (uint32_t)ra.idx | ((s0 & (NBLK - 1)) << 8));
+          ra.advance(g.na);
+          s0 += j + 1 == nin ? (uint32_t)KS : 1u;
+        }
       }
     } else if (warp == CTRL_W0 + 2) {
       // ===== TMA producer of the side rows (FiLM residual, or add / mask sources): one 128-pixel row per output row =====
@@ -368,7 +443,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
               if (g.n_side == 2) tma_load_4d(dst + G::SIDE_ROW, &tm.s1, sideFull + 8 * rs.idx, 0, si.cb * BWG, si.r0 + i, si.n);
             }
             __syncwarp();
-            rs.advance(NSIDEG);
+            rs.advance(NSD);
           }
         }
       }
@@ -399,14 +474,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
 
     uint32_t q0 = 0;        // input-row sequence number of the segment's first input row
-    uint32_t o0 = 0;        // output-row sequence number of the segment's first output row
+    uint32_t sl0 = 0;       // slot sequence number of the segment's first slot
+    uint32_t side0 = 0;     // real-output-row sequence number of the segment's first row (side-stage ring)
     uint32_t step = 0;      // epilogue steps so far (both groups count all of them)
-    uint32_t nstaged = 0;   // steps this warp has staged (staging slot ring)
+    uint32_t nstaged = 0;   // stores this warp has issued (staging slot ring)
     int bseq = 0;
     SegIterG si;
     si.init(g.rows_total, a.H, g.cblocks, E_POOL);
-    for (; si.valid(); q0 += (uint32_t)(si.cnt + KS - 1), o0 += (uint32_t)si.cnt, ++bseq, si.next()) {
+    for (; si.valid(); q0 += (uint32_t)(si.cnt + KS - 1), sl0 += (uint32_t)(si.cnt + 2 * (KS - 1)),
+                       side0 += (uint32_t)si.cnt, ++bseq, si.next()) {
       const int cnt = si.cnt;
+      const int nslots = cnt + 2 * (KS - 1), nin = cnt + KS - 1;
       // per-segment table: v = acc * sc + sh   (BN folded; FiLM: the conditioning affine folded into the same pair)
       float* tb = tab + (bseq & 1) * 2 * CO;
       for (int cidx = lane; cidx < CO; cidx += 32) {
@@ -422,36 +500,49 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
       }
       __syncwarp();
       const int xw = si.cb * BWG + qd * 32;  // first pixel of this warp
-      for (int i = 0; i < cnt; i += RP, ++step) {
+      for (int s = 0; s < nslots; s += RP, ++step) {
         if ((int)(step & 1u) != grp) continue;
-        const int gsz = cnt - i >= RP ? RP : 1;  // rows in this step
-        const uint32_t o = o0 + (uint32_t)i;
-        // Output row i is complete when input row i + KS - 1 of the segment has been accumulated; the step waits for its
-        // last row (MMAs complete in order).  NQG barriers: a barrier is committed again NQG input rows later, which needs
-        // blocks far beyond this step's, i.e. this warp's arrival below.
-        const uint32_t qd_ = q0 + (uint32_t)(i + gsz - 1) + (uint32_t)(KS - 1);
-        mbar_wait(rowDone + 8 * (qd_ % NQG), (qd_ / NQG) & 1u);
+        const int gsz = nslots - s >= RP ? RP : 1;            // slots in this step
+        const int i0 = s - (KS - 1);                          // output row of the step's first slot (may be a phantom)
+        bool real[2];
+        real[0] = i0 >= 0 && i0 < cnt;
+        real[1] = RP == 2 && gsz == 2 && i0 + 1 >= 0 && i0 + 1 < cnt;
+        const uint32_t o = sl0 + (uint32_t)s;                 // slot sequence number -> TMEM block
+        const int trole = qd == 0 ? 2 + grp : 99;
+        if (trole < 4) GTRACE(trole, (int)o, 0);
+        // slot s is final after input row min(s, nin - 1); the step waits for its last slot (MMAs complete in order)
+        const int jl = s + gsz - 1 < nin - 1 ? s + gsz - 1 : nin - 1;
+        const uint32_t qd_ = q0 + (uint32_t)jl;
+        mbar_wait(rowDone + 8 * (qd_ & (NQG - 1)), (qd_ / NQG) & 1u);
         tc_fence_after();
+        if (trole < 4) GTRACE(trole, (int)o, 1);
+        const bool any_real = real[0] || real[1];
         const uint32_t slot = nstaged % NSLOT;
-        // the TMA store that last read this slot was issued NSLOT steps (of this warp) ago
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSLOT - 1) : "memory");
-        __syncwarp();
+        if (any_real) {
+          // the TMA store that last read this staging slot was issued NSLOT stores (of this warp) ago
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NSLOT - 1) : "memory");
+          __syncwarp();
+        }
+        if (trole < 4) GTRACE(trole, (int)o, 2);
         uint32_t pmax[E_POOL ? CO / 2 : 1];  // vertical max of the row pair, packed pairs
 #pragma unroll
         for (int h = 0; h < NH; ++h) {
           uint32_t va[RP][CW];
-          const uint32_t blk[2] = {t_lane + (o % NBLK) * CO + (uint32_t)(h * CW),
-                                   t_lane + ((o + 1u) % NBLK) * CO + (uint32_t)(h * CW)};
-          tg_ld<CW>(blk[0], va[0]);
-          if (RP == 2 && gsz == 2) tg_ld<CW>(blk[1], va[RP - 1]);
-          tg_ld_wait();
+          const uint32_t blk[2] = {t_lane + (o & (NBLK - 1)) * CO + (uint32_t)(h * CW),
+                                   t_lane + ((o + 1u) & (NBLK - 1)) * CO + (uint32_t)(h * CW)};
+          if (any_real) {
+            tg_ld<CW>(blk[0], va[0]);
+            if (RP == 2 && gsz == 2) tg_ld<CW>(blk[1], va[RP - 1]);
+            tg_ld_wait();
 #pragma unroll
-          for (int u = 0; u < RP; ++u) tg_fence<CW>(va[u]);
+            for (int u = 0; u < RP; ++u) tg_fence<CW>(va[u]);
+          }
+          if (trole < 4 && h == 0) GTRACE(trole, (int)o, 3);
           tg_zero<CW>(blk[0]);  // hand the blocks back zeroed (every MMA accumulates); waited for before the arrive
           if (RP == 2 && gsz == 2) tg_zero<CW>(blk[1]);
 #pragma unroll
           for (int u = 0; u < RP; ++u) {
-            if (u < gsz) {
+            if (real[u]) {
               float v[CW];
               // ---- affine (+ FiLM) ----
 #pragma unroll
@@ -464,10 +555,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
                 v[4 * k4 + 3] = fmaf(__uint_as_float(va[u][4 * k4 + 3]), sc4.w, sh4.w);
               }
               if (side) {
-                // side stage sequence = output row sequence (the producer's order)
-                const uint32_t sq = o + (uint32_t)u;
-                const uint32_t ss = sq % NSIDEG;
-                if (h == 0) mbar_wait(sideFull + 8 * ss, (sq / NSIDEG) & 1u);
+                // side stage sequence = real output row sequence (the producer's order)
+                const uint32_t sq = side0 + (uint32_t)(i0 + u);
+                const uint32_t ss = sq % NSD;
+                if (h == 0) mbar_wait(sideFull + 8 * ss, (sq / NSD) & 1u);
                 const uint8_t* sgen = smem_raw + (s_base + (uint32_t)(ss * g.n_side) * G::SIDE_ROW - raw) + sp_off;
                 if (E_RES) {
 #pragma unroll
@@ -518,7 +609,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
 #pragma unroll
                 for (int k = 0; k < CW; ++k) v[k] = fmaxf(v[k], 0.f);
               }
-              uint8_t* ogen = smem_raw + (w_o + slot * G::WSLOT + (uint32_t)u * (32u * OSPAN) - raw) + p_off;
+              // staging row: a step whose first slot is a phantom stages its one real row first
+              const uint32_t srow = real[0] ? (uint32_t)u : 0u;
+              uint8_t* ogen = smem_raw + (w_o + slot * G::WSLOT + srow * (32u * OSPAN) - raw) + p_off;
 #pragma unroll
               for (int uu = 0; uu < CW / 8; ++uu) {
                 uint4 pk;
@@ -537,9 +630,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
             }
           }
         }
-        if (E_POOL) {
+        if (E_POOL && any_real) {
           // 2x2 max-pool of the stored values: the vertical max is in pmax, the horizontal neighbour is lane ^ 1; the
-          // even lane stages pooled pixel lane / 2 (16 pixels per warp)
+          // even lane stages pooled pixel lane / 2 (16 pixels per warp).  (Segments start and end on even rows.)
           uint8_t* pgen = smem_raw + (w_p + slot * G::PSLOT - raw) + pp_off;
 #pragma unroll
           for (int uu = 0; uu < CO / 8; ++uu) {
@@ -553,23 +646,30 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
             if ((lane & 1) == 0) *reinterpret_cast<uint4*>(pgen + (((uint32_t)uu ^ pp_xor) << 4)) = pk;
           }
         }
+        if (trole < 4) GTRACE(trole, (int)o, 4);
         // the zeroed blocks go back to the issuer
         tg_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(blkEmpty + 8 * (o % NBLK));
-          if (gsz == 2) mbar_arrive(blkEmpty + 8 * ((o + 1u) % NBLK));
+          mbar_arrive(blkEmpty + 8 * (o & (NBLK - 1)));
+          if (gsz == 2) mbar_arrive(blkEmpty + 8 * ((o + 1u) & (NBLK - 1)));
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (gsz == 2) tma_store_4d(&tm.out2, w_o + slot * G::WSLOT, 0, xw, si.r0 + i, si.n);
-          else tma_store_4d(&tm.out1, w_o + slot * G::WSLOT, 0, xw, si.r0 + i, si.n);
-          if (E_POOL) tma_store_4d(&tm.pool, w_p + slot * G::PSLOT, 0, xw >> 1, (si.r0 + i) >> 1, si.n);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (trole < 4) GTRACE(trole, (int)o, 5);
+        if (any_real) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (trole < 4) GTRACE(trole, (int)o, 6);
+          if (lane == 0) {
+            const int row = si.r0 + (real[0] ? i0 : i0 + 1);
+            if (real[0] && real[1]) tma_store_4d(&tm.out2, w_o + slot * G::WSLOT, 0, xw, row, si.n);
+            else tma_store_4d(&tm.out1, w_o + slot * G::WSLOT, 0, xw, row, si.n);
+            if (E_POOL) tma_store_4d(&tm.pool, w_p + slot * G::PSLOT, 0, xw >> 1, row >> 1, si.n);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (trole < 4) GTRACE(trole, (int)o, 7);
+          ++nstaged;
         }
-        ++nstaged;
       }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // this warp's output rows are written
@@ -577,6 +677,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  GTRACE_DUMP;
   if (warp == CTRL_W0 + 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -591,7 +692,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode_g = nullptr;
 DgPerDevice g_dev_g;
 thread_local int g_sms_g = 148;
-constexpr uint32_t SMEM_BUDGET_G = 226 * 1024;
+constexpr uint32_t SMEM_BUDGET_G = 226 * 1024 - GTRACE_SMEM;
 
 CUtensorMapSwizzle swz_for(uint32_t span) {
   return span == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : span == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -645,16 +746,15 @@ bool plan_g(const ConvArgs& a, RowgGeom* g, uint32_t* smem) {
   g->rows_total = (long long)a.N * g->cblocks * a.H;
   const uint32_t wbytes = ((uint32_t)KS * nchunks * G::B_TILE + 1023u) & ~1023u;
   const uint32_t fixed = 1024 + wbytes + 8u * G::NSLOT * G::WSLOT + (g->pool ? 8u * G::NSLOT * G::PSLOT : 0u) +
-                         (uint32_t)NSIDEG * g->n_side * G::SIDE_ROW + 8u * (2 * 16 + 1 + NQG + G::NBLK + 2 * NSIDEG) + 64 +
-                         (2 * CO + 8 * 4 * CO) * 4 + 64;
-  const int min_na = nchunks + 1 > 3 ? nchunks + 1 : 3;
-  if (fixed + (uint32_t)min_na * G::A_STAGE > SMEM_BUDGET_G) return false;
-  int na = (int)((SMEM_BUDGET_G - fixed) / G::A_STAGE);
-  if (na > 16) na = 16;
-  const int want = 4 * nchunks > 8 ? 4 * nchunks : 8;  // four input rows in flight is plenty
-  if (na > want) na = want;
+                         (uint32_t)G::NSIDE * g->n_side * G::SIDE_ROW + 8u * (2 * 16 + 1 + NQG + G::NBLK + 2 * NSIDEG) + 64 +
+                         8 * NREC + (2 * CO + 8 * 4 * CO) * 4 + 64;
+  const uint32_t stage = (uint32_t)nchunks * G::A_STAGE;  // one ring stage = one input row, all its chunks
+  if (fixed + 2u * stage > SMEM_BUDGET_G) return false;
+  int na = (int)((SMEM_BUDGET_G - fixed) / stage);
+  if (na > 8) na = 8;  // eight input rows in flight is plenty
   g->na = na;
-  *smem = fixed + (uint32_t)na * G::A_STAGE;
+  g->batch = 1;  // measured: batches of 4 were slower (0.119 -> 0.135 ms on the 16 -> 16 layer): stages are then released in bursts
+  *smem = fixed + (uint32_t)na * stage;
   return true;
 }
 
@@ -667,7 +767,7 @@ int launch_g(const ConvArgs& a, const RowgGeom& g, uint32_t smem, cudaStream_t s
   DG_TRY(dg_device_enter(attr_done, &dev, &first));
   if (first) {
     DG_CHECK_CUDA(cudaFuncSetAttribute(conv_rowg_kernel<KS, CK, CO, EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       227 * 1024));
+                                       227 * 1024 - GTRACE_SMEM));
     dg_device_mark(attr_done, dev);
   }
   RowgMaps tm;
@@ -785,3 +885,9 @@ int conv_fwd_rowg(const ConvArgs& a, cudaStream_t st) {
   DG_REQUIRE(r == 1, "conv_fwd_rowg: no instantiation for this shape");
   return 0;
 }
+
+#ifdef DG_ROWG_TRACE
+extern "C" int depgan_dbg_set_rowg_trace(long long* p) {
+  return (int)cudaMemcpyToSymbol(g_rowg_trace, &p, sizeof(p));
+}
+#endif

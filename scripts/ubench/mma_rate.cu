@@ -14,15 +14,18 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // all parameters are compile-time so that the descriptors stay on the uniform datapath (warp-converged issue)
-template <int N, int ND, int DOFF, int DSTRIDE, int ACCUM, int ASTEP>
+template <int N, int ND, int DOFF, int DSTRIDE, int ACCUM, int ASTEP, int CEVERY = 0>
 __global__ void __launch_bounds__(128, 1) mma_rate(long long* out, int reps) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t bar2[2];  // CEVERY > 0: a commit to these after every CEVERY instructions (never waited for)
   __shared__ uint32_t tmem_slot;
   const uint32_t base = (smem_u32(smem) + 1023u) & ~1023u;
   for (int i = threadIdx.x; i < 48 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar2[1])));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
@@ -53,6 +56,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate(long long* out, int reps) {
               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(da), "l"(db), "r"(idesc),
               "r"((uint32_t)ACCUM)
               : "memory");
+          if (CEVERY > 0 && (u + 1) % CEVERY == 0) {
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[0])) : "memory");
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2[1])) : "memory");
+          }
         }
       }
       __syncwarp();
@@ -74,15 +81,15 @@ __global__ void __launch_bounds__(128, 1) mma_rate(long long* out, int reps) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-template <int N, int ND, int DOFF, int DSTRIDE, int ACCUM, int ASTEP>
+template <int N, int ND, int DOFF, int DSTRIDE, int ACCUM, int ASTEP, int CEVERY = 0>
 void run(long long* d) {
   const int reps = 512;
-  cudaFuncSetAttribute(mma_rate<N, ND, DOFF, DSTRIDE, ACCUM, ASTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-  for (int rep = 0; rep < 2; ++rep) mma_rate<N, ND, DOFF, DSTRIDE, ACCUM, ASTEP><<<148, 128, 64 * 1024>>>(d, reps);
+  cudaFuncSetAttribute(mma_rate<N, ND, DOFF, DSTRIDE, ACCUM, ASTEP, CEVERY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  for (int rep = 0; rep < 2; ++rep) mma_rate<N, ND, DOFF, DSTRIDE, ACCUM, ASTEP, CEVERY><<<148, 128, 64 * 1024>>>(d, reps);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[2];
   cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
-  printf("%-6d %-4d %-6d %-8d %-6d %-6d | %10.1f %10.1f  %s\n", N, ND, DOFF, DSTRIDE, ACCUM, ASTEP, (double)h[0] / reps,
+  printf("%-6d %-4d %-6d %-8d %-6d %-6d c%-2d | %10.1f %10.1f  %s\n", N, ND, DOFF, DSTRIDE, ACCUM, ASTEP, CEVERY, (double)h[0] / reps,
          (double)h[1] / reps, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
@@ -100,5 +107,8 @@ int main() {
   run<256, 1, 0, 0, 1, 0>(d);  run<256, 2, 0, 256, 1, 0>(d);
   run<16, 1, 0, 0, 1, 0>(d);   run<16, 1, 0, 0, 1, 2>(d);    run<48, 1, 0, 0, 1, 0>(d);    run<80, 1, 0, 0, 1, 0>(d);   run<80, 1, 0, 0, 1, 2>(d);
   run<160, 1, 0, 0, 1, 0>(d);  run<160, 1, 0, 0, 1, 4>(d);   run<192, 1, 0, 0, 1, 4>(d);   run<192, 1, 0, 0, 1, 8>(d);
+  // two commits after every 4 / 8 instructions (the row kernels commit "stage free" + "row done" per input row)
+  run<80, 1, 0, 0, 1, 2, 4>(d);  run<80, 1, 0, 0, 1, 2, 8>(d);  run<192, 1, 0, 0, 1, 4, 4>(d);  run<192, 1, 0, 0, 1, 4, 8>(d);
+  run<16, 1, 0, 0, 1, 2, 1>(d);  run<96, 1, 0, 0, 1, 4, 2>(d);
   return 0;
 }
