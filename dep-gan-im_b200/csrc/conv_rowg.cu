@@ -47,7 +47,7 @@ namespace {
 constexpr int RG_THREADS = 384;
 constexpr int BWG = 128;   // pixels per M block
 constexpr int NQG = 64;    // "input row done" barriers (ring)
-constexpr int NREC = 16;   // row records for the issuer (ring; more than the deepest row-tile ring)
+constexpr int NREC = 32;   // row records for the issuer (ring; more than the deepest row-tile ring)
 constexpr int NSIDEG = 4;  // side-row stages (one stage = one 128-pixel row of every side tensor)
 
 #ifdef DG_ROWG_TRACE  // timing experiment only: event clocks of CTA 0 (roles: 0 producer, 1 issuer, 2 epilogue warp 0, 3 warp 4)
@@ -92,6 +92,10 @@ struct RG {
   static constexpr int CW = CO < 32 ? CO : 32;                              // accumulator columns per epilogue pass
   static constexpr int NH = CO / CW;                                        // passes per row
   static constexpr int NSIDE = CO == 64 ? 3 : NSIDEG;                       // side-row stages (shared memory is tight at 64)
+  // Output / side / pooled rows move through TMA as 128-byte "super pixels" (PG = 4 / 2 / 1 neighbouring pixels of
+  // 16 / 32 / 64 channels): a 32- or 64-byte innermost box costs a shared-memory cycle per pixel, a 128-byte one per PG
+  // pixels, and the shared-memory port is what these kernels run out of.
+  static constexpr int PG = 128 / (int)OSPAN;
   static_assert(NBLK >= KS + RP + 1, "TMEM ring too small for the taps in flight");
   static_assert(B_TILE % 256 == 0 && (CO * SPAN) % 256 == 0, "weight tiles must keep the swizzle phase");
 };
@@ -101,6 +105,7 @@ struct RowgGeom {
   int cblocks;           // 128-pixel column blocks per image row
   int na;                // row-tile ring depth
   int batch;             // input rows the issuer issues per wait (<= na)
+  int pf;                // input rows the L2 prefetch runs ahead of the loads (0: off)
   int n_side;            // side tensors per output row (0..2)
   int pool;              // EPI bit 2 active
   long long rows_total;  // N * cblocks * H output rows (of 128 pixels)
@@ -155,6 +160,12 @@ __device__ __forceinline__ uint2 ld_acquire_shared_v2(uint32_t addr) {  // one 6
   unsigned long long v;
   asm volatile("ld.acquire.cta.shared::cta.b64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return make_uint2((uint32_t)v, (uint32_t)(v >> 32));
+}
+// TMA prefetch of one tile into L2 (no shared-memory destination)
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ uint32_t ld_shared_u32(uint32_t addr) {
   uint32_t v;
@@ -300,7 +311,18 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
       uint32_t pq = 0;  // input-row sequence number
       for (; si.valid(); si.next()) {
         const int x0 = si.cb * BWG - G::PAD, r0 = si.r0 - G::PAD;
-        for (int j = 0; j < si.cnt + KS - 1; ++j, ++pq) {
+        const int nin = si.cnt + KS - 1;
+        // optional L2 prefetch g.pf input rows ahead of the loads (an experiment that did not pay, see plan_g)
+        auto prefetch_row = [&](int jr) {
+          for (int c = 0; c < nchunks; ++c) {
+            const bool first = c < g.nchunk0;
+            tma_prefetch_4d(first ? &tm.a0 : &tm.a1, (first ? c : c - g.nchunk0) * CK, x0, r0 + jr, si.n);
+          }
+        };
+        if (g.pf > 0 && elect_one())
+          for (int jr = 0; jr < g.pf && jr < nin; ++jr) prefetch_row(jr);
+        __syncwarp();
+        for (int j = 0; j < nin; ++j, ++pq) {
           GTRACE(0, (int)pq, 0);
           // the stage is free once the row that used it last (na rows ago) has been multiplied: that row's "done"
           // barrier (one commit per row serves the epilogue and this ring)
@@ -310,12 +332,17 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
           }
           GTRACE(0, (int)pq, 1);
           if (elect_one()) {
+            if (g.pf > 0 && j + g.pf < nin) prefetch_row(j + g.pf);
+#ifdef DG_ROWG_NOLOAD  // timing experiment only: the row tiles are never loaded (results are garbage)
+            mbar_arrive(fullA + 8 * ra.idx);
+#else
             mbar_expect_tx(fullA + 8 * ra.idx, (uint32_t)nchunks * G::A_TX);
             for (int c = 0; c < nchunks; ++c) {
               const bool first = c < g.nchunk0;
               tma_load_4d(a_base + ra.idx * a_stage + (uint32_t)c * G::A_STAGE, first ? &tm.a0 : &tm.a1,
                           fullA + 8 * ra.idx, (first ? c : c - g.nchunk0) * CK, x0, r0 + j, si.n);
             }
+#endif
           }
           __syncwarp();
           ra.advance(g.na);
@@ -439,8 +466,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
             if (elect_one()) {
               const uint32_t dst = s_base + (uint32_t)(rs.idx * g.n_side) * G::SIDE_ROW;
               mbar_expect_tx(sideFull + 8 * rs.idx, (uint32_t)g.n_side * G::SIDE_ROW);
-              tma_load_4d(dst, &tm.s0, sideFull + 8 * rs.idx, 0, si.cb * BWG, si.r0 + i, si.n);
-              if (g.n_side == 2) tma_load_4d(dst + G::SIDE_ROW, &tm.s1, sideFull + 8 * rs.idx, 0, si.cb * BWG, si.r0 + i, si.n);
+              tma_load_4d(dst, &tm.s0, sideFull + 8 * rs.idx, 0, si.cb * BWG / G::PG, si.r0 + i, si.n);
+              if (g.n_side == 2)
+                tma_load_4d(dst + G::SIDE_ROW, &tm.s1, sideFull + 8 * rs.idx, 0, si.cb * BWG / G::PG, si.r0 + i, si.n);
             }
             __syncwarp();
             rs.advance(NSD);
@@ -463,13 +491,14 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
     // staging: this warp's NSLOT slots of [RP rows][32 pixels][OSPAN B], 16-byte units XOR-swizzled like the TMA
     const uint32_t w_o = o_base + (uint32_t)warp * NSLOT * G::WSLOT;
     const uint32_t w_p = p_base + (uint32_t)warp * NSLOT * G::PSLOT;
-    const uint32_t p_off = (uint32_t)lane * OSPAN;
-    const uint32_t p_xor = (p_off >> 7) & (UNITS - 1);
-    const uint32_t pp_off = (uint32_t)(lane >> 1) * OSPAN;  // pooled pixel of the even lanes
-    const uint32_t pp_xor = (pp_off >> 7) & (UNITS - 1);
-    // side rows are [128 pixels][OSPAN B] with the same swizzle
-    const uint32_t sp_off = (uint32_t)m * OSPAN;
-    const uint32_t sp_xor = (sp_off >> 7) & (UNITS - 1);
+    // Rows of super pixels [pixels / PG][128 B] in the TMA's 128-byte swizzle: 16-byte unit j of super pixel s lives at
+    // s * 128 + ((j ^ (s & 7)) << 4); pixel p of the row is units (p % PG) * UNITS .. + UNITS - 1 of super pixel p / PG.
+    // x_off = byte offset of the super pixel, x_u0 = first unit of the pixel, x_xor = the super pixel's XOR term.
+    constexpr uint32_t PG = (uint32_t)G::PG;
+    const uint32_t p_off = ((uint32_t)lane / PG) * 128u, p_u0 = ((uint32_t)lane % PG) * UNITS, p_xor = ((uint32_t)lane / PG) & 7u;
+    const uint32_t pl = (uint32_t)(lane >> 1);  // pooled pixel of the even lanes
+    const uint32_t pp_off = (pl / PG) * 128u, pp_u0 = (pl % PG) * UNITS, pp_xor = (pl / PG) & 7u;
+    const uint32_t sp_off = ((uint32_t)m / PG) * 128u, sp_u0 = ((uint32_t)m % PG) * UNITS, sp_xor = ((uint32_t)m / PG) & 7u;
     const uint32_t mask_off = has_add ? G::SIDE_ROW : 0u;
     const uint32_t t_lane = tmem_base + ((uint32_t)(qd * 32) << 16);
 
@@ -516,6 +545,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
         mbar_wait(rowDone + 8 * (qd_ & (NQG - 1)), (qd_ / NQG) & 1u);
         tc_fence_after();
         if (trole < 4) GTRACE(trole, (int)o, 1);
+#ifdef DG_ROWG_NOEPI  // timing experiment only: blocks are only zeroed and handed back (1), not even read (2)
+        real[0] = real[1] = false;
+#endif
         const bool any_real = real[0] || real[1];
         const uint32_t slot = nstaged % NSLOT;
         if (any_real) {
@@ -530,7 +562,11 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
           uint32_t va[RP][CW];
           const uint32_t blk[2] = {t_lane + (o & (NBLK - 1)) * CO + (uint32_t)(h * CW),
                                    t_lane + ((o + 1u) & (NBLK - 1)) * CO + (uint32_t)(h * CW)};
+#if defined(DG_ROWG_NOEPI) && DG_ROWG_NOEPI == 1
+          if (true) {
+#else
           if (any_real) {
+#endif
             tg_ld<CW>(blk[0], va[0]);
             if (RP == 2 && gsz == 2) tg_ld<CW>(blk[1], va[RP - 1]);
             tg_ld_wait();
@@ -563,7 +599,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
                 if (E_RES) {
 #pragma unroll
                   for (int uu = 0; uu < CW / 8; ++uu) {
-                    const uint4 qv = *reinterpret_cast<const uint4*>(sgen + (((uint32_t)(h * (CW / 8) + uu) ^ sp_xor) << 4));
+                    const uint4 qv = *reinterpret_cast<const uint4*>(sgen + (((sp_u0 + (uint32_t)(h * (CW / 8) + uu)) ^ sp_xor) << 4));
                     const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -576,7 +612,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
                 if (has_add) {
 #pragma unroll
                   for (int uu = 0; uu < CW / 8; ++uu) {
-                    const uint4 qv = *reinterpret_cast<const uint4*>(sgen + (((uint32_t)(h * (CW / 8) + uu) ^ sp_xor) << 4));
+                    const uint4 qv = *reinterpret_cast<const uint4*>(sgen + (((sp_u0 + (uint32_t)(h * (CW / 8) + uu)) ^ sp_xor) << 4));
                     const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -590,7 +626,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
 #pragma unroll
                   for (int uu = 0; uu < CW / 8; ++uu) {
                     const uint4 qv =
-                        *reinterpret_cast<const uint4*>(sgen + mask_off + (((uint32_t)(h * (CW / 8) + uu) ^ sp_xor) << 4));
+                        *reinterpret_cast<const uint4*>(sgen + mask_off + (((sp_u0 + (uint32_t)(h * (CW / 8) + uu)) ^ sp_xor) << 4));
                     const uint32_t wv[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -618,7 +654,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
                 uint32_t* hp = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) hp[e] = pack_h2(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16);
-                *reinterpret_cast<uint4*>(ogen + (((uint32_t)(h * (CW / 8) + uu) ^ p_xor) << 4)) = pk;
+                *reinterpret_cast<uint4*>(ogen + (((p_u0 + (uint32_t)(h * (CW / 8) + uu)) ^ p_xor) << 4)) = pk;
                 if (E_POOL) {
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
@@ -643,7 +679,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
               const uint32_t o_ = __shfl_xor_sync(0xffffffffu, pmax[uu * 4 + e], 1);
               hp[e] = max_h2(pmax[uu * 4 + e], o_, f16);
             }
-            if ((lane & 1) == 0) *reinterpret_cast<uint4*>(pgen + (((uint32_t)uu ^ pp_xor) << 4)) = pk;
+            if ((lane & 1) == 0) *reinterpret_cast<uint4*>(pgen + (((pp_u0 + (uint32_t)uu) ^ pp_xor) << 4)) = pk;
           }
         }
         if (trole < 4) GTRACE(trole, (int)o, 4);
@@ -660,11 +696,15 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (trole < 4) GTRACE(trole, (int)o, 6);
+#ifdef DG_ROWG_NOSTORE  // timing experiment only: nothing is written
+          if (false) {
+#else
           if (lane == 0) {
+#endif
             const int row = si.r0 + (real[0] ? i0 : i0 + 1);
-            if (real[0] && real[1]) tma_store_4d(&tm.out2, w_o + slot * G::WSLOT, 0, xw, row, si.n);
-            else tma_store_4d(&tm.out1, w_o + slot * G::WSLOT, 0, xw, row, si.n);
-            if (E_POOL) tma_store_4d(&tm.pool, w_p + slot * G::PSLOT, 0, xw >> 1, row >> 1, si.n);
+            if (real[0] && real[1]) tma_store_4d(&tm.out2, w_o + slot * G::WSLOT, 0, xw / (int)PG, row, si.n);
+            else tma_store_4d(&tm.out1, w_o + slot * G::WSLOT, 0, xw / (int)PG, row, si.n);
+            if (E_POOL) tma_store_4d(&tm.pool, w_p + slot * G::PSLOT, 0, (xw >> 1) / (int)PG, row >> 1, si.n);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           if (trole < 4) GTRACE(trole, (int)o, 7);
@@ -751,8 +791,13 @@ bool plan_g(const ConvArgs& a, RowgGeom* g, uint32_t* smem) {
   const uint32_t stage = (uint32_t)nchunks * G::A_STAGE;  // one ring stage = one input row, all its chunks
   if (fixed + 2u * stage > SMEM_BUDGET_G) return false;
   int na = (int)((SMEM_BUDGET_G - fixed) / stage);
-  if (na > 8) na = 8;  // eight input rows in flight is plenty
+  static const int na_cap = getenv("DEPGAN_ROWG_NA") ? atoi(getenv("DEPGAN_ROWG_NA")) : 8;  // A/B switch
+  if (na > na_cap) na = na_cap;
   g->na = na;
+  // measured (profiles/r02_rowg_pf_sweep.txt): L2 prefetch 8 / 16 / 32 rows ahead is 2-12 % SLOWER on every shape and a
+  // 16-deep ring equals the 8-deep one, so neither the HBM latency nor the ring depth bounds this kernel; off by default
+  static const int pf_env = getenv("DEPGAN_ROWG_PF") ? atoi(getenv("DEPGAN_ROWG_PF")) : 0;  // A/B switch
+  g->pf = pf_env;
   g->batch = 1;  // measured: batches of 4 were slower (0.119 -> 0.135 ms on the 16 -> 16 layer): stages are then released in bursts
   *smem = fixed + (uint32_t)na * stage;
   return true;
@@ -775,8 +820,10 @@ int launch_g(const ConvArgs& a, const RowgGeom& g, uint32_t smem, cudaStream_t s
   if (a.C1 > 0) DG_TRY(make_map_g(&tm.a1, a.in1, a.C1, a.W, a.H, a.N, CK, G::TILE_PX, 1, "input 1"));
   else tm.a1 = tm.a0;
   DG_TRY(make_w_map_g(&tm.b, a.w_tc, a.C0 + a.C1, KS * KS * CO, CK, CO));
-  DG_TRY(make_map_g(&tm.out1, a.out, CO, a.W, a.H, a.N, CO, 32, 1, "output"));
-  DG_TRY(make_map_g(&tm.out2, a.out, CO, a.W, a.H, a.N, CO, 32, G::RP, "output (row pair)"));
+  // output, side and pooled tensors as rows of 128-byte super pixels: (C * PG, W / PG, H, N)
+  constexpr int PG = G::PG, SC = CO * G::PG;
+  DG_TRY(make_map_g(&tm.out1, a.out, SC, a.W / PG, a.H, a.N, SC, 32 / PG, 1, "output"));
+  DG_TRY(make_map_g(&tm.out2, a.out, SC, a.W / PG, a.H, a.N, SC, 32 / PG, G::RP, "output (row pair)"));
   tm.s0 = tm.s1 = tm.pool = tm.out1;
   const void* side[2] = {nullptr, nullptr};
   if (a.film_g) side[0] = a.res;
@@ -785,9 +832,10 @@ int launch_g(const ConvArgs& a, const RowgGeom& g, uint32_t smem, cudaStream_t s
     if (a.add_src) side[k++] = a.add_src;
     if (a.mask_src) side[k++] = a.mask_src;
   }
-  if (side[0]) DG_TRY(make_map_g(&tm.s0, side[0], CO, a.W, a.H, a.N, CO, BWG, 1, "side input"));
-  if (side[1]) DG_TRY(make_map_g(&tm.s1, side[1], CO, a.W, a.H, a.N, CO, BWG, 1, "side input"));
-  if (a.pool_out) DG_TRY(make_map_g(&tm.pool, a.pool_out, CO, a.W / 2, a.H / 2, a.N, CO, 16, 1, "pooled output"));
+  if (side[0]) DG_TRY(make_map_g(&tm.s0, side[0], SC, a.W / PG, a.H, a.N, SC, BWG / PG, 1, "side input"));
+  if (side[1]) DG_TRY(make_map_g(&tm.s1, side[1], SC, a.W / PG, a.H, a.N, SC, BWG / PG, 1, "side input"));
+  if (a.pool_out)
+    DG_TRY(make_map_g(&tm.pool, a.pool_out, SC, a.W / 2 / PG, a.H / 2, a.N, SC, 16 / PG, 1, "pooled output"));
   const long long want = (g.rows_total + 7) / 8;  // at least a few rows per CTA, so the halo rows stay cheap
   const int grid = want < g_sms_g ? (int)(want < 1 ? 1 : want) : g_sms_g;
   DG_CHECK_CUDA(dg_launch_pdl(conv_rowg_kernel<KS, CK, CO, EPI, F16>, dim3(grid), dim3(RG_THREADS), smem, st, tm, a, g));
