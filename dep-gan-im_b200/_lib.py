@@ -62,6 +62,19 @@ SIGNATURES = {
     "depgan_uresnet_labels": (_I, [_P, _D, _I, _P, _P, _P, _LL, _P]),
     "depgan_label_confusion": (_I, [_P, _P, _LL, _P, _P]),
     "depgan_set_sync_hook": (_I, [_P, _P, _I]),
+    "depgan_nccl_load": (_I, [C.c_char_p]),
+    "depgan_nccl_unique_id": (_I, [_P]),
+    "depgan_nccl_init": (_I, [C.POINTER(_P), _I, _I, _P]),
+    "depgan_nccl_destroy": (_I, [_P]),
+    "depgan_allreduce_attach": (_I, [_P, _P, _I]),
+    "depgan_peer_create": (_P, [_LL, _I, _I]),
+    "depgan_peer_handle": (_I, [_P, _P]),
+    "depgan_peer_connect": (_I, [_P, _P]),
+    "depgan_peer_destroy": (None, [_P]),
+    "depgan_peer_attach": (_I, [_P, _P]),
+    "depgan_dp_update": (_I, [_P, _P, _P, _I, _F, _F, _F, _F, _P, _I, _P]),
+    "depgan_dp_allreduce_grads": (_I, [_P, _P, _I, _P]),
+    "depgan_dp_allreduce_f64": (_I, [_P, _P, _I, _P]),
     "depgan_launch_count": (_LL, []),
     "depgan_profile_begin": (_I, []),
     "depgan_profile_end": (_I, [_P, _P, _P, _P, _I]),

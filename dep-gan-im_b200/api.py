@@ -93,6 +93,9 @@ class _Net:
             if getattr(self, "handle", None):
                 _lib.lib().depgan_net_destroy(self.handle)
                 self.handle = None
+            if getattr(self, "_peer", None):
+                _lib.lib().depgan_peer_destroy(self._peer)
+                self._peer = None
         except Exception:
             pass
 
@@ -143,6 +146,62 @@ class _Net:
                                                    self.iterations, lr, beta_1, beta_2, eps, grad_scale,
                                                    _stream(torch)), "adam_step")
             self.prepare()
+
+    # ---- data-parallel update through the C ABI (dp.cu): sum of the buckets over the ranks + Adam + re-pack -------
+    def attach_collective(self, kind, *, comm=None, world=1, rank=0, exchange=None):
+        """kind 'peer': a CUDA-IPC mailbox per rank and the fused reduce + Adam kernel (one node); `exchange(bytes) ->
+        [bytes of every rank, in rank order]` is the caller's transport for the 64-byte handles.  kind 'nccl': attaches
+        the communicator `comm` (an ncclComm_t as an integer, from depgan_nccl_init)."""
+        L = _lib.lib()
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            if kind == "peer":
+                peer = L.depgan_peer_create(self.n_floats, int(world), int(rank))
+                if not peer:
+                    raise RuntimeError("peer_create: " + _lib.last_error())
+                buf = C.create_string_buffer(64)
+                _lib.check(L.depgan_peer_handle(peer, buf), "peer_handle")
+                handles = b"".join(exchange(buf.raw))
+                if len(handles) != 64 * int(world):
+                    raise RuntimeError("peer handle exchange returned %d bytes for %d ranks" % (len(handles), world))
+                _lib.check(L.depgan_peer_connect(peer, handles), "peer_connect")
+                _lib.check(L.depgan_peer_attach(self.handle, peer), "peer_attach")
+                self._peer = peer
+            elif kind == "nccl":
+                _lib.check(L.depgan_allreduce_attach(self.handle, C.c_void_p(comm), int(world)), "allreduce_attach")
+            else:
+                raise ValueError("collective must be 'peer' or 'nccl'")
+        self._collective = kind
+
+    def _adam_state(self):
+        torch = self._torch
+        if self.adam_m is None:
+            self.adam_m = torch.zeros_like(self.params)
+            self.adam_v = torch.zeros_like(self.params)
+
+    def dp_update(self, lr=1e-4, beta_1=0.0, beta_2=0.9, eps=1e-7, extra=None, n_extra=0):
+        """All-reduce of the gradient bucket over the attached transport + Keras Adam + prepare in one native call;
+        `extra` (float64 CUDA tensor): n_extra loss partial sums reduced in the same pass, in place."""
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            self._adam_state()
+            self.iterations += 1
+            _lib.check(_lib.lib().depgan_dp_update(self.handle, self.adam_m.data_ptr(), self.adam_v.data_ptr(),
+                                                   self.iterations, lr, beta_1, beta_2, eps,
+                                                   extra.data_ptr() if extra is not None else None, int(n_extra),
+                                                   _stream(torch)), "dp_update")
+
+    def dp_allreduce_grads(self, extra=None, n_extra=0):
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_dp_allreduce_grads(self.handle, extra.data_ptr() if extra is not None else None,
+                                                            int(n_extra), _stream(torch)), "dp_allreduce_grads")
+
+    def dp_allreduce_f64(self, buf, n):
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().depgan_dp_allreduce_f64(self.handle, buf.data_ptr(), int(n), _stream(torch)),
+                       "dp_allreduce_f64")
 
     def debug_activation(self, name, n):
         torch = self._torch

@@ -100,6 +100,11 @@ struct depgan_net {
   void* c_pool[4] = {};   // pooled outputs (after convs 1,3,5,7)
   float* c_out = nullptr;  // (max_batch) critic scores
 
+  // ---- data-parallel update (dp.cu): an attached NCCL communicator and / or peer-memory mailbox (not owned) ----
+  void* nccl_comm = nullptr;
+  struct depgan_peer* peer = nullptr;
+  int dp_world = 1;
+
   // ---- training scratch (net_train.cu); owned by the handle ----
   struct Train* tr = nullptr;
   depgan_net() = default;

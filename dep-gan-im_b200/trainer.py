@@ -12,13 +12,15 @@ noise]).  Returned values are computed from the pre-update weights; each ``*_tra
 Keras-form Adam step (lr 1e-4, beta_1 0, beta_2 0.9; TG:549,568,594) on exactly one network.
 
 Data parallel: when ``torch.distributed`` is initialised with world size W, every rank passes its
-shard of the global batch; gradients are summed with one NCCL all-reduce of the flat bucket, the loss partial sums
-(incl. the batch-global dice / volume terms) with a tiny all-reduce, so every rank reports the global-batch values
-and applies the identical update.
+shard of the global batch; the flat gradient buckets and the loss partial sums (incl. the batch-global dice / volume
+terms) are summed over the ranks by the native library (``depgan_dp_update``: a fused reduce + Adam kernel over
+CUDA-IPC peer memory on one node, or NCCL), so every rank reports the global-batch values and applies the identical
+update; torch.distributed only carries the 64-byte handles / the NCCL id at start-up.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -26,6 +28,18 @@ from . import _lib
 from .api import _stream, _torch
 
 __all__ = ["DepGanTrainer", "ScalarLog", "epoch_schedule"]
+
+
+def _find_nccl():
+    """Path of the NCCL library PyTorch ships (the wheel's nvidia/nccl/lib), or None to let dlopen search."""
+    try:
+        import nvidia.nccl as _n
+        from pathlib import Path
+        for p in Path(_n.__path__[0]).glob("lib/libnccl.so*"):
+            return str(p).encode()
+    except Exception:
+        pass
+    return None
 
 
 def epoch_schedule(batches, gen_iterations, Diters=5):
@@ -72,7 +86,8 @@ class ScalarLog:
 
 
 class DepGanTrainer:
-    def __init__(self, netG, netD_y2, netD_dem, thr, lrD=1e-4, lrG=1e-4, beta_1=0.0, beta_2=0.9, distributed=None):
+    def __init__(self, netG, netD_y2, netD_dem, thr, lrD=1e-4, lrG=1e-4, beta_1=0.0, beta_2=0.9, distributed=None,
+                 collective=None):
         torch = _torch()
         self.torch = torch
         self.G, self.Dy2, self.Ddem = netG, netD_y2, netD_dem
@@ -87,10 +102,54 @@ class DepGanTrainer:
             distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         self.dist = dist if distributed else None
         self.world = dist.get_world_size() if distributed else 1
+        # Transport of the gradient sum: 'peer' = the native fused reduce + Adam kernel over CUDA-IPC
+        # mailboxes (one node, the default), 'nccl' = ncclAllReduce issued by the native library on its own communicator,
+        # 'torch' = torch.distributed.all_reduce + separate Adam (the round-1 path, kept for A/B measurements).
+        self.collective = None
+        if distributed:
+            self.collective = collective or os.environ.get("DEPGAN_COLLECTIVE", "peer")
+            self._attach_collective()
+        self.ex64 = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.out4 = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.out6 = torch.zeros(6, dtype=torch.float32, device=self.device)
         self.sums = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.gen_iterations = 0
+
+    def _attach_collective(self):
+        dist, rank = self.dist, self.dist.get_rank()
+        nets = (self.G, self.Dy2, self.Ddem)
+        if self.collective == "peer":
+            def exchange(mine):
+                got = [None] * self.world
+                dist.all_gather_object(got, mine)
+                return got
+            for net in nets:
+                net.attach_collective("peer", world=self.world, rank=rank, exchange=exchange)
+            dist.barrier()
+        elif self.collective == "nccl":
+            L = _lib.lib()
+            _lib.check(L.depgan_nccl_load(_find_nccl()), "nccl_load")
+            ident = [None]
+            if rank == 0:
+                buf = C.create_string_buffer(128)
+                _lib.check(L.depgan_nccl_unique_id(buf), "nccl_unique_id")
+                ident = [buf.raw]
+            dist.broadcast_object_list(ident, src=0)
+            comm = C.c_void_p()
+            with self.torch.cuda.device(self.device):
+                _lib.check(L.depgan_nccl_init(C.byref(comm), self.world, rank, ident[0]), "nccl_init")
+            self._nccl_comm = comm
+            for net in nets:
+                net.attach_collective("nccl", comm=comm.value, world=self.world)
+        elif self.collective != "torch":
+            raise ValueError("collective must be 'peer', 'nccl' or 'torch'")
+
+    def _update(self, net, lr, extra=None, n_extra=0):
+        """One optimizer step of `net` on the global-batch gradient."""
+        if self.collective in ("peer", "nccl"):
+            net.dp_update(lr, self.b1, self.b2, extra=extra, n_extra=n_extra)
+        else:
+            net.adam_step(lr, self.b1, self.b2)
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _dev(self, a, dtype=None):
@@ -106,7 +165,7 @@ class DepGanTrainer:
             self.dist.all_reduce(net.grads, op=self.dist.ReduceOp.SUM)
 
     # ---- critics (TG:523-571) -------------------------------------------------------------------------
-    def critic_grads_device(self, which, real2, x1, z, ep):
+    def critic_grads_device(self, which, real2, x1, z, ep, reduce=True):
         """Device tensors in; leaves dLoss/dtheta in the critic's flat gradient buffer and returns the float32
         CUDA tensor [loss_real, loss_fake, gradient_penalty, loss] for the GLOBAL batch."""
         torch = self.torch
@@ -118,19 +177,33 @@ class DepGanTrainer:
             _lib.check(_lib.lib().depgan_critic_grads(D.handle, self.G.handle, which, real2.data_ptr(), x1.data_ptr(),
                                                       z.data_ptr(), ep.data_ptr(), self.out4.data_ptr(), n,
                                                       n * self.world, _stream(torch)), "critic_grads")
-        if self.dist is not None:
+        if self.collective == "torch":
             self.dist.all_reduce(self.out4, op=self.dist.ReduceOp.SUM)
             self._allreduce_grads(D)
+        elif self.dist is not None and reduce:
+            self.ex64[:4].copy_(self.out4)
+            D.dp_allreduce_grads(self.ex64, 4)
+            self.out4.copy_(self.ex64[:4])
         return self.out4
+
+    def _critic_update_native(self, D):
+        """Native transports: the loss partial sums ride along with the gradient bucket of the fused update."""
+        self.ex64[:4].copy_(self.out4)
+        D.dp_update(self.lrD, self.b1, self.b2, extra=self.ex64, n_extra=4)
+        self.out4.copy_(self.ex64[:4])
 
     def _critic_train(self, which, inputs, update=True):
         real2, x1, z, ep = [self._dev(a) for a in inputs]
         ep = ep.reshape(-1).contiguous()
-        out = self.critic_grads_device(which, real2, x1, z, ep)
-        vals = out.cpu().numpy().copy()
+        D = self.Dy2 if which == 0 else self.Ddem
+        native = self.collective in ("peer", "nccl")
+        out = self.critic_grads_device(which, real2, x1, z, ep, reduce=not (native and update))
         if update:
-            D = self.Dy2 if which == 0 else self.Ddem
-            D.adam_step(self.lrD, self.b1, self.b2)
+            if native:
+                self._critic_update_native(D)
+            else:
+                D.adam_step(self.lrD, self.b1, self.b2)
+        vals = out.cpu().numpy().copy()
         self.last_gp = float(vals[2])
         return [np.float32(vals[0]), np.float32(vals[1])]
 
@@ -141,7 +214,7 @@ class DepGanTrainer:
         return self._critic_train(1, inputs, update)
 
     # ---- generator (TG:573-598) -----------------------------------------------------------------------
-    def gen_device(self, x1, real2, z, grads):
+    def gen_device(self, x1, real2, z, grads, update=False):
         torch = self.torch
         n = int(x1.shape[0])
         L = _lib.lib()
@@ -151,13 +224,24 @@ class DepGanTrainer:
                           z.data_ptr(), self.thr, self.out6.data_ptr(), self.sums.data_ptr(), n, n * self.world,
                           _stream(torch)), "gen_grads" if grads else "gen_eval")
             if self.dist is not None:  # batch-global dice / volume / means need the summed partials
-                part = self.sums[:6].clone()
-                self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM)
-                self.sums[:6] = part
+                if self.collective == "torch":
+                    part = self.sums[:6].clone()
+                    self.dist.all_reduce(part, op=self.dist.ReduceOp.SUM)
+                    self.sums[:6] = part
+                    if grads:
+                        self._allreduce_grads(self.G)
+                elif grads and update:      # the sums ride along with the bucket of the fused update
+                    self.G.dp_update(self.lrG, self.b1, self.b2, extra=self.sums, n_extra=6)
+                elif grads:
+                    self.G.dp_allreduce_grads(self.sums, 6)
+                else:
+                    self.G.dp_allreduce_f64(self.sums, 6)
                 _lib.check(L.depgan_gen_loss_finalize(self.out6.data_ptr(), self.sums.data_ptr(), _stream(torch)),
                            "gen_loss_finalize")
-                if grads:
-                    self._allreduce_grads(self.G)
+            elif grads and update:
+                self.G.adam_step(self.lrG, self.b1, self.b2)
+            if self.collective == "torch" and grads and update:
+                self.G.adam_step(self.lrG, self.b1, self.b2)
         return self.out6
 
     def netG_no_update(self, inputs):
@@ -166,16 +250,19 @@ class DepGanTrainer:
 
     def netG_train(self, inputs, update=True):
         x1, real2, z = [self._dev(a) for a in inputs]
-        vals = self.gen_device(x1, real2, z, True).cpu().numpy().copy()
-        if update:
-            self.G.adam_step(self.lrG, self.b1, self.b2)
+        vals = self.gen_device(x1, real2, z, True, update=update).cpu().numpy().copy()
         return [np.float32(v) for v in vals]
 
     # ---- fully asynchronous device-side variants (no host round trip inside a generator iteration) -------
     def critic_update_device(self, which, real2, x1, z, ep):
         """One critic update (grads + all-reduce + Adam) on CUDA tensors; returns the loss tensor (no sync)."""
-        out = self.critic_grads_device(which, real2, x1, z, ep)
-        (self.Dy2 if which == 0 else self.Ddem).adam_step(self.lrD, self.b1, self.b2)
+        D = self.Dy2 if which == 0 else self.Ddem
+        native = self.collective in ("peer", "nccl")
+        out = self.critic_grads_device(which, real2, x1, z, ep, reduce=not native)
+        if native:
+            self._critic_update_native(D)
+        else:
+            D.adam_step(self.lrD, self.b1, self.b2)
         return out
 
     def gen_iteration_device(self, crit_y2_batches, crit_dem_batches, x1, real2, noises):
@@ -191,8 +278,7 @@ class DepGanTrainer:
             losses[k] = self.gen_device(x1, real2, noises[k], False)[0]
         sel = torch.argmin(losses)                        # TG:875-876
         z = noises.index_select(0, sel.reshape(1))[0].contiguous()
-        out = self.gen_device(x1, real2, z, True)
-        self.G.adam_step(self.lrG, self.b1, self.b2)
+        out = self.gen_device(x1, real2, z, True, update=True)
         self.gen_iterations += 1
         return losses, out
 

@@ -159,6 +159,40 @@ int depgan_profile_end(double* ms_by_class, double* flops_by_class, double* byte
 int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, long long cap_floats,
                             long long* n_floats, int n, void* stream);
 
+/* ---- data-parallel update without Python in the loop (depgan_allreduce_attach; TG:549, 568, 594 applied
+ * to the global batch) ----
+ * After depgan_critic_grads / depgan_gen_grads (called with the GLOBAL batch size) each rank's gradient bucket holds its
+ * shard's share of the global-batch gradient.  depgan_dp_update sums the buckets over the ranks, applies Keras' Adam
+ * (step count t >= 1; lr_t = lr * sqrt(1 - beta_2^t) / (1 - beta_1^t), eps added to sqrt(v)) to params / m / v and calls
+ * depgan_net_prepare -- one call per update.  extra_f64 (optional, <= 32 doubles on the device): loss partial sums that
+ * are summed over the ranks in the same pass, in place.  Transport = whatever is attached to the handle:
+ *   depgan_peer_attach      one node: a fused reduce + Adam kernel that reads every rank's mailbox over NVLink (CUDA IPC);
+ *                           the summation order is the rank order on every replica, so the replicas stay bit-identical
+ *   depgan_allreduce_attach any topology: ncclAllReduce on `stream` (NCCL is resolved at run time with dlsym from the
+ *                           library the process already uses, or from the path given to depgan_nccl_load), then Adam
+ *   neither                 single GPU: the local bucket
+ * Mailboxes: depgan_peer_create(n_floats = depgan_manifest_floats, world <= 16, rank) allocates this rank's mailbox on
+ * the current device; depgan_peer_handle copies its 64-byte CUDA IPC handle out; the caller exchanges the handles by any
+ * means (MPI, files, torch.distributed) and passes all `world` of them, in rank order, to depgan_peer_connect. */
+typedef struct depgan_peer depgan_peer;
+int depgan_nccl_load(const char* path_or_null);
+int depgan_nccl_unique_id(void* id128);
+int depgan_nccl_init(void** comm_out, int world, int rank, const void* id128);
+int depgan_nccl_destroy(void* comm);
+int depgan_allreduce_attach(depgan_net* h, void* nccl_comm, int world);
+depgan_peer* depgan_peer_create(long long n_floats, int world, int rank);
+int depgan_peer_handle(depgan_peer* p, void* out64);
+int depgan_peer_connect(depgan_peer* p, const void* handles_world_x_64);
+void depgan_peer_destroy(depgan_peer* p);
+int depgan_peer_attach(depgan_net* h, depgan_peer* p);
+int depgan_dp_update(depgan_net* h, float* m_dev, float* v_dev, int t, float lr, float beta_1, float beta_2, float eps,
+                     double* extra_f64, int n_extra, void* stream);
+/* The sum of the buckets over the ranks left in the bucket (no optimizer step); extra_f64 as above. */
+int depgan_dp_allreduce_grads(depgan_net* h, double* extra_f64, int n_extra, void* stream);
+/* In-place sum over the ranks of n <= 32 doubles on the device: the loss partial sums of the forward-only evaluations
+ * (TG:868-877 -- every rank must see the same ten candidate losses to pick the same noise). */
+int depgan_dp_allreduce_f64(depgan_net* h, double* buf_dev, int n, void* stream);
+
 /* ---- kernel-level entry points (parity tests and micro-benchmarks of the convolution kernels) ----
  * One fused 'same' stride-1 convolution (Keras Conv2D TG:285-304 / Conv2DTranspose k2s2 TG:307-312 when
  * deconv=1) on caller-owned device buffers.  Epilogue order: v = acc*scale+shift; out_pre=v;

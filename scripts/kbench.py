@@ -158,16 +158,27 @@ def main():
             for _ in range(warm):
                 run()
             torch.cuda.synchronize()
+            # spin the clocks up: an idle B200 sits at 120 MHz and needs tens of milliseconds of load to reach its
+            # boost clock -- ten 0.1 ms launches from idle measure the ramp, not the kernel (KBENCH_SPIN_MS=0: off)
+            spin_ms = float(os.environ.get("KBENCH_SPIN_MS", "0" if reps <= 1 else "60"))
+            if spin_ms > 0:
+                import time
+                t_end = time.perf_counter() + spin_ms * 1e-3
+                while time.perf_counter() < t_end:
+                    for _ in range(20):
+                        run()
+                    torch.cuda.synchronize()
         except RuntimeError as e:
             print("%-34s unsupported by this build (%s)" % (name, str(e)[:60]))
             continue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(reps):
+        nrun = reps if reps <= 1 else max(reps, 50)
+        for _ in range(nrun):
             run()
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
+        ms = e0.elapsed_time(e1) / nrun
         print("%-34s %9.4f %9.1f %9.1f" % (name, ms, flops / ms / 1e9, nbytes / ms / 1e6), flush=True)
         del keep, run
         torch.cuda.empty_cache()

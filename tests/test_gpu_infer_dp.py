@@ -172,3 +172,70 @@ def test_uresnet_fit_data_parallel_sync_bn_matches_single_gpu():
     wts = g.get_weights()  # after the Adam step, moving statistics included
     for k in wts:
         assert np.allclose(out["weights"][k], wts[k], rtol=2e-4, atol=2e-5), k
+
+
+# ---- the native transports of the gradient sum (dp.cu): fused peer-memory reduce + Adam, NCCL behind the C ABI ----
+def _collective_worker(rank, world, port, kind, out):
+    import torch.distributed as dist
+    from depgan_b200 import Dis_C2D_FCN1, Gen_UNet2D
+    from depgan_b200.infer import shard_range
+    from depgan_b200.trainer import DepGanTrainer
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    H, N = 32, 4
+    dev = "cuda:%d" % rank
+    PG, PD1, PD2 = util.gen_weights(1, 1, seed=1), util.critic_weights(H, H, seed=2), util.critic_weights(H, H, seed=3)
+    x1, y2, _ = synth.make_im_pair(N, H, H, thr=THR, seed=4)
+    z, ep = synth.make_noise(N, seed=5), synth.make_eps(N, seed=6)
+    lo, hi = shard_range(N, rank, world)
+    n = hi - lo
+    G = Gen_UNet2D((H, H, 1), precision="fp32", max_batch=n, device=dev, training=True)
+    D1 = Dis_C2D_FCN1((H, H, 1), precision="fp32", max_batch=3 * n, device=dev, training=True)
+    D2 = Dis_C2D_FCN1((H, H, 1), precision="fp32", max_batch=3 * n, device=dev, training=True)
+    G.set_weights(PG), D1.set_weights(PD1), D2.set_weights(PD2)
+    tr = DepGanTrainer(G, D1, D2, THR, collective=kind)
+    r = {"d": [], "g": []}
+    for it in range(3):  # three updates of each network: the mailboxes' double buffering wraps
+        r["d"].append([float(v) for v in tr.netD_y2_train([y2[lo:hi], x1[lo:hi], z[lo:hi], ep[lo:hi]])])
+        r["d"].append([float(v) for v in tr.netD_dem_train([y2[lo:hi], x1[lo:hi], z[lo:hi], ep[lo:hi]])])
+        r["g"].append([float(v) for v in tr.netG_no_update([x1[lo:hi], y2[lo:hi], z[lo:hi]])])
+        r["g"].append([float(v) for v in tr.netG_train([x1[lo:hi], y2[lo:hi], z[lo:hi]])])
+    # gradient inspection without an update (the all-reduce that leaves the sum in the bucket)
+    r["d_noupd"] = [float(v) for v in tr.netD_y2_train([y2[lo:hi], x1[lo:hi], z[lo:hi], ep[lo:hi]], update=False)]
+    r["d_grads"] = D1.get_grads()
+    r["w"] = {"G": G.get_weights(), "D1": D1.get_weights(), "D2": D2.get_weights()}
+    out[(kind, rank)] = r
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_native_collectives_reproduce_the_torch_distributed_path():
+    """Three full update rounds (both critics, ten... one evaluation, the generator) on two GPUs with each transport:
+    'peer' (fused reduce + Adam over CUDA-IPC mailboxes) and 'nccl' (ncclAllReduce issued by the library) give the losses
+    and the weights of the torch.distributed path to float rounding; with 'peer' the two replicas are bit-identical
+    (same summation order on every rank)."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    for kind in ("torch", "peer", "nccl"):
+        mp.spawn(_collective_worker, args=(2, _free_port(), kind, out), nprocs=2, join=True)
+    ref = out[("torch", 0)]
+    for kind in ("peer", "nccl"):
+        got = out[(kind, 0)]
+        assert np.allclose(got["d"], ref["d"], rtol=2e-4, atol=1e-5), (kind, got["d"], ref["d"])
+        assert np.allclose(got["g"], ref["g"], rtol=2e-4, atol=1e-5), (kind, got["g"], ref["g"])
+        assert np.allclose(got["d_noupd"], ref["d_noupd"], rtol=2e-4, atol=1e-5)
+        for k, w in ref["d_grads"].items():
+            if np.linalg.norm(w) > 1e-9:
+                assert np.linalg.norm(got["d_grads"][k] - w) / np.linalg.norm(w) < 1e-4, (kind, k)
+        for net in ("G", "D1", "D2"):
+            for k, w in ref["w"][net].items():
+                # Adam with beta_1 = 0 moves every weight by ~lr per step whatever the gradient's size, so weights whose
+                # gradient is rounding noise may differ by 2 * lr * steps; everything else agrees far tighter
+                assert np.abs(got["w"][net][k] - w).max() <= 6.5e-4, (kind, net, k)
+    for net in ("G", "D1", "D2"):
+        for k, w in out[("peer", 0)]["w"][net].items():
+            assert np.array_equal(out[("peer", 1)]["w"][net][k], w), (net, k)
