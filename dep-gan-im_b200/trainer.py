@@ -68,8 +68,9 @@ def epoch_schedule(batches, gen_iterations, Diters=5):
 
 
 class ScalarLog:
-    """Minimal stand-in for the reference's TensorBoard ``Logger`` (TG:167-248): ``log_scalar(tag, value, step)`` keeps
-    the series in memory (``.series[tag] = [(step, value), ...]``) and, if a path is given, appends CSV lines."""
+    """In-memory / CSV variant of the reference's TensorBoard ``Logger`` (TG:167-248): ``log_scalar(tag, value, step)``
+    keeps the series in memory (``.series[tag] = [(step, value), ...]``) and, if a path is given, appends CSV lines.
+    ``tblog.TensorBoardLogger`` has the same interface and writes real event files (scalars, images, histograms)."""
 
     def __init__(self, csv_path=None):
         self.series = {}
@@ -306,7 +307,7 @@ class DepGanTrainer:
 
     # ---- the reference's training loop (TG:780-894) ------------------------------------------------------
     def fit(self, x1_train, y2_train, niter=1, batchSize=16, Diters=5, noiseSize=32, k_noise=10, val=None,
-            fixed_noise=None, logger=None, save_path=None, save_every=1, seed=None, shuffle=True, verbose=False):
+            fixed_noise=None, logger=None, log_dir=None, save_path=None, save_every=1, seed=None, shuffle=True, verbose=False):
         """``niter`` epochs of the DEP-GAN loop on host arrays ``x1_train (M,H,W,nicg)`` / ``y2_train (M,H,W,1)``:
         per epoch a shuffle (TG:785-788), then :func:`epoch_schedule`; noise ~ N(0,1), ep ~ U(0,1) per critic update
         (TG:807-808, 822-823), ``k_noise`` candidate noises for the generator and the argmin rule (TG:869-878); the
@@ -315,7 +316,9 @@ class DepGanTrainer:
         ``save_every`` generator iterations (the reference saves after each, TG:892).  The reference draws from the
         global NumPy RNG; ``seed`` makes the run reproducible.  Returns the logger."""
         rng = np.random.default_rng(seed)
-        logger = logger if logger is not None else ScalarLog()
+        if logger is None:  # TG:775: Logger('./logs/...') -> TensorBoard event files when a directory is given
+            from .tblog import TensorBoardLogger
+            logger = TensorBoardLogger(log_dir) if log_dir else ScalarLog()
         x1_train = np.ascontiguousarray(x1_train, np.float32)
         y2_train = np.ascontiguousarray(y2_train, np.float32)
         crit_it = crit_dem_it = 0
@@ -361,6 +364,11 @@ class DepGanTrainer:
                     logger.log_scalar("val_D_fake_loss", v_fake, g_it)
                     logger.log_scalar("val_D_real_loss", v_real, g_it)
                     logger.log_scalar("val_D_real_generated_loss", v_gen, g_it)
+                    if g_it % 500 == 0:                                        # TG:857-865: image summaries
+                        attributed = self.G.predict([x1_v, fz])
+                        fake = np.ascontiguousarray(x1_v[..., :1], np.float32) + attributed
+                        logger.log_images("attributed_img_step%d" % g_it, attributed[:50], g_it, "")
+                        logger.log_images("fake_img_step%d" % g_it, fake[:50], g_it, "")
                 r1, r2 = x1_e[b * batchSize:(b + 1) * batchSize], y2_e[b * batchSize:(b + 1) * batchSize]
                 noises = rng.standard_normal((k_noise, batchSize, noiseSize, 1)).astype("float32")
                 _, _, out = self.gen_iteration([], [], r1, r2, noises)        # TG:867-878
