@@ -270,7 +270,8 @@ def run_gpu(args, w, rank, world, local_rank):
         if arr_n[k] > 0 and arr_ms[k] > 0:
             achieved = arr_fl[k] / (arr_ms[k] * 1e-3) / 1e12
             conv_share = arr_ms[k] / max(1e-9, sum(arr_ms))
-            roof = {"kernel": "conv_tc_kernel<3> (tcgen05 implicit-GEMM 3x3 conv, %d launches/step)" % (arr_n[k] // psteps),
+            roof = {"kernel": "tcgen05 implicit-GEMM 3x3 convolutions: conv_tc_kernel<3> (tile) / conv_row_kernel / "
+                              "conv_rowg_kernel (row-streaming), %d launches/step" % (arr_n[k] // psteps),
                     "bound": "tensor", "achieved": achieved, "peak": pk["tf_sust"], "unit": "TFLOP/s",
                     "frac": achieved / pk["tf_sust"], "peak_source": pk["src"] + " (sustained bf16)",
                     "traffic": None, "avg_launch_ms": arr_ms[k] / arr_n[k],
@@ -309,6 +310,8 @@ def run_gpu(args, w, rank, world, local_rank):
     torch.cuda.empty_cache()
     if not args.no_extra:
         extra["configs[0]"] = measure_config0(args, rank, world, dev)
+        torch.cuda.empty_cache()
+        extra["precision_variants"] = measure_precision_variants(args, rank, dev)
         torch.cuda.empty_cache()
         extra["configs[4]"] = measure_cohort(args, rank, world, dev)
         torch.cuda.empty_cache()
@@ -358,6 +361,7 @@ def run_gpu(args, w, rank, world, local_rank):
                     "configs[2]": "the 'train' record of this line (IM, 32 slices per GPU, weak scaling)",
                     "configs[3]": train_pf, "configs[4]": extra.get("configs[4]")},
         "predict_numpy": extra.get("predict_numpy"),
+        "precision_variants": extra.get("precision_variants"),
     }
     print(json.dumps(line))
     if world > 1:
@@ -423,6 +427,46 @@ def measure_config0(args, rank, world, dev):
                     "what": "Gen_UNet2D.predict([x, z], batch_size=16) on pageable NumPy arrays, %d slices per call, "
                             "host wall clock (max over ranks)" % xs.shape[0],
                     "h2d_bytes_per_step": int(x.nbytes + z.nbytes), "d2h_bytes_per_step": int(y.nbytes // nb)}}
+
+
+def measure_precision_variants(args, rank, dev):
+    """The other arithmetic variants of the same forward (configs[0] shape, batch 16, device-resident, rank 0 only):
+    'fp32' = the FP32-storage / FP32-accumulate CUDA-core path (the <= 1e-4 variant of BASELINE.json's north_star) and
+    'bf16' = the tcgen05 path with bfloat16 storage (what training runs), next to the IEEE-half default."""
+    import torch
+    from depgan_b200 import Gen_UNet2D
+    if rank != 0:
+        return None
+    w = WORKLOADS["depgan_infer"]
+    B = w["batch"]
+    x, z = make_inputs(w, B, seed=300)
+    xd, zd = torch.from_numpy(x).to(dev), torch.from_numpy(z).to(dev)
+    out = torch.empty((B, 256, 256, 1), dtype=torch.float32, device=dev)
+    res, ref = {}, None
+    for prec, steps in (("fp32", 3), ("bf16", 20), ("f16", 20)):
+        g = Gen_UNet2D((256, 256, 1), (32, 1), 32, 1, precision=prec, max_batch=B, device=str(dev))
+        g.set_weights(make_weights(w, g))
+        for _ in range(2):
+            g.forward_device(xd, zd, out)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            g.forward_device(xd, zd, out)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / steps
+        y = out.clone()
+        if ref is None:
+            ref = y  # the fp32 path (<= 1e-4 of the fp64 oracle, tests/test_gpu_nets.py) is the yardstick here
+        res[prec] = {"slices_per_s": B / (ms * 1e-3), "ms_per_step": ms,
+                     "tflops_effective": B / (ms * 1e-3) * G_FLOP[(1, 1)] / 1e12,
+                     "dem_max_abs_vs_fp32_path": float((y - ref).abs().max())}
+        del g
+        torch.cuda.empty_cache()
+    res["what"] = ("DEP-GAN generator forward, batch 16, device-resident; fp32 = CUDA-core FP32 storage + accumulate, "
+                   "bf16 / f16 = tcgen05 (fp32 accumulate in TMEM) with bfloat16 / IEEE-half activations and weights")
+    return res
 
 
 def measure_predict_numpy(args, w, g, rank, world, dev, B):
