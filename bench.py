@@ -178,6 +178,9 @@ def run_gpu(args, w, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # every rank's pinned staging buffers on the memory of its own GPU's NUMA node (DEPGAN_NO_NUMA=1: off, for A/B)
+    from depgan_b200.infer import bind_to_gpu_numa_node
+    numa = None if os.environ.get("DEPGAN_NO_NUMA") else bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch or w["batch"]
@@ -350,7 +353,8 @@ def run_gpu(args, w, rank, world, local_rank):
         "config": {"workload": w["desc"], "batch_per_gpu": B, "precision": args.precision,
                    "weights": "synthetic (seeded), round-tripped through the Keras-h5 layout",
                    "l2": "per-step activation working set (~%.1f GB) >> 126 MB L2; no explicit flush" % (B * 0.1137),
-                   "parallelism": "slices sharded across %d GPU(s), no collective" % world},
+                   "parallelism": "slices sharded across %d GPU(s), no collective" % world,
+                   "numa_binding_rank0": numa},
         "tflops_effective": value * flop / 1e12,
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": slices / (ms_e2e * 1e-3), "unit": "slices/s",
