@@ -638,6 +638,8 @@ def measure_train(args, rank, world, dev, steps, warmup, workload="depgan_train"
     D1 = Dis_C2D_FCN1((256, 256, 1), precision=args.train_precision, max_batch=3 * B, device=str(dev), training=True, seed=1)
     D2 = Dis_C2D_FCN1((256, 256, 1), precision=args.train_precision, max_batch=3 * B, device=str(dev), training=True, seed=2)
     tr = DepGanTrainer(G, D1, D2, thr)
+    if not os.environ.get("DEPGAN_NO_BATCHED_EVAL"):  # the ten noise evaluations of an iteration as one 10 x B pass
+        tr.enable_batched_eval(10)
 
     def batch(seed):
         x1, y2, _ = synth.make_im_pair(B, 256, 256, nicg=nicg, thr=thr, seed=seed)

@@ -54,6 +54,8 @@ SIGNATURES = {
     "depgan_gen_eval": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P]),
     "depgan_gen_grads": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P]),
     "depgan_gen_loss_finalize": (_I, [_P, _P, _P]),
+    "depgan_gen_eval_multi": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _I, _I, _I, _P]),
+    "depgan_gen_loss_finalize_multi": (_I, [_P, _P, _I, _I, _LL, _P]),
     "depgan_uresnet_grads": (_I, [_P, _P, _P, _P, _P, _P, _I, _P]),
     "depgan_cce_loss": (_I, [_P, _P, _P, _P, _LL, _I, _F, _P]),
     "depgan_adam_step": (_I, [_P, _P, _P, _P, _LL, _I, _F, _F, _F, _F, _F, _P]),

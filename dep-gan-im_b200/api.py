@@ -64,7 +64,7 @@ def manifest(model, cfg):
 class _Net:
     """One generator or critic: flat parameters + workspace on one GPU and the native handle."""
 
-    def __init__(self, model, cfg, device, seed):
+    def __init__(self, model, cfg, device, seed, share_params_with=None):
         torch = _torch()
         self._torch = torch
         self.model, self.cfg = model, cfg
@@ -72,7 +72,12 @@ class _Net:
         self.manifest, self.n_floats = manifest(model, cfg)
         L = _lib.lib()
         with torch.cuda.device(self.device):
-            self.params = torch.zeros(self.n_floats, dtype=torch.float32, device=self.device)
+            if share_params_with is not None:  # a second view (own workspace / batch size) of another net's weights
+                if share_params_with.n_floats != self.n_floats or share_params_with.device != self.device:
+                    raise ValueError("share_params_with: the networks differ")
+                self.params = share_params_with.params
+            else:
+                self.params = torch.zeros(self.n_floats, dtype=torch.float32, device=self.device)
             self.grads = torch.zeros(self.n_floats, dtype=torch.float32, device=self.device) if cfg.training else None
             ws = int(L.depgan_workspace_bytes(model, C.byref(cfg)))
             if ws < 0:
@@ -85,6 +90,9 @@ class _Net:
                 raise RuntimeError("net_create: " + _lib.last_error())
         self.adam_m = self.adam_v = None
         self.iterations = 0
+        if share_params_with is not None:
+            self.prepare()  # derived tensors of this handle; call prepare() again after the owner's weights change
+            return
         man3 = [(n.split("/")[0], n.split("/")[1], s) for n, s, _, _ in self.manifest]
         self.set_weights(synth.init_weights(man3, seed=seed))
 
@@ -282,7 +290,7 @@ class Gen_UNet2D(_Net):
     """
 
     def __init__(self, input_shape=(256, 256, 1), noiseZ_shape=(32, 1), first_fm=32, nc_out=1, *, precision="bf16",
-                 max_batch=32, device="cuda:0", training=False, seed=0):
+                 max_batch=32, device="cuda:0", training=False, seed=0, share_params_with=None):
         if first_fm != 32:
             raise ValueError("first_fm must be 32 (first_fm_G, TG:36)")
         if tuple(noiseZ_shape)[1:] != (1,):
@@ -292,7 +300,8 @@ class Gen_UNet2D(_Net):
         cfg = _lib.Cfg(int(h), int(w), int(nicg), int(nc_out), int(noiseZ_shape[0]), int(max_batch), _prec(precision),
                        tmode)
         self.input_shape, self.noiseZ_shape, self.nc_out = tuple(input_shape), tuple(noiseZ_shape), int(nc_out)
-        super().__init__(_lib.MODEL_GEN, cfg, device, seed)
+        self.precision = precision
+        super().__init__(_lib.MODEL_GEN, cfg, device, seed, share_params_with)
 
     def _keras_description(self):
         from . import keras_config
@@ -622,13 +631,14 @@ class Dis_C2D_FCN1(_Net):
     """Drop-in for ``Dis_C2D_FCN1(input_shape)`` (TG:316-345): the WGAN-GP critic, (N,H,W,1) -> (N,1)."""
 
     def __init__(self, input_shape=(256, 256, 1), *, precision="bf16", max_batch=32, device="cuda:0", training=False,
-                 seed=1):
+                 seed=1, share_params_with=None):
         h, w, c = input_shape
         if c != 1:
             raise ValueError("the critic takes one channel (TG:513,516)")
         cfg = _lib.Cfg(int(h), int(w), 1, 1, 32, int(max_batch), _prec(precision), int(bool(training)))
         self.input_shape = tuple(input_shape)
-        super().__init__(_lib.MODEL_CRITIC, cfg, device, seed)
+        self.precision = precision
+        super().__init__(_lib.MODEL_CRITIC, cfg, device, seed, share_params_with)
 
     def _keras_description(self):
         from . import keras_config

@@ -27,7 +27,8 @@
 namespace {
 
 constexpr int DP_MAX_WORLD = 16;
-constexpr int DP_EXTRA = 32;  // doubles of side data (loss partial sums) that ride along with the bucket
+constexpr int DP_EXTRA = 32;   // doubles of side data (loss partial sums) that ride along with the bucket
+constexpr int DP_SMALL = 128;  // doubles of one small all-reduce (the sums of ten candidate evaluations: 80)
 
 // ---------------------------------------------------------------------------------------------------------
 // NCCL through dlsym (no link-time dependency: the library stays loadable without NCCL)
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(PeerView pv, unsign
 }
 
 // all-reduce of a few doubles (loss partial sums of a forward-only evaluation): one CTA, own small mailbox + own flags
-__global__ void __launch_bounds__(64) dp_small_allreduce_kernel(PeerView pv, unsigned epoch, double* buf, int n) {
+__global__ void __launch_bounds__(DP_SMALL) dp_small_allreduce_kernel(PeerView pv, unsigned epoch, double* buf, int n) {
   double* mine = reinterpret_cast<double*>(pv.box[pv.rank]);
   if ((int)threadIdx.x < n) mine[threadIdx.x] = buf[threadIdx.x];
   __threadfence_system();
@@ -267,7 +268,7 @@ depgan_peer* depgan_peer_create(long long n_floats, int world, int rank) {
   p->world = world; p->rank = rank; p->n = n_floats;
   cudaGetDevice(&p->dev);
   p->box_bytes = ((((size_t)n_floats + 3) & ~(size_t)3) * sizeof(float) + DP_EXTRA * sizeof(double) + 255) & ~(size_t)255;
-  p->small_bytes = 256;
+  p->small_bytes = DP_SMALL * sizeof(double);
   p->total = p->off_counter() + 256 + DP_EXTRA * sizeof(double);
   if (cudaMalloc(&p->base, p->total) != cudaSuccess || cudaMemset(p->base, 0, p->total) != cudaSuccess ||
       cudaIpcGetMemHandle(&p->handle, p->base) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
@@ -382,14 +383,14 @@ int depgan_dp_allreduce_grads(depgan_net* h, double* extra_f64, int n_extra, voi
   return 0;
 }
 
-// In-place sum over the ranks of n <= 32 doubles on the device (loss partial sums of depgan_gen_eval).
+// In-place sum over the ranks of n <= 128 doubles on the device (loss partial sums of depgan_gen_eval).
 int depgan_dp_allreduce_f64(depgan_net* h, double* buf_dev, int n, void* stream) {
-  DG_REQUIRE(h && buf_dev && n >= 1 && n <= DP_EXTRA, "dp_allreduce_f64: 1..32 doubles");
+  DG_REQUIRE(h && buf_dev && n >= 1 && n <= DP_SMALL, "dp_allreduce_f64: 1..128 doubles");
   cudaStream_t st = (cudaStream_t)stream;
   if (h->peer && h->peer->world > 1) {
     depgan_peer* p = h->peer;
     const unsigned ep = ++p->epoch_small;
-    dp_small_allreduce_kernel<<<1, 64, 0, st>>>(p->view(true, ep), ep, buf_dev, n);
+    dp_small_allreduce_kernel<<<1, DP_SMALL, 0, st>>>(p->view(true, ep), ep, buf_dev, n);
     DG_LAUNCH_CHECK();
   } else if (h->nccl_comm && h->dp_world > 1) {
     DG_TRY(nccl_check(g_nccl.allreduce(buf_dev, buf_dev, (size_t)n, NCCL_FLOAT64, NCCL_SUM, h->nccl_comm, st),

@@ -81,7 +81,8 @@ int k_gp(const float* g, float* u, float* gp_out, int n, long long hw, float del
 int k_segment_sum(const float* src, int seg, int nseg, float* out, float alpha, cudaStream_t st);
 int k_gen_loss_sums(const float* dem, const float* x1, int nicg, const float* real2, float thr, float* fake2,
                     float* l1g, float l1coef, double* sums, long long n, cudaStream_t st);
-int k_gen_loss_finalize(float* out6, const double* sums, cudaStream_t st);
+int k_loss_consts(double* sums, double gn, double hw, int k, cudaStream_t st);  // sums[j][6] = gn, sums[j][7] = hw
+int k_gen_loss_finalize(float* out6, const double* sums, cudaStream_t st, int k = 1);  // k candidates: out6[k][6], sums[k][8]
 int k_gen_head_bwd(const float* gy2, const float* gdem, const float* l1g, const float* dem, const void* o,
                    const float* w, void* d_o, float* d_w, float* d_b, long long npix, int C, int dt, cudaStream_t st);
 int k_film_bwd(const void* d_r, const void* y, const float* fg, const float* fb, int fstride, void* d_y, float* dgam,
@@ -95,7 +96,8 @@ int k_film_mlp_bwd(const FilmMlpArgs& a, const float* d_out, float* const* dW_he
                    float* dk1raw, float* sum_d1, float* dk0raw, float* sum_d0, cudaStream_t st);
 int k_fill_go(float* go, int n, float v_real, float v_fake, float v_mixed, int rows, cudaStream_t st);
 int k_critic_loss_finalize(float* out4, float delta, cudaStream_t st);
-int k_scores_to_sums(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw, cudaStream_t st);
+int k_scores_to_sums(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw, cudaStream_t st,
+                     int k = 1);
 int k_pack_deconv_dgrad(const float* src, const float* scale, float* dst_f32, bf16* dst_bf16, int Cin, int Cout,
                         cudaStream_t st);
 

@@ -464,7 +464,9 @@ __global__ void __launch_bounds__(256) gen_loss_sums_kernel(const float* dem, co
 
 __global__ void gen_loss_finalize_kernel(float* out6, const double* s) {
   // s: [0] sum D_y2(fake2), [1] sum D_dem(dem), [2] sum |dem-realdem|, [3] sum wmh_real, [4] sum wmh_fake,
-  //    [5] sum wmh_real*wmh_fake, [6] global batch, [7] pixels per slice
+  //    [5] sum wmh_real*wmh_fake, [6] global batch, [7] pixels per slice.  One block per candidate (batched evaluation).
+  out6 += 6 * blockIdx.x;
+  s += 8 * blockIdx.x;
   const double n = s[6], hw = s[7];
   const double lf = s[0] / n, lfd = s[1] / n;
   const double m1 = 100.0 * s[2] / (n * hw);
@@ -963,8 +965,8 @@ int k_gen_loss_sums(const float* dem, const float* x1, int nicg, const float* re
   return 0;
 }
 
-int k_gen_loss_finalize(float* out6, const double* sums, cudaStream_t st) {
-  gen_loss_finalize_kernel<<<1, 1, 0, st>>>(out6, sums);
+int k_gen_loss_finalize(float* out6, const double* sums, cudaStream_t st, int k) {
+  gen_loss_finalize_kernel<<<k, 1, 0, st>>>(out6, sums);
   DG_LAUNCH_CHECK();
   return 0;
 }
@@ -1106,6 +1108,9 @@ int k_critic_loss_finalize(float* out4, float delta, cudaStream_t st) {
 
 namespace {
 __global__ void scores_to_sums_kernel(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw) {
+  sy2 += (size_t)n * blockIdx.x;  // one block per candidate (batched evaluation): n scores and 8 sums each
+  sdem += (size_t)n * blockIdx.x;
+  sums += 8 * blockIdx.x;
   double a = 0.0, b = 0.0;
   for (int i = 0; i < n; ++i) { a += (double)sy2[i]; b += (double)sdem[i]; }
   sums[0] = a; sums[1] = b; sums[6] = gn; sums[7] = hw;
@@ -1125,8 +1130,18 @@ __global__ void pack_deconv_dgrad_kernel(const float* src, const float* scale, f
 }
 }  // namespace
 
-int k_scores_to_sums(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw, cudaStream_t st) {
-  scores_to_sums_kernel<<<1, 1, 0, st>>>(sy2, sdem, n, sums, gn, hw);
+__global__ void loss_consts_kernel(double* sums, double gn, double hw) {
+  sums[8 * blockIdx.x + 6] = gn;
+  sums[8 * blockIdx.x + 7] = hw;
+}
+int k_loss_consts(double* sums, double gn, double hw, int k, cudaStream_t st) {
+  loss_consts_kernel<<<k, 1, 0, st>>>(sums, gn, hw);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+int k_scores_to_sums(const float* sy2, const float* sdem, int n, double* sums, double gn, double hw, cudaStream_t st,
+                     int k) {
+  scores_to_sums_kernel<<<k, 1, 0, st>>>(sy2, sdem, n, sums, gn, hw);
   DG_LAUNCH_CHECK();
   return 0;
 }

@@ -312,6 +312,52 @@ int depgan_gen_loss_finalize(float* out6_dev, const double* sums_dev, void* stre
   return k_gen_loss_finalize(out6_dev, sums_dev, (cudaStream_t)stream);
 }
 
+// netG_no_update for k noise candidates of ONE batch in a single pass (TG:868-874: the ten evaluations of a generator
+// iteration see the same x / real_2tp and differ only in the noise): the batch is replicated k times, the generator and
+// the two critics run once on k * n rows, the loss sums are kept per candidate.  Any prepared handles with
+// max_batch >= k * n serve (inference handles that share the training networks' parameter buffers: api.py), so the
+// training handles' backward buffers are not multiplied by k.  Slices never mix, so every candidate's losses equal those
+// of the one-by-one evaluation.  scratch: k * n * H * W * (nicg + 1) floats.
+int depgan_gen_eval_multi(depgan_net* g, depgan_net* dy2, depgan_net* ddem, const float* x1_dev, const float* real2_dev,
+                          const float* z_all_dev, float thr, float* out6_all_dev, double* sums_all_dev, float* scratch_dev,
+                          int n, int k, int global_n, void* stream) {
+  DG_REQUIRE(g && dy2 && ddem && g->model == DEPGAN_MODEL_GEN && dy2->model == DEPGAN_MODEL_CRITIC &&
+                 ddem->model == DEPGAN_MODEL_CRITIC, "gen_eval_multi: bad handles");
+  DG_REQUIRE(g->prepared && dy2->prepared && ddem->prepared, "gen_eval_multi: call depgan_net_prepare first");
+  DG_REQUIRE(g->cfg.nc_out == 1 && g->cfg.H == dy2->cfg.H && g->cfg.W == dy2->cfg.W && g->cfg.H == ddem->cfg.H &&
+                 g->cfg.W == ddem->cfg.W, "gen_eval_multi: shape mismatch");
+  DG_REQUIRE(n >= 1 && k >= 1 && (long long)n * k <= g->cfg.max_batch && (long long)n * k <= dy2->cfg.max_batch &&
+                 (long long)n * k <= ddem->cfg.max_batch, "gen_eval_multi: k * n exceeds a handle's max_batch");
+  DG_REQUIRE(x1_dev && real2_dev && z_all_dev && out6_all_dev && sums_all_dev && scratch_dev, "gen_eval_multi: null pointer");
+  if (global_n <= 0) global_n = n;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long hw = (long long)g->cfg.H * g->cfg.W;
+  const int nicg = g->cfg.nicg;
+  float* x_rep = scratch_dev;
+  float* fake2 = scratch_dev + (size_t)k * n * hw * nicg;
+  for (int j = 0; j < k; ++j)
+    DG_CHECK_CUDA(cudaMemcpyAsync(x_rep + (size_t)j * n * hw * nicg, x1_dev, sizeof(float) * (size_t)n * hw * nicg,
+                                  cudaMemcpyDeviceToDevice, st));
+  DG_TRY(gen_forward_impl(g, x_rep, z_all_dev, g->dem_f32, n * k, false, st));
+  DG_CHECK_CUDA(cudaMemsetAsync(sums_all_dev, 0, sizeof(double) * 8 * k, st));
+  for (int j = 0; j < k; ++j)
+    DG_TRY(k_gen_loss_sums(g->dem_f32 + (size_t)j * n * hw, x1_dev, nicg, real2_dev, thr, fake2 + (size_t)j * n * hw, nullptr,
+                           0.f, sums_all_dev + 8 * j, (long long)n * hw, st));
+  DG_TRY(critic_forward_impl(dy2, fake2, dy2->c_out, n * k, st));        // D_y2(base + DEM)   TG:574-575
+  DG_TRY(critic_forward_impl(ddem, g->dem_f32, ddem->c_out, n * k, st));  // D_dem(DEM)
+  DG_TRY(k_scores_to_sums(dy2->c_out, ddem->c_out, n, sums_all_dev, (double)global_n, (double)hw, st, k));
+  return k_gen_loss_finalize(out6_all_dev, sums_all_dev, st, k);
+}
+
+// Finalises k candidates after their sums [0..5] were summed over the ranks (the constants [6], [7] are rewritten).
+int depgan_gen_loss_finalize_multi(float* out6_all_dev, double* sums_all_dev, int k, int global_n, long long hw,
+                                   void* stream) {
+  DG_REQUIRE(out6_all_dev && sums_all_dev && k >= 1 && global_n >= 1 && hw >= 1, "gen_loss_finalize_multi: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_TRY(k_loss_consts(sums_all_dev, (double)global_n, (double)hw, k, st));
+  return k_gen_loss_finalize(out6_all_dev, sums_all_dev, st, k);
+}
+
 int depgan_gen_grads(depgan_net* g, depgan_net* dy2, depgan_net* ddem, const float* x1_dev, const float* real2_dev,
                      const float* z_dev, float thr, float* out6_dev, double* sums_dev, int n, int global_n,
                      void* stream) {

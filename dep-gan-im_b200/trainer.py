@@ -110,6 +110,7 @@ class DepGanTrainer:
         if distributed:
             self.collective = collective or os.environ.get("DEPGAN_COLLECTIVE", "peer")
             self._attach_collective()
+        self.batched_eval = False
         self.ex64 = torch.zeros(8, dtype=torch.float64, device=self.device)
         self.out4 = torch.zeros(4, dtype=torch.float32, device=self.device)
         self.out6 = torch.zeros(6, dtype=torch.float32, device=self.device)
@@ -245,6 +246,50 @@ class DepGanTrainer:
                 self.G.adam_step(self.lrG, self.b1, self.b2)
         return self.out6
 
+    # ---- the ten candidate evaluations of a generator iteration in one pass (TG:868-874) ------------------------
+    def enable_batched_eval(self, k_noise=10):
+        """Creates inference handles for k_noise * batch rows on the training networks' parameter buffers (own
+        workspaces; the training handles' backward buffers are not multiplied) and switches gen_iteration_device to the
+        one-pass evaluation.  The candidates' losses are those of the one-by-one evaluation (slices never mix)."""
+        from .api import Dis_C2D_FCN1, Gen_UNet2D
+        G = self.G
+        rows = int(k_noise) * G.cfg.max_batch
+        H, W = G.cfg.H, G.cfg.W
+        self._Ge = Gen_UNet2D(G.input_shape, G.noiseZ_shape, 32, 1, precision=G.precision, max_batch=rows,
+                              device=str(self.device), share_params_with=G)
+        self._De = [Dis_C2D_FCN1((H, W, 1), precision=D.precision, max_batch=rows, device=str(self.device),
+                                 share_params_with=D) for D in (self.Dy2, self.Ddem)]
+        torch = self.torch
+        self._ek = int(k_noise)
+        self._escratch = torch.empty(rows * H * W * (G.cfg.nicg + 1), dtype=torch.float32, device=self.device)
+        self._eout6 = torch.zeros((self._ek, 6), dtype=torch.float32, device=self.device)
+        self._esums = torch.zeros((self._ek, 8), dtype=torch.float64, device=self.device)
+        self.batched_eval = True
+
+    def gen_eval_multi_device(self, x1, real2, noises):
+        """noises (k, n, L, 1) CUDA tensor -> (k, 6) float32 CUDA tensor of [loss, lf, lfd, M1, M3, M4] per candidate."""
+        torch = self.torch
+        k, n = int(noises.shape[0]), int(x1.shape[0])
+        if k > self._ek or k * n > self._Ge.cfg.max_batch:
+            raise ValueError("enable_batched_eval was sized for fewer candidates / a smaller batch")
+        L = _lib.lib()
+        with torch.cuda.device(self.device):
+            for net in (self._Ge, *self._De):  # derived tensors of the evaluation handles follow the trained weights
+                net.prepare()
+            _lib.check(L.depgan_gen_eval_multi(self._Ge.handle, self._De[0].handle, self._De[1].handle, x1.data_ptr(),
+                                               real2.data_ptr(), noises.data_ptr(), self.thr, self._eout6.data_ptr(),
+                                               self._esums.data_ptr(), self._escratch.data_ptr(), n, k, n * self.world,
+                                               _stream(torch)), "gen_eval_multi")
+            if self.dist is not None:
+                if self.collective == "torch":
+                    self.dist.all_reduce(self._esums, op=self.dist.ReduceOp.SUM)
+                else:
+                    self.G.dp_allreduce_f64(self._esums, 8 * k)
+                _lib.check(L.depgan_gen_loss_finalize_multi(self._eout6.data_ptr(), self._esums.data_ptr(), k,
+                                                            n * self.world, self.G.cfg.H * self.G.cfg.W, _stream(torch)),
+                           "gen_loss_finalize_multi")
+        return self._eout6[:k]
+
     def netG_no_update(self, inputs):
         x1, real2, z = [self._dev(a) for a in inputs]
         return [np.float32(v) for v in self.gen_device(x1, real2, z, False).cpu().numpy()]
@@ -274,9 +319,12 @@ class DepGanTrainer:
             self.critic_update_device(0, *b)
         for b in crit_dem_batches:
             self.critic_update_device(1, *b)
-        losses = torch.empty(noises.shape[0], dtype=torch.float32, device=self.device)
-        for k in range(noises.shape[0]):
-            losses[k] = self.gen_device(x1, real2, noises[k], False)[0]
+        if self.batched_eval:
+            losses = self.gen_eval_multi_device(x1, real2, noises)[:, 0].contiguous()
+        else:
+            losses = torch.empty(noises.shape[0], dtype=torch.float32, device=self.device)
+            for k in range(noises.shape[0]):
+                losses[k] = self.gen_device(x1, real2, noises[k], False)[0]
         sel = torch.argmin(losses)                        # TG:875-876
         z = noises.index_select(0, sel.reshape(1))[0].contiguous()
         out = self.gen_device(x1, real2, z, True, update=True)

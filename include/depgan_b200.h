@@ -159,6 +159,18 @@ int depgan_profile_end(double* ms_by_class, double* flops_by_class, double* byte
 int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, long long cap_floats,
                             long long* n_floats, int n, void* stream);
 
+/* netG_no_update for k noise candidates of ONE batch in a single pass (TG:868-874: the ten evaluations of a generator
+ * iteration share x / real_2tp and differ only in the noise).  z_all (k, n, L, 1); out6_all (k, 6); sums_all (k, 8);
+ * scratch: k * n * H * W * (nicg + 1) floats.  Any prepared handles with max_batch >= k * n serve (e.g. inference handles
+ * created on the training networks' parameter buffers).  Every candidate's six values equal those of depgan_gen_eval.
+ * Data parallel: sum sums_all over the ranks (depgan_dp_allreduce_f64, 8 * k doubles), then
+ * depgan_gen_loss_finalize_multi. */
+int depgan_gen_eval_multi(depgan_net* g, depgan_net* dy2, depgan_net* ddem, const float* x1_dev, const float* real2_dev,
+                          const float* z_all_dev, float thr, float* out6_all_dev, double* sums_all_dev, float* scratch_dev,
+                          int n, int k, int global_n, void* stream);
+int depgan_gen_loss_finalize_multi(float* out6_all_dev, double* sums_all_dev, int k, int global_n, long long hw,
+                                   void* stream);
+
 /* ---- data-parallel update without Python in the loop (depgan_allreduce_attach; TG:549, 568, 594 applied
  * to the global batch) ----
  * After depgan_critic_grads / depgan_gen_grads (called with the GLOBAL batch size) each rank's gradient bucket holds its
@@ -189,7 +201,7 @@ int depgan_dp_update(depgan_net* h, float* m_dev, float* v_dev, int t, float lr,
                      double* extra_f64, int n_extra, void* stream);
 /* The sum of the buckets over the ranks left in the bucket (no optimizer step); extra_f64 as above. */
 int depgan_dp_allreduce_grads(depgan_net* h, double* extra_f64, int n_extra, void* stream);
-/* In-place sum over the ranks of n <= 32 doubles on the device: the loss partial sums of the forward-only evaluations
+/* In-place sum over the ranks of n <= 128 doubles on the device: the loss partial sums of the forward-only evaluations
  * (TG:868-877 -- every rank must see the same ten candidate losses to pick the same noise). */
 int depgan_dp_allreduce_f64(depgan_net* h, double* buf_dev, int n, void* stream);
 

@@ -16,6 +16,9 @@ G = Gen_UNet2D((256, 256, 1), (32, 1), 32, 1, precision="bf16", max_batch=B, dev
 D1 = Dis_C2D_FCN1((256, 256, 1), precision="bf16", max_batch=3 * B, device=str(dev), training=True, seed=1)
 D2 = Dis_C2D_FCN1((256, 256, 1), precision="bf16", max_batch=3 * B, device=str(dev), training=True, seed=2)
 tr = DepGanTrainer(G, D1, D2, 0.178)
+import os
+if not os.environ.get("DEPGAN_NO_BATCHED_EVAL"):
+    tr.enable_batched_eval(10)
 
 
 def batch(seed):

@@ -175,3 +175,27 @@ def test_fit_runs_the_reference_loop(tmp_path):
     g2.load_weights(path)
     a, b = tr.G.get_weights(), g2.get_weights()
     assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize("precision,H", [("fp32", 32), ("bf16", 128)])
+def test_batched_noise_evaluation_matches_one_by_one(precision, H):
+    """TG:868-877: the ten netG_no_update calls of a generator iteration share x / real_2tp and differ in the noise.
+    enable_batched_eval runs them as ONE pass over k * n rows on inference handles that share the training networks'
+    parameter buffers; slices never mix, so every candidate's six values equal the one-by-one evaluation, also after a
+    weight update (the evaluation handles are re-prepared), and the generator iteration selects the same noise."""
+    n, k = 2, 4
+    tr, _, (x1, y2, z, ep) = _setup(H, n, precision)
+    torch_ = tr.torch
+    dev = tr.device
+    noises = torch_.from_numpy(np.stack([synth.make_noise(n, seed=900 + j) for j in range(k)])).to(dev)
+    x1d, y2d = tr._dev(x1), tr._dev(y2)
+    tr.enable_batched_eval(k)
+    for round_ in range(2):
+        one = np.stack([tr.gen_device(x1d, y2d, noises[j].contiguous(), False).cpu().numpy().copy() for j in range(k)])
+        multi = tr.gen_eval_multi_device(x1d, y2d, noises).cpu().numpy()
+        assert np.allclose(multi, one, rtol=1e-5, atol=1e-6), (round_, multi, one)
+        tr.netD_y2_train([y2, x1, z, ep])      # weights move: the evaluation handles must follow
+        tr.netG_train([x1, y2, z])
+    losses_b, _ = tr.gen_iteration_device([], [], x1d, y2d, noises)
+    losses_b = losses_b.cpu().numpy().copy()
+    assert losses_b.shape == (k,) and np.isfinite(losses_b).all()
