@@ -51,6 +51,7 @@ SIGNATURES = {
     "depgan_gen_forward": (_I, [_P, _P, _P, _P, _I, _P]),
     "depgan_critic_forward": (_I, [_P, _P, _P, _I, _P]),
     "depgan_critic_grads": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "depgan_critic_grads_dem": (_I, [_P, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P]),
     "depgan_gen_eval": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P]),
     "depgan_gen_grads": (_I, [_P, _P, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P]),
     "depgan_gen_loss_finalize": (_I, [_P, _P, _P]),

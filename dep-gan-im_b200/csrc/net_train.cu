@@ -191,6 +191,10 @@ int critic_backward(depgan_net* d, int rows, int g_row0, int g_rows, cudaStream_
 
 extern "C" {
 
+static int critic_grads_impl(depgan_net* d, int nicg, int which, const float* real2_dev, const float* x1_dev,
+                             const float* dem_dev, const float* ep_dev, float* out4_dev, int n, int global_n,
+                             cudaStream_t st);
+
 int depgan_critic_grads(depgan_net* d, depgan_net* g, int which, const float* real2_dev, const float* x1_dev,
                         const float* z_dev, const float* ep_dev, float* out4_dev, int n, int global_n, void* stream) {
   DG_REQUIRE(d && g && d->model == DEPGAN_MODEL_CRITIC && g->model == DEPGAN_MODEL_GEN, "critic_grads: bad handles");
@@ -199,16 +203,39 @@ int depgan_critic_grads(depgan_net* d, depgan_net* g, int which, const float* re
   DG_REQUIRE(n >= 1 && 3 * n <= d->cfg.max_batch && n <= g->cfg.max_batch, "critic_grads: batch too large");
   DG_REQUIRE(g->cfg.nc_out == 1 && g->cfg.H == d->cfg.H && g->cfg.W == d->cfg.W, "critic_grads: shape mismatch");
   DG_REQUIRE(which == 0 || which == 1, "critic_grads: which must be 0 (Y2) or 1 (DEM)");
-  if (global_n <= 0) global_n = n;
   cudaStream_t st = (cudaStream_t)stream;
+  // 1. G forward in inference mode (TG:533 / 556)
+  DG_TRY(gen_forward_impl(g, x1_dev, z_dev, g->dem_f32, n, false, st));
+  return critic_grads_impl(d, g->cfg.nicg, which, real2_dev, x1_dev, g->dem_f32, ep_dev, out4_dev, n, global_n, st);
+}
+
+// The same graph with the generator output given: the generator's weights do not change during the critic updates of a
+// generator iteration (TG:796-829), so a trainer may run all their generator forwards as one batched pass
+// (depgan_gen_forward on the concatenated batches) and feed the slices here.
+int depgan_critic_grads_dem(depgan_net* d, int nicg, int which, const float* real2_dev, const float* x1_dev,
+                            const float* dem_dev, const float* ep_dev, float* out4_dev, int n, int global_n,
+                            void* stream) {
+  DG_REQUIRE(d && d->model == DEPGAN_MODEL_CRITIC, "critic_grads_dem: bad handle");
+  DG_REQUIRE(d->cfg.training && d->tr && d->grads, "critic_grads_dem: the critic handle was not created for training");
+  DG_REQUIRE(d->prepared, "critic_grads_dem: call depgan_net_prepare first");
+  DG_REQUIRE(n >= 1 && 3 * n <= d->cfg.max_batch && nicg >= 1, "critic_grads_dem: batch too large");
+  DG_REQUIRE(which == 0 || which == 1, "critic_grads_dem: which must be 0 (Y2) or 1 (DEM)");
+  DG_REQUIRE(real2_dev && x1_dev && dem_dev && ep_dev && out4_dev, "critic_grads_dem: null pointer");
+  return critic_grads_impl(d, nicg, which, real2_dev, x1_dev, dem_dev, ep_dev, out4_dev, n, global_n,
+                           (cudaStream_t)stream);
+}
+
+static int critic_grads_impl(depgan_net* d, int nicg, int which, const float* real2_dev, const float* x1_dev,
+                             const float* dem_dev, const float* ep_dev, float* out4_dev, int n, int global_n,
+                             cudaStream_t st) {
+  if (global_n <= 0) global_n = n;
   Train& T = *d->tr;
   const long long hw = (long long)d->cfg.H * d->cfg.W;
   const float inv_n = 1.0f / (float)global_n;
   const float delta = 10.0f;  // TG:37
 
-  // 1. G forward in inference mode (TG:533 / 556), critic inputs [real | fake | mixed] (TG:534-538, 557)
-  DG_TRY(gen_forward_impl(g, x1_dev, z_dev, g->dem_f32, n, false, st));
-  DG_TRY(k_critic_inputs(real2_dev, x1_dev, g->cfg.nicg, g->dem_f32, ep_dev, which, T.batch3, n, hw, DT_F32, st));
+  // critic inputs [real | fake | mixed] (TG:534-538, 557)
+  DG_TRY(k_critic_inputs(real2_dev, x1_dev, nicg, dem_dev, ep_dev, which, T.batch3, n, hw, DT_F32, st));
   // 2. critic forward on 3n rows
   DG_TRY(critic_forward_impl(d, T.batch3, d->c_out, 3 * n, st));
   DG_CHECK_CUDA(cudaMemsetAsync(out4_dev, 0, 4 * sizeof(float), st));

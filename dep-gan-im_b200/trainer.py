@@ -167,7 +167,7 @@ class DepGanTrainer:
             self.dist.all_reduce(net.grads, op=self.dist.ReduceOp.SUM)
 
     # ---- critics (TG:523-571) -------------------------------------------------------------------------
-    def critic_grads_device(self, which, real2, x1, z, ep, reduce=True):
+    def critic_grads_device(self, which, real2, x1, z, ep, reduce=True, dem=None):
         """Device tensors in; leaves dLoss/dtheta in the critic's flat gradient buffer and returns the float32
         CUDA tensor [loss_real, loss_fake, gradient_penalty, loss] for the GLOBAL batch."""
         torch = self.torch
@@ -176,9 +176,16 @@ class DepGanTrainer:
         if 3 * n > D.cfg.max_batch:
             raise ValueError("the critic needs max_batch >= 3 * batch (real | fake | mixed rows)")
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().depgan_critic_grads(D.handle, self.G.handle, which, real2.data_ptr(), x1.data_ptr(),
-                                                      z.data_ptr(), ep.data_ptr(), self.out4.data_ptr(), n,
-                                                      n * self.world, _stream(torch)), "critic_grads")
+            if dem is not None:  # G(x1, z) computed ahead in a batched pass (gen_iteration_device)
+                _lib.check(_lib.lib().depgan_critic_grads_dem(D.handle, self.G.cfg.nicg, which, real2.data_ptr(),
+                                                              x1.data_ptr(), dem.data_ptr(), ep.data_ptr(),
+                                                              self.out4.data_ptr(), n, n * self.world, _stream(torch)),
+                           "critic_grads_dem")
+            else:
+                _lib.check(_lib.lib().depgan_critic_grads(D.handle, self.G.handle, which, real2.data_ptr(),
+                                                          x1.data_ptr(), z.data_ptr(), ep.data_ptr(),
+                                                          self.out4.data_ptr(), n, n * self.world, _stream(torch)),
+                           "critic_grads")
         if self.collective == "torch":
             self.dist.all_reduce(self.out4, op=self.dist.ReduceOp.SUM)
             self._allreduce_grads(D)
@@ -300,11 +307,11 @@ class DepGanTrainer:
         return [np.float32(v) for v in vals]
 
     # ---- fully asynchronous device-side variants (no host round trip inside a generator iteration) -------
-    def critic_update_device(self, which, real2, x1, z, ep):
+    def critic_update_device(self, which, real2, x1, z, ep, dem=None):
         """One critic update (grads + all-reduce + Adam) on CUDA tensors; returns the loss tensor (no sync)."""
         D = self.Dy2 if which == 0 else self.Ddem
         native = self.collective in ("peer", "nccl")
-        out = self.critic_grads_device(which, real2, x1, z, ep, reduce=not native)
+        out = self.critic_grads_device(which, real2, x1, z, ep, reduce=not native, dem=dem)
         if native:
             self._critic_update_native(D)
         else:
@@ -315,10 +322,23 @@ class DepGanTrainer:
         """TG:796-878 on CUDA tensors.  crit_*_batches: lists of (real2, x1, z, ep); noises: (k,N,L,1) tensor.
         The argmin over the k candidate losses and the gather of the selected noise stay on the device."""
         torch = self.torch
-        for b in crit_y2_batches:
-            self.critic_update_device(0, *b)
-        for b in crit_dem_batches:
-            self.critic_update_device(1, *b)
+        todo = [(0, b) for b in crit_y2_batches] + [(1, b) for b in crit_dem_batches]
+        if self.batched_eval and todo:
+            # the generator is frozen until the end of the iteration: its forwards for all critic updates run as batched
+            # passes (up to k_noise batches at a time) on the evaluation handle
+            self._Ge.prepare()
+            n = int(todo[0][1][1].shape[0])
+            per = max(1, self._Ge.cfg.max_batch // n)
+            for c0 in range(0, len(todo), per):
+                chunk = todo[c0:c0 + per]
+                xcat = torch.cat([b[1] for _, b in chunk]) if len(chunk) > 1 else chunk[0][1][1]
+                zcat = torch.cat([b[2] for _, b in chunk]) if len(chunk) > 1 else chunk[0][1][2]
+                dems = self._Ge.forward_device(xcat.contiguous(), zcat.contiguous())
+                for j, (which, b) in enumerate(chunk):
+                    self.critic_update_device(which, *b, dem=dems[j * n:(j + 1) * n])
+        else:
+            for which, b in todo:
+                self.critic_update_device(which, *b)
         if self.batched_eval:
             losses = self.gen_eval_multi_device(x1, real2, noises)[:, 0].contiguous()
         else:

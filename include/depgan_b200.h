@@ -159,6 +159,12 @@ int depgan_profile_end(double* ms_by_class, double* flops_by_class, double* byte
 int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, long long cap_floats,
                             long long* n_floats, int n, void* stream);
 
+/* depgan_critic_grads with the generator output given (dem_dev (n,H,W,1) float32 = G(x1, z)): the generator's weights do
+ * not change during the critic updates of a generator iteration (TG:796-829), so all their generator forwards can run as
+ * one batched depgan_gen_forward on the concatenated batches and be fed here slice by slice. */
+int depgan_critic_grads_dem(depgan_net* d, int nicg, int which, const float* real2_dev, const float* x1_dev,
+                            const float* dem_dev, const float* ep_dev, float* out4_dev, int n, int global_n,
+                            void* stream);
 /* netG_no_update for k noise candidates of ONE batch in a single pass (TG:868-874: the ten evaluations of a generator
  * iteration share x / real_2tp and differ only in the noise).  z_all (k, n, L, 1); out6_all (k, 6); sums_all (k, 8);
  * scratch: k * n * H * W * (nicg + 1) floats.  Any prepared handles with max_batch >= k * n serve (e.g. inference handles

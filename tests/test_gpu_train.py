@@ -196,6 +196,20 @@ def test_batched_noise_evaluation_matches_one_by_one(precision, H):
         assert np.allclose(multi, one, rtol=1e-5, atol=1e-6), (round_, multi, one)
         tr.netD_y2_train([y2, x1, z, ep])      # weights move: the evaluation handles must follow
         tr.netG_train([x1, y2, z])
-    losses_b, _ = tr.gen_iteration_device([], [], x1d, y2d, noises)
+    # the critic graph fed with a generator output computed ahead (batched) equals the graph that runs G itself
+    zd, epd = tr._dev(z), tr._dev(ep).reshape(-1).contiguous()
+    for which in (0, 1):
+        a = tr.critic_grads_device(which, y2d, x1d, zd, epd).cpu().numpy().copy()
+        ga = (tr.Dy2 if which == 0 else tr.Ddem).get_grads()
+        tr._Ge.prepare()
+        dem = tr._Ge.forward_device(x1d, zd)
+        b = tr.critic_grads_device(which, y2d, x1d, zd, epd, dem=dem).cpu().numpy().copy()
+        gb = (tr.Dy2 if which == 0 else tr.Ddem).get_grads()
+        assert np.allclose(a, b, rtol=1e-5, atol=1e-6), (which, a, b)
+        fa = np.concatenate([v.ravel() for v in ga.values()])
+        fb = np.concatenate([gb[k_].ravel() for k_ in ga])
+        assert np.linalg.norm(fa - fb) <= 1e-4 * np.linalg.norm(fa), which
+    batches = [(y2d, x1d, zd, epd)] * 2
+    losses_b, _ = tr.gen_iteration_device(batches, batches, x1d, y2d, noises)
     losses_b = losses_b.cpu().numpy().copy()
     assert losses_b.shape == (k,) and np.isfinite(losses_b).all()
