@@ -901,6 +901,11 @@ int dispatch_g(const ConvArgs& a, cudaStream_t st, bool run) {
     RG_CASE(5, 32, 16, 2, false) RG_CASE(5, 32, 16, 0, false)
     RG_CASE(5, 32, 32, 0, false) RG_CASE(5, 32, 32, 2, false) RG_CASE(5, 32, 32, 4, false)
   }
+  // generator 3x3 32 -> 32 at full resolution with the fused max-pool (conv2d_gen_1 + maxpool2d_gen_0, TG:408-409); the
+  // other epilogues of this shape belong to conv_row.cu, which is asked first
+  if (a.ks == 3 && cin == 32) {
+    RG_CASE(3, 32, 32, 4, false) RG_CASE(3, 32, 32, 4, true) RG_CASE(3, 32, 32, 0, false)
+  }
   // generator 3x3 layers with 64 output channels at half resolution: 32 -> 64, 64 -> 64 (two 32-channel chunks)
   if (a.ks == 3 && (cin == 32 || cin == 64)) {
     RG_CASE(3, 32, 64, 0, false) RG_CASE(3, 32, 64, 1, false) RG_CASE(3, 32, 64, 2, false)

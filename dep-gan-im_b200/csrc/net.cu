@@ -396,7 +396,10 @@ int gen_forward_impl(depgan_net* g, const float* x, const float* z, float* out, 
     // profile counts those launches as their own class, 6, with the pooled bytes included).  Inference handles keep
     // the separate bandwidth pass: measured at batch 64 the two are equal within noise (27.37 k fused vs 27.46 k
     // slices/s), the epilogue's extra shared-memory traffic costing what the saved pass would have.
-    const bool fuse_pool = bi < 3 && g->cfg.training != 0;
+    // Round 2: the first block's pool (32 channels at full resolution) is fused for inference handles too -- the generic
+    // row kernel pools the row pair it holds in registers, which saves re-reading the 268 MB tensor (A/B switch below).
+    static const bool no_infer_fuse = getenv("DEPGAN_NO_INFER_POOLFUSE") != nullptr;
+    const bool fuse_pool = bi < 3 && (g->cfg.training != 0 || (bi == 0 && dt_is_half(g->act_dt) && !no_infer_fuse));
     if (fuse_pool) e.pool_out = g->act_pool[bi];
     DG_TRY(net_conv(g, g->g_out[bi], g->act_r[bi], w, nullptr, 0, g->act_dt, e, n, st));
     if (bi < 3) {

@@ -254,31 +254,40 @@ class DepGanTrainer:
         return self.out6
 
     # ---- the ten candidate evaluations of a generator iteration in one pass (TG:868-874) ------------------------
-    def enable_batched_eval(self, k_noise=10):
-        """Creates inference handles for k_noise * batch rows on the training networks' parameter buffers (own
-        workspaces; the training handles' backward buffers are not multiplied) and switches gen_iteration_device to the
-        one-pass evaluation.  The candidates' losses are those of the one-by-one evaluation (slices never mix)."""
+    def enable_batched_eval(self, k_noise=10, max_rows=640):
+        """Creates inference handles for up to k_noise * batch rows (capped at max_rows: ~0.14 GB of workspace per row at
+        256 x 256) on the training networks' parameter buffers (own workspaces; the training handles' backward buffers
+        are not multiplied) and switches gen_iteration_device to batched evaluation passes.  The candidates' losses are
+        those of the one-by-one evaluation (slices never mix).  Returns False (and changes nothing) when not even two
+        batches fit under max_rows -- large batches fill the GPU on their own."""
         from .api import Dis_C2D_FCN1, Gen_UNet2D
         G = self.G
-        rows = int(k_noise) * G.cfg.max_batch
+        per = min(int(k_noise), int(max_rows) // G.cfg.max_batch)
+        if per < 2:
+            return False
+        rows = per * G.cfg.max_batch
         H, W = G.cfg.H, G.cfg.W
         self._Ge = Gen_UNet2D(G.input_shape, G.noiseZ_shape, 32, 1, precision=G.precision, max_batch=rows,
                               device=str(self.device), share_params_with=G)
         self._De = [Dis_C2D_FCN1((H, W, 1), precision=D.precision, max_batch=rows, device=str(self.device),
                                  share_params_with=D) for D in (self.Dy2, self.Ddem)]
         torch = self.torch
-        self._ek = int(k_noise)
+        self._ek = per
         self._escratch = torch.empty(rows * H * W * (G.cfg.nicg + 1), dtype=torch.float32, device=self.device)
         self._eout6 = torch.zeros((self._ek, 6), dtype=torch.float32, device=self.device)
         self._esums = torch.zeros((self._ek, 8), dtype=torch.float64, device=self.device)
         self.batched_eval = True
+        return True
 
     def gen_eval_multi_device(self, x1, real2, noises):
         """noises (k, n, L, 1) CUDA tensor -> (k, 6) float32 CUDA tensor of [loss, lf, lfd, M1, M3, M4] per candidate."""
         torch = self.torch
         k, n = int(noises.shape[0]), int(x1.shape[0])
-        if k > self._ek or k * n > self._Ge.cfg.max_batch:
-            raise ValueError("enable_batched_eval was sized for fewer candidates / a smaller batch")
+        if n > self.G.cfg.max_batch:
+            raise ValueError("batch larger than the networks' max_batch")
+        if k > self._ek:  # more candidates than one pass holds: several passes
+            return torch.cat([self.gen_eval_multi_device(x1, real2, noises[c:c + self._ek]).clone()
+                              for c in range(0, k, self._ek)])
         L = _lib.lib()
         with torch.cuda.device(self.device):
             for net in (self._Ge, *self._De):  # derived tensors of the evaluation handles follow the trained weights

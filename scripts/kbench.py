@@ -24,7 +24,7 @@ def act(shape, bf16, seed):
 
 
 def conv_case(name, N, H, W, c0, cout, ks, *, c1=0, tc=True, in_bf16=None, film=False, add=False, mask=False,
-              deconv=False, pre=False, relu=True, out_bf16=True, head=0, film_self=False):
+              deconv=False, pre=False, relu=True, out_bf16=True, head=0, film_self=False, pool=False):
     in_bf16 = tc if in_bf16 is None else in_bf16
     keep = []
     d = _lib.ConvDesc()
@@ -67,6 +67,9 @@ def conv_case(name, N, H, W, c0, cout, ks, *, c1=0, tc=True, in_bf16=None, film=
     if mask:
         t = act((N, H, W, cout), out_bf16, 5); keep.append(t); d.mask_src = t.data_ptr()
         nbytes += t.numel() * t.element_size()
+    if pool:
+        t = torch.empty((N, oh // 2, ow // 2, cout), dtype=odt, device=dev); keep.append(t); d.pool_out = t.data_ptr()
+        nbytes += t.numel() * t.element_size()
     if head:
         hw, hb = torch.randn(cout, head, device=dev) * 0.1, torch.zeros(head, device=dev)
         ho = torch.empty((N, H, W, head), device=dev); keep += [hw, hb, ho]
@@ -107,6 +110,8 @@ CASES = [
     lambda: wgrad_case("wgrad_first_5x5_1to16_N64", 64, 256, 256, 1, 16, 5, 2),
     lambda: wgrad_case("wgrad_first_3x3_1to32_N32", 32, 256, 256, 1, 32, 3, 2),
     lambda: conv_case("tc_3x3_32to32_plain_N64", 64, 256, 256, 32, 32, 3),
+    lambda: conv_case("tc_3x3_32to32_pool_N64", 64, 256, 256, 32, 32, 3, pool=True),
+    lambda: conv_case("tc_3x3_64to64_pool_N64", 64, 128, 128, 64, 64, 3, pool=True),
     lambda: conv_case("tc_3x3_32to32_plain_N8_l2", 8, 256, 256, 32, 32, 3),
     lambda: conv_case("tc_3x3_32to32_plain_N16_l2", 16, 256, 256, 32, 32, 3),
     lambda: conv_case("tc_3x3_32to32_filmA_N8_l2", 8, 256, 256, 32, 32, 3, film=True, relu=False, film_self=True),
