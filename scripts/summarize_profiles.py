@@ -44,12 +44,12 @@ def full_summary(src, dst, traffic_json, batch, bench_batch, alg_bytes_b16):
     name_i, dur_i = hdr.index("Kernel Name"), hdr.index("gpu__time_duration.sum")
     rd_i, wr_i = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     tp_i = hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
-    k3 = [d for d in data if "conv_tc_kernel<3" in d[name_i] or "conv_row_kernel" in d[name_i]]
+    k3 = [d for d in data if "conv_tc_kernel<3" in d[name_i] or "conv_row_kernel" in d[name_i] or "conv_rowg_kernel<3" in d[name_i]]
     dur = sum(float(d[dur_i]) for d in k3)
     dram = sum(float(d[rd_i]) + float(d[wr_i]) for d in k3) * 1e6
     tens = sum(float(d[tp_i]) * float(d[dur_i]) for d in k3) / dur
     json.dump({
-        "source": "ncu --set full --clock-control none, conv_tc_kernel<3,*,*,*> + conv_row_kernel, the %d launches of one DEP-UResNet "
+        "source": "ncu --set full --clock-control none, conv_tc_kernel<3,*> + conv_row_kernel + conv_rowg_kernel<3,*>, the %d launches of one DEP-UResNet "
                   "forward at batch %d (profiles/%s)" % (len(k3), batch, dst.name),
         "launches": len(k3), "dram_bytes_total_batch%d" % batch: dram,
         "algorithmic_bytes_total_batch%d" % batch: alg_bytes_b16,
