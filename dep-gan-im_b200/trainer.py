@@ -254,7 +254,7 @@ class DepGanTrainer:
         return self.out6
 
     # ---- the ten candidate evaluations of a generator iteration in one pass (TG:868-874) ------------------------
-    def enable_batched_eval(self, k_noise=10, max_rows=640):
+    def enable_batched_eval(self, k_noise=10, max_rows=320):
         """Creates inference handles for up to k_noise * batch rows (capped at max_rows: ~0.14 GB of workspace per row at
         256 x 256) on the training networks' parameter buffers (own workspaces; the training handles' backward buffers
         are not multiplied) and switches gen_iteration_device to batched evaluation passes.  The candidates' losses are
