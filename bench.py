@@ -436,7 +436,8 @@ def measure_config0(args, rank, world, dev):
 def measure_precision_variants(args, rank, dev):
     """The other arithmetic variants of the same forward (configs[0] shape, batch 16, device-resident, rank 0 only):
     'fp32' = the FP32-storage / FP32-accumulate CUDA-core path (the <= 1e-4 variant of BASELINE.json's north_star) and
-    'bf16' = the tcgen05 path with bfloat16 storage (what training runs), next to the IEEE-half default."""
+    'f16x3' = the tensor-core <= 1e-4 variant (split-half storage, three products per convolution), 'bf16' = the tcgen05
+    path with bfloat16 storage (what training runs), next to the IEEE-half default."""
     import torch
     from depgan_b200 import Gen_UNet2D
     if rank != 0:
@@ -447,7 +448,7 @@ def measure_precision_variants(args, rank, dev):
     xd, zd = torch.from_numpy(x).to(dev), torch.from_numpy(z).to(dev)
     out = torch.empty((B, 256, 256, 1), dtype=torch.float32, device=dev)
     res, ref = {}, None
-    for prec, steps in (("fp32", 3), ("bf16", 20), ("f16", 20)):
+    for prec, steps in (("fp32", 3), ("f16x3", 10), ("bf16", 20), ("f16", 20)):
         g = Gen_UNet2D((256, 256, 1), (32, 1), 32, 1, precision=prec, max_batch=B, device=str(dev))
         g.set_weights(make_weights(w, g))
         for _ in range(2):
@@ -469,7 +470,9 @@ def measure_precision_variants(args, rank, dev):
         del g
         torch.cuda.empty_cache()
     res["what"] = ("DEP-GAN generator forward, batch 16, device-resident; fp32 = CUDA-core FP32 storage + accumulate, "
-                   "bf16 / f16 = tcgen05 (fp32 accumulate in TMEM) with bfloat16 / IEEE-half activations and weights")
+                   "f16x3 = the tensor-core <= 1e-4 variant (values as IEEE-half (hi, lo) pairs, three tcgen05 products "
+                   "per convolution, fp32 accumulate in TMEM), bf16 / f16 = tcgen05 with bfloat16 / IEEE-half "
+                   "activations and weights")
     return res
 
 

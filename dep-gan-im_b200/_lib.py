@@ -13,7 +13,7 @@ HERE = Path(__file__).resolve().parent
 HEADER = HERE.parent / "include" / "depgan_b200.h"
 
 MODEL_GEN, MODEL_CRITIC = 0, 1
-PREC_FP32, PREC_BF16, PREC_F16 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_F16, PREC_F16X3 = 0, 1, 2, 3
 
 
 class Cfg(C.Structure):

@@ -277,7 +277,9 @@ def _prec(precision):
         return _lib.PREC_FP32
     if precision in ("f16", "fp16", _lib.PREC_F16):
         return _lib.PREC_F16
-    raise ValueError("precision must be 'bf16', 'f16' (generator inference) or 'fp32'")
+    if precision in ("f16x3", "split", _lib.PREC_F16X3):
+        return _lib.PREC_F16X3
+    raise ValueError("precision must be 'bf16', 'f16' / 'f16x3' (generator inference) or 'fp32'")
 
 
 class Gen_UNet2D(_Net):
@@ -285,7 +287,9 @@ class Gen_UNet2D(_Net):
 
     nc_out == 1 -> tanh head (DEP-GAN generator); nc_out == 4 -> softmax head (DEP-UResNet).
     Extra keyword arguments choose the arithmetic ('bf16' tcgen05 path; 'f16' = the same kernels with IEEE-half
-    activations and weights, inference handles only, ~7x smaller DEM error at the same speed; 'fp32' CUDA-core path),
+    activations and weights, inference handles only, ~7x smaller DEM error at the same speed; 'f16x3' = the tensor-core
+    <= 1e-4 variant: values kept as (hi, lo) half pairs, three tcgen05 products per convolution, inference handles with
+    H, W multiples of 128; 'fp32' CUDA-core path),
     the workspace batch, the device and the synthetic-initialisation seed.
     """
 

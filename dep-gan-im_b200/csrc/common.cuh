@@ -103,9 +103,14 @@ inline void dg_device_mark(DgPerDevice& s, int dev) { if (dev < 64) s.done |= 1u
 // DT_F16: IEEE half storage of the inference-only generator handles (DEPGAN_PREC_F16): same tcgen05 kind::f16 rate and
 // the same kernels as bf16 (the 16-bit format is a run-time flag of the pack / unpack points), 3 more mantissa bits
 // per stored activation -- DEM max-abs error ~1.5e-3 instead of ~1e-2 with un-normalised (freshly initialised) weights.
-enum DType { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
-static inline size_t dt_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+// DT_F16S: "split half" storage of the tensor-core <= 1e-4 handles (DEPGAN_PREC_F16X3): every value v is kept as the pair
+// hi = half(v), lo = half(v - hi) (22 significant bits), a pixel's C channels stored as [C hi | C lo] (4 bytes per
+// element, the size of fp32).  Convolutions run as three kind::f16 products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32
+// accumulation in TMEM (the dropped x_lo*w_lo term is 2^-22 relative), i.e. a K = 3*Cin implicit GEMM of the same kernel.
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2, DT_F16S = 3 };
+static inline size_t dt_size(int dt) { return (dt == DT_F32 || dt == DT_F16S) ? 4 : 2; }
 static inline bool dt_is_half(int dt) { return dt == DT_BF16 || dt == DT_F16; }
+static inline bool dt_is_tc(int dt) { return dt_is_half(dt) || dt == DT_F16S; }  // formats the tcgen05 kernels take
 
 // ---- typed load/store helpers ----
 __device__ __forceinline__ float ldf(const float* p) { return *p; }

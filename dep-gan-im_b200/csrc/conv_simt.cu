@@ -4,6 +4,7 @@
 // tcgen05 path does not take (Cin < 16 first layers, Cout = 1 dgrad of the critic's first layer).
 // Replaces Keras Conv2D (+BatchNormalization, +Activation) of TG:285-304 and its K.gradients (TG:543-549).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -144,6 +145,7 @@ int launch_fwd(const ConvArgs& a, cudaStream_t st) {
 //     shuffles, over the CTA in shared memory and over CTAs by one atomic per element.
 // ------------------------------------------------------------------------------------------------------
 constexpr int EDGE_ROWS = 32;  // rows per CTA band
+struct hsplit { char pad_[4]; };  // output tag: split-half storage (DT_F16S), a pixel = [COUT hi | COUT lo] IEEE halves
 
 template <int N>
 struct VecIO;  // N consecutive channels of one pixel
@@ -343,6 +345,17 @@ __global__ void __launch_bounds__(256, 2) conv_first_kernel(const float* __restr
           acc[c] = fmaf(acc[c], sc[c], sh[c]);
           if (relu) acc[c] = fmaxf(acc[c], 0.f);
         }
+        if constexpr (std::is_same<TO, hsplit>::value) {
+          __half* op = reinterpret_cast<__half*>(out) + 2 * (o - c0) + c0;  // pixel pitch 2*COUT
+          float lo[CPT];
+#pragma unroll
+          for (int c = 0; c < CPT; ++c) {
+            const float hi = __half2float(__float2half_rn(fminf(fmaxf(acc[c], -65504.f), 65504.f)));
+            lo[c] = acc[c] - hi;
+          }
+          VecIO<CPT>::store(op, acc);
+          VecIO<CPT>::store(op + COUT, lo);
+        } else {
         if (mask) {  // activation-pattern mask of the JVP pass (TG:543: the critic linearised at the mixed sample)
           float m[CPT];
           VecIO<CPT>::load(mask + o, m);
@@ -350,6 +363,7 @@ __global__ void __launch_bounds__(256, 2) conv_first_kernel(const float* __restr
           for (int c = 0; c < CPT; ++c) acc[c] = m[c] > 0.f ? acc[c] : 0.f;
         }
         VecIO<CPT>::store(out + o, acc);
+        }
       }
     }
   }
@@ -706,13 +720,16 @@ int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
       if (r0 != 0) return r0 < 0 ? r0 : 0;
     }
     const int r = a.out_dt == DT_BF16 ? try_first<bf16>(a, st)
-                  : a.out_dt == DT_F16 ? try_first<__half>(a, st) : try_first<float>(a, st);
+                  : a.out_dt == DT_F16 ? try_first<__half>(a, st)
+                  : a.out_dt == DT_F16S ? try_first<hsplit>(a, st) : try_first<float>(a, st);
     if (r != 0) return r < 0 ? r : 0;
     if (a.in_dt != DT_F16) {
       const int r2 = a.in_dt == DT_BF16 ? try_last<bf16>(a, st) : try_last<float>(a, st);
       if (r2 != 0) return r2 < 0 ? r2 : 0;
     }
   }
+  DG_REQUIRE(a.in_dt != DT_F16S && a.out_dt != DT_F16S,
+             "conv_fwd_simt: split-half storage has no CUDA-core path beyond the first layer (H, W multiples of 128)");
   // IEEE-half handles (generator inference): first layer (fp32 image in) and the levels below 16x16
   if (a.in_dt == DT_F32 && a.out_dt == DT_F16) return launch_fwd<float, __half>(a, st);
   if (a.in_dt == DT_F16 && a.out_dt == DT_F16) return launch_fwd<__half, __half>(a, st);

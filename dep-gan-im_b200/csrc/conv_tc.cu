@@ -21,10 +21,13 @@ CUtensorMapSwizzle swizzle_for(int kc) {  // kc bf16 channels = one swizzle span
   return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
 }
 
+// `pitch` = 16-bit elements per pixel in memory when the map covers only a channel range of the tensor (the hi or lo half
+// of a split-half tensor); 0 = the tensor has exactly C channels
 int make_nhwc_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int box_c, int box_w, int box_h,
-                  const char* what) {
+                  const char* what, int pitch = 0) {
+  const cuuint64_t P = pitch ? pitch : C;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint64_t strides[3] = {P * 2, (cuuint64_t)W * P * 2, (cuuint64_t)H * W * P * 2};
   cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p), dims, strides, box, es,
@@ -43,10 +46,10 @@ int make_act_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int
 
 // Output of the k2 s2 transposed convolution, (N, 2H, 2W, C), seen from the input grid as (c, b, w, a, n*H + h):
 // element ((n*2H + 2h + a) * 2W + 2w + b) * C + c.  One box = the [16 h][16 w] tile of one output parity (a, b).
-int make_deconv_out_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int ch) {
+int make_deconv_out_map(CUtensorMap* tm, const void* p, int C, int W, int H, int N, int ch, int pitch = 0) {
+  const cuuint64_t P = pitch ? pitch : C;
   cuuint64_t dims[5] = {(cuuint64_t)C, 2, (cuuint64_t)W, 2, (cuuint64_t)N * H};
-  cuuint64_t strides[4] = {(cuuint64_t)C * 2, (cuuint64_t)2 * C * 2, (cuuint64_t)2 * W * C * 2,
-                           (cuuint64_t)4 * W * C * 2};
+  cuuint64_t strides[4] = {P * 2, 2 * P * 2, (cuuint64_t)2 * W * P * 2, (cuuint64_t)4 * W * P * 2};
   cuuint32_t box[5] = {(cuuint32_t)ch, 1, 16, 1, 16};
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
   CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(p), dims, strides, box, es,
@@ -94,15 +97,21 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   // epilogue staging: ch-channel chunks of the item's [16][16] tile (a transposed-conv chunk stays inside one parity)
   int ch = ncta % 32 == 0 ? 32 : 16;
   if (a.deconv) ch = (a.Cout % 64 == 0 && ncta % 64 == 0) ? 64 : (a.Cout % 32 == 0 && ncta % 32 == 0) ? 32 : 16;
-  const int n_side = a.film_g ? 1 : (a.add_src ? 1 : 0) + (a.mask_src ? 1 : 0);
+  const bool split = a.in_dt == DT_F16S;  // hi / lo tiles everywhere: K = 3*Cin, two staging tiles and residual tiles
+  if (split) {  // measurement switch: staging chunk width of the split-half layers (the hi + lo tiles double the staging)
+    static const int split_ch = getenv("DEPGAN_SPLIT_CH") ? atoi(getenv("DEPGAN_SPLIT_CH")) : 0;
+    if ((split_ch == 16 || split_ch == 32 || split_ch == 64) && ncta % split_ch == 0 && (!a.deconv || a.Cout % split_ch == 0))
+      ch = split_ch;
+  }
+  const int n_side = a.film_g ? (split ? 2 : 1) : (a.add_src ? 1 : 0) + (a.mask_src ? 1 : 0);
   const int stage_out = a.out ? 1 : 0;
   const uint32_t slot = 256u * ch * 2u;
   const int pool = a.pool_out ? 1 : 0;
-  const uint32_t staging = (stage_out ? 2u : 0u) * slot + 2u * n_side * slot + (pool ? slot / 2u : 0u);
+  const uint32_t staging = (stage_out ? (split ? 4u : 2u) : 0u) * slot + 2u * n_side * slot + (pool ? slot / 2u : 0u);
   const uint32_t floats = 2u * ncols * 4 + (a.head_w ? 16u * a.Cout : 0u) + (a.film_g ? 24u * ncta : 0u) + 64u;
   for (int kc = 64; kc >= 16; kc /= 2) {
     if (a.C0 % kc || a.C1 % kc) continue;
-    const int nchunks = (a.C0 + a.C1) / kc;
+    const int nchunks = (split ? 3 : 1) * (a.C0 + a.C1) / kc;
     const uint32_t a_bytes = round1024((uint32_t)ht * ht * kc * 2), b_bytes = round1024((uint32_t)ncta * kc * 2);
     int na = 0, nb = 0, resident = 0, tps = 1;
     const int nb_all = taps * nchunks;
@@ -138,7 +147,9 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
       }
     }
     g->tiles_w = a.W / 16; g->tiles_h = a.H / 16;
-    g->nchunk0 = a.C0 / kc; g->nchunk1 = a.C1 / kc;
+    g->nchunk0 = (split ? 2 : 1) * a.C0 / kc; g->nchunk1 = (split ? 2 : 1) * a.C1 / kc;
+    g->nchunk2 = split ? a.C0 / kc : 0; g->nchunk3 = split ? a.C1 / kc : 0;
+    g->split = split ? 1 : 0;
     g->kc = kc; g->ncols_total = ncols; g->ncta = ncta; g->tmem_cols = tmem_cols;
     g->na = na; g->nb = nb; g->b_tps = tps; g->a_bytes = a_bytes; g->b_bytes = b_bytes;
     g->a_tx = (uint32_t)ht * ht * kc * 2; g->b_tx = (uint32_t)ncta * kc * 2;
@@ -179,6 +190,7 @@ int conv_tc_init() {
     DG_TRY(set_attrs_ks1());
     DG_TRY(set_attrs_ks3());
     DG_TRY(set_attrs_ks5());
+    DG_TRY(set_attrs_split());
     dg_device_mark(g_dev, dev);
   }
   if (dev < 64) g_num_sms = g_dev.sms[dev];
@@ -192,7 +204,11 @@ bool conv_tc_supported(const ConvArgs& a) {
 }
 
 static bool tile_kernel_supported(const ConvArgs& a) {
-  if (!dt_is_half(a.in_dt) || a.out_dt != a.in_dt) return false;
+  if (!dt_is_tc(a.in_dt) || a.out_dt != a.in_dt) return false;
+  // split-half storage is instantiated for generator inference on the tile kernel: plain / FiLM 3x3, transposed conv
+  if (a.in_dt == DT_F16S && (a.add_src || a.mask_src || a.pool_out || a.out_pre ||
+                             !(a.ks == 3 || (a.ks == 1 && a.deconv && !a.film_g))))
+    return false;
   // IEEE-half storage is instantiated for what generator inference runs: plain / FiLM 3x3 layers and the transposed conv
   if (a.in_dt == DT_F16 && (a.add_src || a.mask_src || a.pool_out || a.out_pre || !(a.ks == 3 || (a.ks == 1 && !a.film_g))))
     return false;
@@ -234,16 +250,25 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
   uint32_t smem;
   DG_REQUIRE(tile_kernel_supported(a) && plan(a, &g, &smem), "conv_fwd_tc: unsupported shape");
   const int ht = 16 + a.ks - 1;
+  const bool split = g.split != 0;
+  const int kmul = split ? 2 : 1;      // stored channels per logical input channel
+  const int opitch = split ? 2 * a.Cout : 0;  // split-half outputs / side inputs: [Cout hi | Cout lo] per pixel
   TcMaps tm;
-  DG_TRY(make_act_map(&tm.a0, a.in0, a.C0, a.W, a.H, a.N, g.kc, ht));
-  if (a.C1 > 0) DG_TRY(make_act_map(&tm.a1, a.in1, a.C1, a.W, a.H, a.N, g.kc, ht));
+  DG_TRY(make_act_map(&tm.a0, a.in0, kmul * a.C0, a.W, a.H, a.N, g.kc, ht));
+  if (a.C1 > 0) DG_TRY(make_act_map(&tm.a1, a.in1, kmul * a.C1, a.W, a.H, a.N, g.kc, ht));
   else tm.a1 = tm.a0;
-  DG_TRY(make_w_map(&tm.b, a.w_tc, a.C0 + a.C1, a.ks * a.ks * g.ncols_total, g.kc, g.ncta));
-  tm.out = tm.s0 = tm.s1 = tm.pool = tm.a0;  // placeholders for the maps this launch does not use
+  DG_TRY(make_w_map(&tm.b, a.w_tc, (split ? 3 : 1) * (a.C0 + a.C1), a.ks * a.ks * g.ncols_total, g.kc, g.ncta));
+  tm.out = tm.out2 = tm.s0 = tm.s1 = tm.pool = tm.a0;  // placeholders for the maps this launch does not use
   if (a.pool_out) DG_TRY(make_nhwc_map(&tm.pool, a.pool_out, a.Cout, a.W / 2, a.H / 2, a.N, g.ch, 8, 8, "pooled output"));
   if (a.out) {
-    if (a.deconv) DG_TRY(make_deconv_out_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch));
-    else DG_TRY(make_nhwc_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "output"));
+    const bf16* lo = reinterpret_cast<const bf16*>(a.out) + a.Cout;
+    if (a.deconv) {
+      DG_TRY(make_deconv_out_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch, opitch));
+      if (split) DG_TRY(make_deconv_out_map(&tm.out2, lo, a.Cout, a.W, a.H, a.N, g.ch, opitch));
+    } else {
+      DG_TRY(make_nhwc_map(&tm.out, a.out, a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "output", opitch));
+      if (split) DG_TRY(make_nhwc_map(&tm.out2, lo, a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "output (lo half)", opitch));
+    }
   }
   // side inputs of the epilogue: the FiLM residual, or the add source followed by the mask source
   const void* side[2] = {nullptr, nullptr};
@@ -253,14 +278,16 @@ int conv_fwd_tc(const ConvArgs& a, cudaStream_t st) {
     if (a.add_src) side[k++] = a.add_src;
     if (a.mask_src) side[k++] = a.mask_src;
   }
-  if (side[0]) DG_TRY(make_nhwc_map(&tm.s0, side[0], a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "side input"));
-  if (side[1]) DG_TRY(make_nhwc_map(&tm.s1, side[1], a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "side input"));
+  if (split && a.film_g) side[1] = reinterpret_cast<const bf16*>(a.res) + a.Cout;  // the residual's lo half
+  if (side[0]) DG_TRY(make_nhwc_map(&tm.s0, side[0], a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "side input", opitch));
+  if (side[1]) DG_TRY(make_nhwc_map(&tm.s1, side[1], a.Cout, a.W, a.H, a.N, g.ch, 16, 16, "side input", opitch));
   const int n_items = g.tiles_w * g.tiles_h * a.N * (g.ncols_total / g.ncta);
   const int grid = n_items < g_num_sms ? n_items : g_num_sms;
   // side inputs the epilogue has to stream (selects the EPI instantiation): 1 FiLM residual, 2 add / mask
   const int need = (a.film_g ? 1 : ((a.add_src || a.mask_src) ? 2 : (a.pool_out ? 4 : 0))) + (a.in_dt == DT_F16 ? 8 : 0);
   int rc;
-  switch (a.ks) {
+  if (split) rc = launch_split(grid, smem, st, tm, a, g, a.film_g ? 1 : 0);
+  else switch (a.ks) {
     case 1: rc = launch_ks1(grid, smem, st, tm, a, g, need); break;
     case 3: rc = launch_ks3(grid, smem, st, tm, a, g, need); break;
     case 5: rc = launch_ks5(grid, smem, st, tm, a, g, need); break;

@@ -43,6 +43,7 @@ namespace convtc {
 struct TcGeom {
   int tiles_w, tiles_h;
   int nchunk0, nchunk1;  // channel chunks taken from in0 / in1
+  int nchunk2, nchunk3;  // split-half storage: the hi halves of in0 / in1 once more (the x_hi * w_lo term); else 0
   int kc;                // channels per chunk
   int ncols_total;       // weight rows per tap (Cout, or 4*Cout for the transposed conv)
   int ncta;              // output columns per CTA
@@ -60,17 +61,22 @@ struct TcGeom {
   int stage_out;              // 1: `out` is written tile-wise from shared memory by TMA stores
   uint32_t slot_bytes;        // one staging tile: 256 pixels x ch x 2 bytes
   int pool;                   // 1: the 2x2 max-pooled tile is staged and stored as well (EPI bit 2)
+  int split;                  // 1: split-half storage (DT_F16S): K = 3*Cin, hi / lo staging tiles, two stores per chunk
 };
 
 // tensor maps of one launch: activations (two concatenated sources), weights, output, epilogue side inputs
 struct TcMaps {
   CUtensorMap a0, a1, b, out, s0, s1, pool;
+  CUtensorMap out2;  // split-half storage: the lo half of the output (out = the hi half)
 };
 
 // one launcher per kernel size, defined in conv_tc_k{1,3,5}.cu; epi = bit mask of the side inputs the call uses
 int launch_ks1(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi);
 int launch_ks3(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi);
 int launch_ks5(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi);
+// split-half storage (conv_tc_split.cu): 1x1 plain (the transposed conv) and 3x3 plain / FiLM
+int launch_split(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g, int epi);
+int set_attrs_split();
 int set_attrs_ks1();
 int set_attrs_ks3();
 int set_attrs_ks5();
@@ -318,7 +324,10 @@ __device__ __forceinline__ bool elect_one() {
 // ---------------------------------------------------------------------------------------------------------
 // F16: the 16-bit storage format of activations and weights is IEEE half instead of bfloat16 (generator inference handles,
 // DEPGAN_PREC_F16); a template parameter, because a run-time flag doubles the pack / unpack instructions of the epilogue.
-template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false>
+// SPLIT (implies F16): split-half storage, see DT_F16S in common.cuh.  The K loop runs over [in0 hi|lo], [in1 hi|lo],
+// [in0 hi], [in1 hi] against weight rows packed in that order; the epilogue stages hi = half(v) and lo = half(v - hi) as
+// two tiles and stores them to the two channel halves of the output pixel; the FiLM residual arrives as a hi and a lo tile.
+template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false, bool SPLIT = false>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcMaps tm, const ConvArgs a,
                                                                 const TcGeom g) {
   constexpr int PAD = KS / 2, HT = 16 + KS - 1, TAPS = KS * KS;
@@ -329,7 +338,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + g.na * g.a_bytes;
   const uint32_t o_base = b_base + g.nb * g.b_tps * g.b_bytes;             // 2 output staging slots
-  const uint32_t p_base = o_base + (g.stage_out ? 2u * g.slot_bytes : 0u);  // 2 pooled staging slots (64 pixels)
+  const uint32_t p_base = o_base + (g.stage_out ? (SPLIT ? 4u : 2u) * g.slot_bytes : 0u);  // 2 pooled staging slots (64 pixels)
   const uint32_t s_base = p_base + (g.pool ? g.slot_bytes / 2u : 0u);       // 2 side stages x n_side slots
   const uint32_t bar_base = s_base + 2u * g.n_side * g.slot_bytes;
   const uint32_t fullA = bar_base, emptyA = fullA + 8 * g.na;
@@ -348,7 +357,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   // warp index made provably warp-uniform so the role loops run on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int rowb = KSTEPS * 32;  // bytes per pixel row of a chunk = one swizzle span (kc = 16*KSTEPS)
-  const int nchunks = g.nchunk0 + g.nchunk1;
+  const int nchunks = g.nchunk0 + g.nchunk1 + g.nchunk2 + g.nchunk3;
   const int nsplit = g.ncols_total / g.ncta;
   const int tiles_per_img = g.tiles_w * g.tiles_h;
   const int n_items = tiles_per_img * a.N * nsplit;
@@ -402,7 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (elect_one()) {
         mbar_expect_tx(fullB, g.b_tx * TAPS * nchunks);
         for (int c = 0; c < nchunks; ++c) {
-          const int kglob = c < g.nchunk0 ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
+          const int kglob = c * g.kc;  // weight rows are packed in chunk order
           for (int tap = 0; tap < TAPS; ++tap)
             tma_load_2d(b_base + (c * TAPS + tap) * g.b_bytes, &tm.b, fullB, kglob, tap * g.ncols_total);
         }
@@ -420,17 +429,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(emptyA + 8 * ra.idx, ra.phase ^ 1u);
         if (c == 0) DG_TRACE(0, p_it, 1);
-        const bool first = c < g.nchunk0;
+        // chunk -> (source, channel offset): in0, in1, then (split-half storage) the hi halves of in0 and in1 again
+        int cs = c;
+        bool first = true;
+        if (cs >= g.nchunk0) {
+          cs -= g.nchunk0; first = false;
+          if (cs >= g.nchunk1) {
+            cs -= g.nchunk1; first = true;
+            if (cs >= g.nchunk2) { cs -= g.nchunk2; first = false; }
+          }
+        }
         if (elect_one()) {
           mbar_expect_tx(fullA + 8 * ra.idx, g.a_tx);
-          tma_load_4d(a_base + ra.idx * g.a_bytes, first ? &tm.a0 : &tm.a1, fullA + 8 * ra.idx,
-                      (first ? c : c - g.nchunk0) * g.kc, w0 - PAD, h0 - PAD, n);
+          tma_load_4d(a_base + ra.idx * g.a_bytes, first ? &tm.a0 : &tm.a1, fullA + 8 * ra.idx, cs * g.kc, w0 - PAD,
+                      h0 - PAD, n);
         }
         __syncwarp();
         ra.advance(g.na);
         if (!RES) {
           // weight ring: one stage = b_tps consecutive taps of this channel chunk (all taps, one kernel row, or one tap)
-          const int kglob = first ? c * g.kc : a.C0 + (c - g.nchunk0) * g.kc;
+          const int kglob = c * g.kc;
           for (int tap = 0; tap < TAPS; tap += g.b_tps) {
             mbar_wait(emptyB + 8 * rb.idx, rb.phase ^ 1u);
             if (elect_one()) {
@@ -672,6 +690,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           rs16.q[1] = *reinterpret_cast<const uint4*>(sgen + u1);
           float rsv[16];
           rs16.unpack(rsv, f16);
+          if (SPLIT) {  // residual = hi + lo (second side slot)
+            Packed16 rl16;
+            rl16.q[0] = *reinterpret_cast<const uint4*>(sgen + g.slot_bytes + u0);
+            rl16.q[1] = *reinterpret_cast<const uint4*>(sgen + g.slot_bytes + u1);
+            float rlv[16];
+            rl16.unpack(rlv, true);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) rsv[i] += rlv[i];
+          }
 #pragma unroll
           for (int i4 = 0; i4 < 4; ++i4) {
             const float4 sc = reinterpret_cast<const float4*>(sF + gi * 16)[i4];
@@ -720,9 +747,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           uint32_t* hp = reinterpret_cast<uint32_t*>(pk);
 #pragma unroll
           for (int i = 0; i < 8; ++i) hp[i] = pack_h2(v[2 * i], v[2 * i + 1], f16);
-          uint8_t* ogen = smem_raw + (o_base + oslot * g.slot_bytes - raw);
+          uint8_t* ogen = smem_raw + (o_base + (SPLIT ? 2u * oslot : oslot) * g.slot_bytes - raw);
           *reinterpret_cast<uint4*>(ogen + u0) = pk[0];
           *reinterpret_cast<uint4*>(ogen + u1) = pk[1];
+          if (SPLIT) {  // lo = half(v - hi) into the slot after the hi tile
+            uint4 pl[2];
+            uint32_t* lp = reinterpret_cast<uint32_t*>(pl);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 hf = unpack_h2(hp[i], true);
+              lp[i] = pack_h2(v[2 * i] - hf.x, v[2 * i + 1] - hf.y, true);
+            }
+            *reinterpret_cast<uint4*>(ogen + g.slot_bytes + u0) = pl[0];
+            *reinterpret_cast<uint4*>(ogen + g.slot_bytes + u1) = pl[1];
+          }
           if (E_POOL) {
             // 2x2 max-pool on the packed bf16 pairs (the rounding is monotonic, so this equals pooling the stored
             // tensor): the window's pixels are lanes l, l^1 (column) and l^8 (row); the even/even lane stages it
@@ -780,9 +818,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (ew == 0 && gi == ng - 1) DG_TRACE(2, k_it, 6);
             if (t0) {
-              const uint32_t src = o_base + oslot * g.slot_bytes;
+              const uint32_t src = o_base + (SPLIT ? 2u * oslot : oslot) * g.slot_bytes;
               if (a.deconv) tma_store_5d(&tm.out, src, c0, c1, cur.tw * 16, c3, cur.n * a.H + cur.th * 16);
               else tma_store_4d(&tm.out, src, c0, cur.tw * 16, cur.th * 16, cur.n);
+              if (SPLIT) {
+                if (a.deconv) tma_store_5d(&tm.out2, src + g.slot_bytes, c0, c1, cur.tw * 16, c3, cur.n * a.H + cur.th * 16);
+                else tma_store_4d(&tm.out2, src + g.slot_bytes, c0, cur.tw * 16, cur.th * 16, cur.n);
+              }
               if (E_POOL)
                 tma_store_4d(&tm.pool, p_base + oslot * (g.slot_bytes / 4u), c0, cur.tw * 8, cur.th * 8, cur.n);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -870,15 +912,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 }
 
 // ---- instantiation helpers used by conv_tc_k{1,3,5}.cu ----
-template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false>
+template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false, bool SPLIT = false>
 int launch_one(int grid, uint32_t smem, cudaStream_t st, const TcMaps& tm, const ConvArgs& a, const TcGeom& g) {
-  DG_CHECK_CUDA(dg_launch_pdl(conv_tc_kernel<KS, KSTEPS, RES, EPI, F16>, dim3(grid), dim3(TC_THREADS), smem, st, tm, a, g));
+  DG_CHECK_CUDA(dg_launch_pdl(conv_tc_kernel<KS, KSTEPS, RES, EPI, F16, SPLIT>, dim3(grid), dim3(TC_THREADS), smem, st, tm, a, g));
   DG_LAUNCH_CHECK();
   return 0;
 }
-template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false>
+template <int KS, int KSTEPS, bool RES, int EPI, bool F16 = false, bool SPLIT = false>
 int set_attr_one() {
-  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, KSTEPS, RES, EPI, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<KS, KSTEPS, RES, EPI, F16, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024 - DG_TRACE_SMEM));
   return 0;
 }
@@ -913,6 +955,21 @@ int set_attr_one() {
   DG_TRY((set_attr_one<KS_, 2, true, EPI_, true>()));       \
   DG_TRY((set_attr_one<KS_, 4, false, EPI_, true>()));      \
   DG_TRY((set_attr_one<KS_, 4, true, EPI_, true>()));
+// split-half storage instantiations (conv_tc_split.cu): key = ks * 1000 + epi * 100 + (kc/16)*10 + resident
+#define DG_TC_CASES_SPLIT(KS_, EPI_)                                                                                 \
+  case KS_ * 1000 + EPI_ * 100 + 10: return launch_one<KS_, 1, false, EPI_, true, true>(grid, smem, st, tm, a, g);   \
+  case KS_ * 1000 + EPI_ * 100 + 11: return launch_one<KS_, 1, true, EPI_, true, true>(grid, smem, st, tm, a, g);    \
+  case KS_ * 1000 + EPI_ * 100 + 20: return launch_one<KS_, 2, false, EPI_, true, true>(grid, smem, st, tm, a, g);   \
+  case KS_ * 1000 + EPI_ * 100 + 21: return launch_one<KS_, 2, true, EPI_, true, true>(grid, smem, st, tm, a, g);    \
+  case KS_ * 1000 + EPI_ * 100 + 40: return launch_one<KS_, 4, false, EPI_, true, true>(grid, smem, st, tm, a, g);   \
+  case KS_ * 1000 + EPI_ * 100 + 41: return launch_one<KS_, 4, true, EPI_, true, true>(grid, smem, st, tm, a, g);
+#define DG_TC_ATTRS_SPLIT(KS_, EPI_)                              \
+  DG_TRY((set_attr_one<KS_, 1, false, EPI_, true, true>()));      \
+  DG_TRY((set_attr_one<KS_, 1, true, EPI_, true, true>()));       \
+  DG_TRY((set_attr_one<KS_, 2, false, EPI_, true, true>()));      \
+  DG_TRY((set_attr_one<KS_, 2, true, EPI_, true, true>()));       \
+  DG_TRY((set_attr_one<KS_, 4, false, EPI_, true, true>()));      \
+  DG_TRY((set_attr_one<KS_, 4, true, EPI_, true, true>()));
 #endif  // __CUDACC__
 
 }  // namespace convtc

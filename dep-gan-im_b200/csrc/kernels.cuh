@@ -64,6 +64,12 @@ int k_adam(float* p, const float* g, float* m, float* v, long long n, float lr_t
            float gscale, cudaStream_t st);
 
 int k_cast_narrow(const float* src, void* dst, long long n, int to_f16, cudaStream_t st);
+// ---- split-half storage (DT_F16S: per pixel [C hi | C lo] IEEE halves, v = hi + lo) -------------------------------
+// tcgen05 B operand of a split-half layer: dst[row][3*Cin] with row = tap*Cout + co, columns in the kernel's K order
+// [hi(0:c0), hi(0:c0), hi(c0:Cin), hi(c0:Cin), lo(0:c0), lo(c0:Cin)] (c0 = channels of the first input tensor).
+// src: Keras HWIO [tap][ci][co], or (kmajor = 1, the transposed conv) [tap][co][ci].
+int k_pack_split_weights(const float* src, bf16* dst, int taps, int Cin, int Cout, int c0, int kmajor, cudaStream_t st);
+int k_split_to_f32(const void* src, float* dst, long long npix, int C, cudaStream_t st);
 int k_copy_to_f32(const void* src, float* dst, long long n, int dt, cudaStream_t st);
 
 // ---- backward / loss kernels (kernels_bwd.cu) ------------------------------------------------------------

@@ -94,6 +94,71 @@ __global__ void prep_pack_all_kernel(const PrepTable t) {
   }
 }
 
+// ---- split-half storage (DT_F16S) ----
+__device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  lo = __float2half_rn(v - __half2float(hi));
+}
+__global__ void pack_split_kernel(const float* src, __half* dst, int taps, int Cin, int Cout, int c0, int kmajor) {
+  const size_t total = (size_t)taps * Cin * Cout;
+  const int c1 = Cin - c0, K = 3 * Cin;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int co, ci, tap;
+    if (kmajor) { ci = i % Cin; co = (i / Cin) % Cout; tap = i / ((size_t)Cout * Cin); }
+    else { co = i % Cout; ci = (i / Cout) % Cin; tap = i / ((size_t)Cout * Cin); }
+    __half hi, lo;
+    split_h(src[i], hi, lo);
+    __half* row = dst + ((size_t)tap * Cout + co) * K;
+    if (ci < c0) {
+      row[ci] = hi; row[c0 + ci] = hi; row[2 * Cin + ci] = lo;
+    } else {
+      const int cj = ci - c0;
+      row[2 * c0 + cj] = hi; row[2 * c0 + c1 + cj] = hi; row[2 * Cin + ci] = lo;
+    }
+  }
+}
+// 2x2 max-pool of (hi, lo) pairs, 8 channels per thread.  hi = half(v) is monotonic in v, so the window's maximum is the
+// pair with the largest hi and, among equal hi, the largest lo.
+__global__ void maxpool_fwd_split_kernel(const uint4* in, uint4* out, int N, int H, int W, int C8) {
+  const int Ho = H / 2, Wo = W / 2;
+  const size_t total = (size_t)N * Ho * Wo * C8;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % C8;
+    const size_t p = i / C8;
+    const int wo = p % Wo, ho = (p / Wo) % Ho;
+    const size_t n = p / ((size_t)Wo * Ho);
+    // a pixel = 2*C8 vectors: C8 of hi, then C8 of lo
+    const uint4* b = in + (((size_t)n * H + 2 * ho) * W + 2 * wo) * (2 * C8) + c;
+    const size_t offs[4] = {0, (size_t)2 * C8, (size_t)W * 2 * C8, (size_t)W * 2 * C8 + 2 * C8};
+    uint4 bh = __ldg(b), bl = __ldg(b + C8);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const uint4 qh = __ldg(b + offs[k]), ql = __ldg(b + offs[k] + C8);
+      __half* rh = reinterpret_cast<__half*>(&bh);
+      __half* rl = reinterpret_cast<__half*>(&bl);
+      const __half* xh = reinterpret_cast<const __half*>(&qh);
+      const __half* xl = reinterpret_cast<const __half*>(&ql);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = __half2float(rh[j]), bq = __half2float(xh[j]);
+        const bool take = bq > a || (bq == a && __half2float(xl[j]) > __half2float(rl[j]));
+        if (take) { rh[j] = xh[j]; rl[j] = xl[j]; }
+      }
+    }
+    uint4* o = out + p * (2 * C8) + c;
+    o[0] = bh;
+    o[C8] = bl;
+  }
+}
+__global__ void split_to_f32_kernel(const __half* src, float* dst, long long npix, int C) {
+  const long long total = npix * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const int c = (int)(i - p * C);
+    dst[i] = __half2float(src[p * 2 * C + c]) + __half2float(src[p * 2 * C + C + c]);
+  }
+}
+
 template <typename T>
 __global__ void maxpool_fwd_kernel(const T* in, T* out, int N, int H, int W, int C) {
   const int Ho = H / 2, Wo = W / 2;
@@ -481,6 +546,19 @@ int k_pack_conv_weights(const float* src, const float* scale, bf16* dst_tc, floa
   return 0;
 }
 
+int k_pack_split_weights(const float* src, bf16* dst, int taps, int Cin, int Cout, int c0, int kmajor, cudaStream_t st) {
+  pack_split_kernel<<<grid_for((long long)taps * Cin * Cout), 256, 0, st>>>(src, reinterpret_cast<__half*>(dst), taps, Cin,
+                                                                            Cout, c0, kmajor);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+int k_split_to_f32(const void* src, float* dst, long long npix, int C, cudaStream_t st) {
+  if (npix * C == 0) return 0;
+  split_to_f32_kernel<<<grid_for(npix * C), 256, 0, st>>>((const __half*)src, dst, npix, C);
+  DG_LAUNCH_CHECK();
+  return 0;
+}
+
 int k_prepare_convs(const PrepTable& t, cudaStream_t st) {
   if (t.n <= 0) return 0;
   prep_fold_all_kernel<<<t.n, 256, 0, st>>>(t);
@@ -493,7 +571,11 @@ int k_prepare_convs(const PrepTable& t, cudaStream_t st) {
 int k_maxpool_fwd(const void* in, void* out, int N, int H, int W, int C, int dt, cudaStream_t st) {
   long long total = (long long)N * (H / 2) * (W / 2) * C;
   if (total == 0) return 0;
-  if (dt == DT_F32)
+  if (dt == DT_F16S) {
+    DG_REQUIRE(C % 8 == 0, "maxpool (split-half storage): C must be a multiple of 8");
+    maxpool_fwd_split_kernel<<<grid_for(total / 8, 256, 148 * 32), 256, 0, st>>>((const uint4*)in, (uint4*)out, N, H, W,
+                                                                                  C / 8);
+  } else if (dt == DT_F32)
     maxpool_fwd_kernel<float><<<grid_for(total), 256, 0, st>>>((const float*)in, (float*)out, N, H, W, C);
   else if (C % 8 == 0 && dt == DT_F16)
     maxpool_fwd_bf16x8_kernel<__half2><<<grid_for(total / 8, 256, 148 * 32), 256, 0, st>>>((const uint4*)in, (uint4*)out,
@@ -625,6 +707,8 @@ int k_copy_to_f32(const void* src, float* dst, long long n, int dt, cudaStream_t
   if (n == 0) return 0;
   if (dt == DT_F32)
     copy_to_f32_kernel<float><<<grid_for(n), 256, 0, st>>>((const float*)src, dst, n);
+  else if (dt == DT_F16)
+    copy_to_f32_kernel<__half><<<grid_for(n), 256, 0, st>>>((const __half*)src, dst, n);
   else
     copy_to_f32_kernel<bf16><<<grid_for(n), 256, 0, st>>>((const bf16*)src, dst, n);
   DG_LAUNCH_CHECK();

@@ -115,9 +115,12 @@ int check_cfg(int model, const depgan_cfg* cfg) {
   DG_REQUIRE(cfg->H >= 16 && cfg->W >= 16 && cfg->H % 16 == 0 && cfg->W % 16 == 0, "H, W must be multiples of 16");
   DG_REQUIRE(cfg->max_batch >= 1, "max_batch must be >= 1");
   DG_REQUIRE(cfg->precision == DEPGAN_PREC_FP32 || cfg->precision == DEPGAN_PREC_BF16 ||
-                 cfg->precision == DEPGAN_PREC_F16, "unknown precision");
+                 cfg->precision == DEPGAN_PREC_F16 || cfg->precision == DEPGAN_PREC_F16X3, "unknown precision");
   DG_REQUIRE(cfg->precision != DEPGAN_PREC_F16 || (model == DEPGAN_MODEL_GEN && cfg->training == 0),
              "DEPGAN_PREC_F16 is the inference format of the generator (training handles keep the bf16 range)");
+  DG_REQUIRE(cfg->precision != DEPGAN_PREC_F16X3 ||
+                 (model == DEPGAN_MODEL_GEN && cfg->training == 0 && cfg->H % 128 == 0 && cfg->W % 128 == 0),
+             "DEPGAN_PREC_F16X3 is an inference format of the generator; H and W must be multiples of 128");
   if (model == DEPGAN_MODEL_GEN) {
     DG_REQUIRE(cfg->nicg >= 1 && cfg->nicg <= 8, "nicg must be 1..8");
     DG_REQUIRE(cfg->nc_out >= 1 && cfg->nc_out <= 4, "nc_out must be 1..4");
@@ -153,7 +156,8 @@ void alloc_conv_derived(depgan_net* h, ConvL& L, Bump& b) {
   L.scale = b.arr<float>(L.cout);
   L.shift = b.arr<float>(L.cout);
   const size_t nw = (size_t)L.taps() * L.cin * L.cout;
-  if (dt_is_half(h->act_dt)) L.w_tc = b.arr<bf16>(nw);  // 16-bit slots: bf16, or IEEE half for DT_F16 handles
+  // 16-bit slots: bf16, or IEEE half for DT_F16 handles; split-half handles keep K = 3*Cin rows (hi, hi, lo)
+  if (dt_is_tc(h->act_dt)) L.w_tc = b.arr<bf16>(nw * (h->act_dt == DT_F16S ? 3 : 1));
   if (h->cfg.training) {
     L.inv_std = b.arr<float>(L.cout);
     L.w_dg = b.arr<float>(nw);
@@ -183,6 +187,7 @@ int layout_net(depgan_net* h, Bump& b) {
       for (int j = 0; j < 3; ++j) {
         ConvL& L = *Ls[j];
         L.name = names[j]; L.ks = 3; L.cin = cins[j]; L.cout = w; L.lvl = lvl;
+        if (j == 0 && bi >= 4) L.split_c0 = cin - skip_c[6 - bi];  // [deconv_out, skip]
         bind_conv(h, L, std::string("conv2d_") + names[j], std::string("bn_") + names[j]);
         alloc_conv_derived(h, L, b);
       }
@@ -255,6 +260,10 @@ int layout_net(depgan_net* h, Bump& b) {
 int fold_conv(depgan_net* h, ConvL& L, cudaStream_t st) {
   DG_TRY(k_fold_bn(h->P(L.b_off), h->P(L.g_off), h->P(L.be_off), h->P(L.mu_off), h->P(L.var_off), L.scale, L.shift,
                    L.inv_std, L.cout, st));
+  if (h->act_dt == DT_F16S) {  // inference only: no dgrad operands
+    const int c0 = L.split_c0 ? L.split_c0 : L.cin;
+    return k_pack_split_weights(h->P(L.k_off), L.w_tc, L.taps(), L.cin, L.cout, c0, L.deconv ? 1 : 0, st);
+  }
   if (L.deconv) {
     if (L.w_tc) DG_TRY(k_convert_in(h->P(L.k_off), L.w_tc, (long long)4 * L.cin * L.cout, h->act_dt, st));
     DG_TRY(k_pack_deconv_dgrad(h->P(L.k_off), h->cfg.training == 2 ? nullptr : L.scale, L.w_dg, L.w_dg_tc, L.cin,
@@ -323,13 +332,13 @@ int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void*
   a.shift = L.shift;
   a.N = n; a.H = h->lvl_h(L.lvl); a.W = h->lvl_w(L.lvl); a.Cout = L.cout; a.ks = L.ks;
   a.in_dt = in_dt; a.out_dt = h->act_dt;
-  if (a.pool_out && !(dt_is_half(h->act_dt) && conv_tc_supported(a))) {  // unfused fallback: conv, then the pool
+  if (a.pool_out && !(dt_is_tc(h->act_dt) && conv_tc_supported(a))) {  // unfused fallback: conv, then the pool
     void* pool_out = a.pool_out;
     a.pool_out = nullptr;
     DG_TRY(net_conv(h, L, in0, C0, in1, C1, in_dt, a, n, st));
     return k_maxpool_fwd(a.out, pool_out, n, a.H, a.W, a.Cout, h->act_dt, st);
   }
-  const bool tc = dt_is_half(h->act_dt) && conv_tc_supported(a);
+  const bool tc = dt_is_tc(h->act_dt) && conv_tc_supported(a);
   ProfScope prof(a, tc, st);
   if (tc) return conv_fwd_tc(a, st);
   if (a.head_w) {  // unfused fallback: conv, then the 1x1 head
@@ -344,7 +353,7 @@ int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void*
 
 static int net_deconv(depgan_net* h, const ConvL& L, const void* in, void* out, int n, cudaStream_t st) {
   const int H = h->lvl_h(L.lvl), W = h->lvl_w(L.lvl);
-  if (dt_is_half(h->act_dt)) {
+  if (dt_is_tc(h->act_dt)) {
     ConvArgs a{};
     a.in0 = in; a.C0 = L.cin; a.w_tc = L.w_tc; a.scale = L.scale; a.shift = L.shift; a.out = out; a.relu = 1;
     a.deconv = 1; a.N = n; a.H = H; a.W = W; a.Cout = L.cout; a.ks = 1; a.in_dt = h->act_dt; a.out_dt = h->act_dt;
@@ -390,7 +399,7 @@ int gen_forward_impl(depgan_net* g, const float* x, const float* z, float* out, 
     if (bi == 6) {                                                       // + gen_segmentation 1x1 + tanh/softmax
       e.head_w = g->P(g->g_seg.k_off); e.head_b = g->P(g->g_seg.b_off); e.head_out = out;
       e.head_nc = c.nc_out; e.head_act = c.nc_out == 1 ? 0 : 1;
-      if (!keep && dt_is_half(g->act_dt)) e.out = nullptr;                // inference: gen_17 never leaves the SM
+      if (!keep && dt_is_tc(g->act_dt)) e.out = nullptr;                // inference: gen_17 never leaves the SM
     }
     // MaxPooling2D (TG:409): fused into the epilogue of the block's last conv for training handles (the per-launch
     // profile counts those launches as their own class, 6, with the pooled bytes included).  Inference handles keep
@@ -469,7 +478,7 @@ long long depgan_workspace_bytes(int model, const depgan_cfg* cfg) {
   if (check_cfg(model, cfg)) return -2;
   depgan_net h;
   h.model = model; h.cfg = *cfg; h.man = build_manifest(model, *cfg);
-  h.act_dt = cfg->precision == DEPGAN_PREC_BF16 ? DT_BF16 : cfg->precision == DEPGAN_PREC_F16 ? DT_F16 : DT_F32;
+  h.act_dt = act_dt_of(cfg->precision);
   h.es = dt_size(h.act_dt);
   Bump b;
   if (layout_net(&h, b)) return -2;
@@ -489,7 +498,7 @@ depgan_net* depgan_net_create(int model, const depgan_cfg* cfg, float* params_de
   depgan_net* h = new depgan_net();
   h->model = model; h->cfg = *cfg; h->man = build_manifest(model, *cfg);
   h->params = params_dev; h->grads = grads_dev;
-  h->act_dt = cfg->precision == DEPGAN_PREC_BF16 ? DT_BF16 : cfg->precision == DEPGAN_PREC_F16 ? DT_F16 : DT_F32;
+  h->act_dt = act_dt_of(cfg->precision);
   h->es = dt_size(h->act_dt);
   Bump b;
   b.base = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(workspace_dev) + 255) & ~uintptr_t(255));
@@ -499,7 +508,7 @@ depgan_net* depgan_net_create(int model, const depgan_cfg* cfg, float* params_de
     delete h;
     return nullptr;
   }
-  if (dt_is_half(h->act_dt) && conv_tc_init()) { delete h; return nullptr; }
+  if (dt_is_tc(h->act_dt) && conv_tc_init()) { delete h; return nullptr; }
   return h;
 }
 
@@ -635,11 +644,13 @@ int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, lon
   DG_REQUIRE(h && name, "debug_activation: bad arguments");
   const void* src = nullptr;
   long long cnt = 0;
+  int ch = 1;  // channels of the activation found
   std::string nm(name);
   if (h->model == DEPGAN_MODEL_GEN) {
     for (int bi = 0; bi < 7 && !src; ++bi) {
       const long long px = (long long)n * h->lvl_h(GEN_LVL[bi]) * h->lvl_w(GEN_LVL[bi]);
       const int w = FIRST_FM * GEN_MULT[bi];
+      ch = w;
       if (nm == GEN_IN[bi]) { src = h->act_a[bi]; cnt = px * w; }
       else if (nm == GEN_NOISE[bi]) { src = h->act_r[bi]; cnt = px * w; }
       else if (nm == GEN_OUT[bi]) { src = h->act_o[bi]; cnt = px * w; }
@@ -662,6 +673,7 @@ int depgan_debug_activation(depgan_net* h, const char* name, float* out_dev, lon
   DG_REQUIRE(src != nullptr, "debug_activation: unknown activation name");
   DG_REQUIRE(cnt <= cap_floats, "debug_activation: buffer too small");
   if (n_floats) *n_floats = cnt;
+  if (h->act_dt == DT_F16S) return k_split_to_f32(src, out_dev, cnt / ch, ch, (cudaStream_t)stream);
   return k_copy_to_f32(src, out_dev, cnt, h->act_dt, (cudaStream_t)stream);
 }
 

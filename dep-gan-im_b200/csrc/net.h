@@ -42,6 +42,7 @@ struct ConvL {
   float* w_dg = nullptr;     // dgrad weights for the SIMT path  [taps][cout][cin] * scale[cout], taps flipped
   bf16* w_dg_tc = nullptr;   // dgrad weights for the tcgen05 path [taps][cin][cout] * scale[cout], taps flipped
   float* w_lin = nullptr;    // critic JVP: same as kernel (alias into params)
+  int split_c0 = 0;          // split-half handles: channels of the first input of a two-source layer (0: one source)
   int taps() const { return deconv ? 4 : ks * ks; }
 };
 
@@ -171,6 +172,10 @@ struct ProfScope {
   ~ProfScope();
 };
 
+inline int act_dt_of(int precision) {
+  return precision == DEPGAN_PREC_BF16 ? DT_BF16 : precision == DEPGAN_PREC_F16 ? DT_F16
+         : precision == DEPGAN_PREC_F16X3 ? DT_F16S : DT_F32;
+}
 int net_conv(depgan_net* h, const ConvL& L, const void* in0, int C0, const void* in1, int C1, int in_dt, ConvArgs extra,
              int n, cudaStream_t st);
 int gen_forward_impl(depgan_net* g, const float* x, const float* z, float* out, int n, bool keep, cudaStream_t st);

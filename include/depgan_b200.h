@@ -27,6 +27,10 @@ extern "C" {
 #define DEPGAN_PREC_BF16 1 /* bf16 activations, tcgen05/TMEM implicit GEMM, fp32 accumulate (<=1e-2) */
 #define DEPGAN_PREC_F16 2  /* IEEE-half activations and weights, same tcgen05 kernels and rate (kind::f16), fp32 accumulate:
                               generator inference handles only (training == 0); DEM error ~7x below the bf16 path */
+#define DEPGAN_PREC_F16X3 3 /* the tensor-core <= 1e-4 variant: activations and weights as (hi, lo) IEEE-half pairs, every
+                               convolution as the three tcgen05 products x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with fp32 accumulate
+                               (22 significant bits per stored value); generator inference handles only, H and W multiples
+                               of 128 */
 
 #define DEPGAN_HEAD_TANH 0    /* DEP-GAN generator TG:494-495 */
 #define DEPGAN_HEAD_SOFTMAX 1 /* DEP-UResNet TU:423-424 */
