@@ -98,8 +98,10 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   int ch = ncta % 32 == 0 ? 32 : 16;
   if (a.deconv) ch = (a.Cout % 64 == 0 && ncta % 64 == 0) ? 64 : (a.Cout % 32 == 0 && ncta % 32 == 0) ? 32 : 16;
   const bool split = a.in_dt == DT_F16S;  // hi / lo tiles everywhere: K = 3*Cin, two staging tiles and residual tiles
-  if (split) {  // measurement switch: staging chunk width of the split-half layers (the hi + lo tiles double the staging)
-    static const int split_ch = getenv("DEPGAN_SPLIT_CH") ? atoi(getenv("DEPGAN_SPLIT_CH")) : 0;
+  if (split) {
+    // the hi + lo tiles double the staging and residual slots: 16-channel chunks leave room for more activation stages
+    // (measured at batch 64: 10.1 k slices/s against 9.2 k with 32-channel chunks; DEPGAN_SPLIT_CH = 32 / 64 to compare)
+    static const int split_ch = getenv("DEPGAN_SPLIT_CH") ? atoi(getenv("DEPGAN_SPLIT_CH")) : 16;
     if ((split_ch == 16 || split_ch == 32 || split_ch == 64) && ncta % split_ch == 0 && (!a.deconv || a.Cout % split_ch == 0))
       ch = split_ch;
   }
