@@ -1,11 +1,15 @@
 """CPU ORACLE (test infrastructure, NOT product code) for the DEP-GAN / DEP-UResNet hot path.
 
-PARITY UNPINNED: the reference (febrianrachmadi/dep-gan-im) is four Python-2 / Keras-2 / TF-1 scripts that
-cannot run in this environment (no tensorflow/keras/h5py, weights and data absent) and ships no tests, golden
-vectors or fixtures.  This file is therefore a *restatement* of the reference's
-arithmetic on torch-CPU (fp64 for truth, fp32 for the timed CPU baseline).  It is cross-checked by an
-independent naive NumPy forward (oracle/naive_numpy.py), by finite differences of the three loss graphs
-(tests/test_oracle.py) and by the parameter-count identities of SURVEY.md section 2a.
+PARITY: pinned to the reference's own source, EXECUTED.  The reference (febrianrachmadi/dep-gan-im) is four Python-2 /
+Keras-2 / TF-1 scripts that cannot be imported in this environment (no tensorflow / keras / h5py; weights and data
+absent) and ships no tests or golden vectors.  tests/golden/make_reference_vectors.py therefore cuts the hot path out of
+the scripts under /root/reference by anchor lines (networks TG:255-498, loss / optimizer graph construction TG:513-598,
+the testing scripts' evaluation blocks, the training loop) and exec's it unmodified on oracle/keras_shim.py, a torch-fp64
+stand-in for the few Keras calls those lines make; tests/test_reference_vectors.py holds this file to the resulting
+vectors (manifest order, forwards 1e-9, step functions + gradients + Adam updates 1e-8, post-processing exact).  What is
+still restated rather than executed: the Keras layers' own arithmetic (inside the shim) and the Keras training phase of
+the DEP-UResNet fit.  Further guards: an independent naive NumPy forward (oracle/naive_numpy.py), finite differences of
+the three loss graphs (tests/test_oracle.py) and the parameter-count identities of SURVEY.md section 2a.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this
 module.  The product (depgan_b200) never does.

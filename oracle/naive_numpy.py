@@ -1,6 +1,6 @@
 """Independent naive NumPy forward of Gen_UNet2D / Dis_C2D_FCN1 (test infrastructure, NOT product code).
 
-Purpose: the torch restatement in depgan_oracle.py is itself unpinned (the reference cannot run here), so this
+Purpose: the torch restatement in depgan_oracle.py restates the Keras layers' arithmetic (the reference cannot run here), so this
 file re-derives the same forward passes from the Keras layer definitions with explicit shifted-sum
 convolutions in NHWC and no torch.  It shares *no code* with depgan_oracle.py beyond the layer-name tables.
 Only usable on small H, W (pure NumPy).  Citations as in depgan_oracle.py (TG:255-498).

@@ -1,7 +1,7 @@
 """Regenerates the committed golden fixtures (run from the repo root: python tests/golden/make_golden.py).
 
 The reference (Keras/TF-1, Python 2) cannot be imported or run in this environment and ships no golden vectors
-(parity unpinned), so these fixtures pin (a) the oracle restatement itself against silent drift,
+(the vectors made from its executed source are reference_vectors.npz, make_reference_vectors.py); these fixtures pin (a) the oracle restatement itself against silent drift,
 (b) the byte layout of the HDF5 writer, (c) hand-derived known answers of the DEM post-processing.
 """
 import sys

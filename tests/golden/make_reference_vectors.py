@@ -224,9 +224,81 @@ def testing_blocks(out):
     out["EU_eval/row"] = np.array([float(v) for v in env["vol_dsc"]])
 
 
+class _Rec:
+    """Stand-ins for the step functions, the networks and the logger while the reference's training loop runs."""
+
+    def __init__(self, env):
+        self.ev, self.env, self.n_eval = [], env, 0
+
+    def first_id(self, real_1tp):   # batch index of a mini-batch inside the (shuffled) training array of the moment
+        pos = int(np.where(self.env["prob_flair_1tp_train"].ravel() == real_1tp.ravel()[0])[0][0])
+        return pos // self.env["batchSize"]
+
+    def critic(self, kind):
+        def f(inputs):
+            real_2tp, real_1tp, noise, ep = inputs
+            assert noise.shape == (self.env["batchSize"], self.env["noiseSize"], 1) and ep.shape == (self.env["batchSize"], 1, 1, 1)
+            self.ev.append([kind, self.first_id(real_1tp)])
+            return 0.25, 0.75
+        return f
+
+    def no_update(self, inputs):
+        self.n_eval += 1
+        self.last_eval = self.first_id(inputs[0])
+        return [float(self.n_eval % 7)] + [0.0] * 5
+
+    def train(self, inputs):
+        assert self.n_eval == 10 and self.last_eval == self.first_id(inputs[0])   # k_noise evaluations on the same batch
+        self.n_eval = 0
+        self.ev.append(["gen", self.first_id(inputs[0]), int(self.env["gen_iterations"])])
+        return [1.0, 2.0, 3.0, 4.0, 5.0, 6.0]
+
+    # logger
+    def log_scalar(self, tag, value, step): self.ev.append(["log", tag, int(step)])
+    def log_images(self, tag, images, step, *a): self.ev.append(["img", tag, int(step)])
+    # networks
+    def predict(self, x, **kw): return np.zeros((1,), np.float32)
+    def save(self, path): self.ev.append(["save"])
+
+
+class _NoShuffleRandom:
+    """np.random with shuffle disabled, so batch indices of the trace are positions in the caller's order."""
+    def shuffle(self, a): pass
+    def normal(self, size=None): return np.zeros(size)
+    def uniform(self, size=None): return np.zeros(size)
+
+
+class _NP:
+    random = _NoShuffleRandom()
+    def __getattr__(self, k): return getattr(np, k)
+
+
+def training_loop_trace(out):
+    """TG:778-894 (the `for epoch in range(niter)` loop) executed with recording stand-ins: which mini-batch every critic
+    update, noise search and generator update touches, every logged tag with its step counter, validation, saves."""
+    import time as _time
+    src, span = cut(TG, r"^\s+for epoch in range\(niter\):", r"^\s+gen_iterations\+=1", include_end=True)
+    out["loop/lines"] = np.array(span)
+    for tag, g0, niter, batches in (("warmup_to_steady", 23, 2, 260), ("every_500th", 498, 1, 140), ("from_scratch", 0, 1, 230)):
+        bs = 2
+        data = np.arange(batches * bs + 1, dtype=np.float32).reshape(-1, 1, 1, 1)   # one sample left over: // batchSize
+        env = dict(np=_NP(), time=_time, niter=niter, batchSize=bs, noiseSize=4, Diters=5, gen_iterations=g0, crit_iterations=0,
+                   crit_dem_iterations=0, fold=1, errG=0, save_file_name="x", prob_flair_1tp_train=data, prob_2tp_train=data.copy(),
+                   prob_flair_1tp_val=np.zeros((3, 2, 2, 1), np.float32), prob_2tp_val=np.zeros((3, 2, 2, 1), np.float32),
+                   fixed_noise=np.zeros((3, 4, 1), np.float32), vn=3, vx=2, vy=2, vc=1, t0=0.0)
+        rec = _Rec(env)
+        env.update(netD_y2_train=rec.critic("y2"), netD_dem_train=rec.critic("dem"), netG_no_update=rec.no_update,
+                   netG_train=rec.train, logger=rec, netD_y2=rec, netG=rec)
+        run(src, env, "TG:loop")
+        out["loop/%s" % tag] = np.array(json.dumps({"g0": g0, "niter": niter, "batches": batches, "batchSize": bs,
+                                                    "events": rec.ev, "gen_iterations_end": int(env["gen_iterations"]),
+                                                    "crit_iterations_end": int(env["crit_iterations"])}))
+
+
 def main():
     torch.set_num_threads(8)
     out = {}
+    training_loop_trace(out)
     gan_training_graph(1, 0.178, out, "gan_im")
     gan_training_graph(2, 0.5, out, "gan_pf")
     generator_topologies(out)

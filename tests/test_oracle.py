@@ -1,5 +1,5 @@
 """Pins the CPU oracle (oracle/depgan_oracle.py).  The reference ships no tests or golden vectors and cannot
-run here (parity unpinned), so the restatement is guarded by: an independent naive NumPy forward,
+run here (its executed source pins the oracle in tests/test_reference_vectors.py); the restatement is additionally guarded by: an independent naive NumPy forward,
 finite differences of the loss graphs in fp64, the parameter-count identities, hand-derived known answers for the
 integer post-processing and Keras-Adam, and committed golden vectors (tests/golden/make_golden.py)."""
 from pathlib import Path
