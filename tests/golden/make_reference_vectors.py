@@ -295,9 +295,40 @@ def training_loop_trace(out):
                                                     "crit_iterations_end": int(env["crit_iterations"])}))
 
 
+def host_functions(out):
+    """The reference's NumPy-only helpers, executed: data_prep, data_prep_save, map_image_to_intensity_range (TG:105-149)
+    and convert_to_1hot (TU:209-223)."""
+    env = dict(np=np)
+    src, _ = cut(TG, r"^def data_prep\(", r"^# Calculate Dice coefficient score")
+    run(src, env, "TG:host")
+    src, _ = cut(TU, r"^def convert_to_1hot\(", r"^''' SECTION 4")
+    run(src, env, "TU:1hot")
+    rng = np.random.default_rng(77)
+    vol = rng.standard_normal((5, 7, 4)).astype(np.float32)
+
+    class _Img:
+        image = vol
+    out["host/vol"] = vol
+    out["host/data_prep"] = env["data_prep"](_Img())
+    stack = rng.standard_normal((4, 5, 7, 1)).astype(np.float32)
+    out["host/stack"] = stack
+    out["host/data_prep_save"] = np.ascontiguousarray(env["data_prep_save"](stack))
+    img64 = rng.standard_normal((6, 9)) * 3.0 + 1.0
+    out["host/img64"] = img64
+    out["host/map_p0"] = env["map_image_to_intensity_range"](img64, 0, 1, percentiles=0)
+    out["host/map_p5"] = env["map_image_to_intensity_range"](img64, -1, 1, percentiles=5)
+    u8 = rng.integers(0, 256, size=(5, 5)).astype(np.uint8)
+    out["host/u8"] = u8
+    out["host/map_u8"] = env["map_image_to_intensity_range"](u8, 0, 255, percentiles=2)
+    lab = rng.integers(0, 4, size=(2, 3, 4, 1)).astype(np.float32)
+    out["host/labels"] = lab
+    out["host/onehot"] = env["convert_to_1hot"](lab, 4)
+
+
 def main():
     torch.set_num_threads(8)
     out = {}
+    host_functions(out)
     training_loop_trace(out)
     gan_training_graph(1, 0.178, out, "gan_im")
     gan_training_graph(2, 0.5, out, "gan_pf")

@@ -198,3 +198,17 @@ def test_uresnet_subject_evaluation_block_matches_the_executed_testing_script():
     v2 = np.count_nonzero(np.multiply(mask.reshape(Z, H, H), w2)) * _pix() / 1000
     row = O.evaluation_row(labels, G["EG_eval/code"], v1, v2, np.int64(count) * _pix() / 1000)
     _close(row, G["EU_eval/row"], rtol=1e-12)
+
+
+def test_host_side_helpers_match_the_executed_reference_functions():
+    """data_prep / data_prep_save / map_image_to_intensity_range (TG:105-149) executed on random inputs: the product's
+    rewritten versions (depgan_b200/preproc.py) return the same arrays; convert_to_1hot (TU:209-223) is what fit() is fed."""
+    from depgan_b200 import preproc
+    assert np.array_equal(preproc.data_prep(G["host/vol"]), G["host/data_prep"])
+    assert np.array_equal(preproc.data_prep_save(G["host/stack"]), G["host/data_prep_save"])
+    _close(preproc.map_image_to_intensity_range(G["host/img64"], 0, 1, percentiles=0), G["host/map_p0"], rtol=1e-13)
+    _close(preproc.map_image_to_intensity_range(G["host/img64"], -1, 1, percentiles=5), G["host/map_p5"], rtol=1e-13)
+    _close(preproc.map_image_to_intensity_range(G["host/u8"], 0, 255, percentiles=2), G["host/map_u8"], rtol=1e-13)
+    lab = G["host/labels"]
+    onehot = np.eye(4, dtype=np.int16)[lab.astype(int)[..., 0]][..., None, :]   # (N,H,W,1,C) like the reference returns
+    assert np.array_equal(onehot, G["host/onehot"]) and G["host/onehot"].shape == lab.shape + (4,)
