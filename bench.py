@@ -405,6 +405,19 @@ def measure_config0(args, rank, world, dev):
     _barrier(torch, dist, dev, world)
     ms = e0.elapsed_time(e1)
     launches = launch_count() - l0
+    # the same forward replayed from a CUDA graph (whole-step capture: one graph launch instead of 28 kernel launches)
+    out_g = torch.empty_like(out)
+    for _ in range(3):
+        g.forward_graph(xd, zd, out_g)
+    _barrier(torch, dist, dev, world)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g0.record()
+    for _ in range(steps):
+        g.forward_graph(xd, zd, out_g)
+    g1.record()
+    _barrier(torch, dist, dev, world)
+    ms_graph = g0.elapsed_time(g1)
+    graph_same = bool(torch.equal(out, out_g))
     # the drop-in call itself: predict() on NumPy arrays, 8 batches of 16 per call
     nb = 8
     xs, zs = np.concatenate([x] * nb), np.concatenate([z] * nb)
@@ -427,6 +440,9 @@ def measure_config0(args, rank, world, dev):
     return {"workload": w["desc"], "metric": "256x256 slices/sec (gen inference)", "unit": "slices/s",
             "value": B * steps * world / (ms * 1e-3), "ms_per_step": ms / steps, "steps": steps, "batch_per_gpu": B,
             "n_gpus": world, "gpu_launches": int(launches), "tflops_effective": B * steps * world / (ms * 1e-3) * G_FLOP[(1, 1)] / 1e12,
+            "cuda_graph_replay": {"value": B * steps * world / (ms_graph * 1e-3), "ms_per_step": ms_graph / steps,
+                                  "bit_identical": graph_same,
+                                  "what": "Gen_UNet2D.forward_graph: the same forward captured once and replayed"},
             "e2e": {"value": reps * xs.shape[0] * world / dt, "unit": "slices/s",
                     "what": "Gen_UNet2D.predict([x, z], batch_size=16) on pageable NumPy arrays, %d slices per call, "
                             "host wall clock (max over ranks)" % xs.shape[0],

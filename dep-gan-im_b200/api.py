@@ -326,6 +326,34 @@ class Gen_UNet2D(_Net):
                                                      _stream(torch)), "gen_forward")
         return out
 
+    def forward_graph(self, x, z, out):
+        """``forward_device`` replayed from a CUDA graph: the whole forward (28 launches with their tensor maps and
+        programmatic-dependent-launch edges) is captured once per (batch size, buffer addresses) and launched as one
+        graph afterwards.  Same kernels, same results bit for bit; what it removes is the per-launch host work
+        (descriptor encoding, ``cudaLaunchKernelEx``), which matters for small batches where the GPU outruns the host.
+        Weight updates need no re-capture (the derived weight buffers keep their addresses)."""
+        torch = self._torch
+        key = (int(x.shape[0]), x.data_ptr(), z.data_ptr(), out.data_ptr())
+        cache = self.__dict__.setdefault("_graphs", {})
+        g = cache.get(key)
+        if g is None:
+            if len(cache) >= 16:   # callers that keep allocating new buffers would grow the cache without bound
+                cache.clear()
+            with torch.cuda.device(self.device):
+                cur = torch.cuda.current_stream(self.device)
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    self.forward_device(x, z, out)   # warm-up outside the capture (one-time set-up paths)
+                side.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self.forward_device(x, z, out)
+                cur.wait_stream(side)
+            cache[key] = g
+        g.replay()
+        return out
+
     # ---- DEP-UResNet supervised training: my_network.fit(...) TU:602-606 (model compiled at TU:427) ----------
     def enable_data_parallel(self):
         """Data-parallel ``fit`` under torchrun (one process per GPU, ``torch.distributed`` initialised with NCCL):

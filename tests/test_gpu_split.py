@@ -101,3 +101,28 @@ def test_split_half_rejects_what_it_does_not_cover():
         Gen_UNet2D((128, 128, 1), precision="f16x3", max_batch=1, training=True)
     with pytest.raises(Exception):
         Dis_C2D_FCN1((128, 128, 1), precision="f16x3", max_batch=1)
+
+
+def test_forward_graph_replay_is_bit_identical_and_follows_weight_updates():
+    """Whole-forward CUDA-graph capture (Gen_UNet2D.forward_graph): same bits as the launch-by-launch forward, for two
+    batch sizes on one model, and still valid after the weights change (derived buffers keep their addresses)."""
+    from depgan_b200 import Gen_UNet2D
+    H = 128
+    dev = torch.device("cuda:0")
+    g = Gen_UNet2D((H, H, 1), (32, 1), 32, 4, precision="f16", max_batch=6)
+    g.set_weights(util.gen_weights(1, 4, seed=3))
+    for n in (6, 2):
+        x, _ = synth.make_flair(n, H, H, seed=n)
+        z = synth.make_noise(n, seed=n + 1)
+        xd, zd = torch.from_numpy(x).to(dev), torch.from_numpy(z).to(dev)
+        a = torch.empty((n, H, H, 4), dtype=torch.float32, device=dev)
+        b = torch.empty_like(a)
+        g.forward_device(xd, zd, a)
+        for _ in range(3):
+            b.zero_()
+            g.forward_graph(xd, zd, b)
+            assert torch.equal(a, b)
+    g.set_weights(util.gen_weights(1, 4, seed=4))
+    g.forward_device(xd, zd, a)
+    g.forward_graph(xd, zd, b)
+    assert torch.equal(a, b) and len(g._graphs) == 2
