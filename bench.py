@@ -250,11 +250,28 @@ def run_gpu(args, w, rank, world, local_rank):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)  # f1 is recorded after all three pipeline streams were flushed
+    # the same pipeline with the opt-in float16 device->host output (half the PCIe bytes per slice; predict(out_dtype=))
+    ohs16 = [torch.empty((B, 256, 256, w["nc_out"]), dtype=torch.float16).pin_memory() for _ in range(2)]
+    pipe16 = InferencePipeline(g, depth=int(os.environ.get("DEPGAN_PIPE_DEPTH", "2")), out_dtype=torch.float16)
+    for i in range(max(3, args.warmup)):
+        pipe16.submit(xh, zh, ohs16[i % 2])
+    pipe16.flush()
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for i in range(args.steps):
+        pipe16.submit(xh, zh, ohs16[i % 2])
+    pipe16.flush()
+    h1.record()
+    barrier()
+    ms_e2e16 = h0.elapsed_time(h1)
+    d2h16 = int(ohs16[0].numel() * ohs16[0].element_size())
+    del pipe16, ohs16
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, ms_e2e, ms_e2e16], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, ms_e2e16 = float(t[0]), float(t[1]), float(t[2])
 
     # ---- roofline leg: per-launch CUDA events around every convolution of the same step ----
     roof = None
@@ -359,6 +376,10 @@ def run_gpu(args, w, rank, world, local_rank):
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": slices / (ms_e2e * 1e-3), "unit": "slices/s",
                 "h2d_bytes_per_step": int(xh.numel() * 4 + zh.numel() * 4), "d2h_bytes_per_step": int(oh.numel() * 4)},
+        "e2e_float16_output": {"value": slices / (ms_e2e16 * 1e-3), "unit": "slices/s",
+                               "h2d_bytes_per_step": int(xh.numel() * 4 + zh.numel() * 4), "d2h_bytes_per_step": d2h16,
+                               "what": "the same pipeline with the opt-in float16 device->host output "
+                                       "(InferencePipeline(out_dtype=float16) / predict(out_dtype=np.float16))"},
         "roofline": roof, "cpu_baseline": cpu, "train": train,
         "configs": {"configs[0]": extra.get("configs[0]"),
                     "configs[1]": "this line (value / e2e / roofline); predict(numpy) below",

@@ -12,7 +12,10 @@ z = synth.make_noise(B, seed=2)
 xd, zd = torch.from_numpy(x).to(dev), torch.from_numpy(z).to(dev)
 out = torch.empty((B, 256, 256, 4), dtype=torch.float32, device=dev)
 ref = None
-for prec, steps in (("f16x3", 10), ("f16", 20), ("fp32", 2)):
+only = os.environ.get("DEPGAN_ONLY")  # e.g. DEPGAN_ONLY=f16x3 under ncu
+for prec, steps in (("f16x3", 10 if not only else 1), ("f16", 20), ("fp32", 2)):
+    if only and prec != only:
+        continue
     g = Gen_UNet2D((256, 256, 1), (32, 1), 32, 4, precision=prec, max_batch=B)
     man = [(n.split("/")[0], n.split("/")[1], s) for n, s, _, _ in g.manifest]
     g.set_weights(synth.init_weights(man, seed=0, trained_like=True))

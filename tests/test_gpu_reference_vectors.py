@@ -72,6 +72,14 @@ def test_fp32_forward_and_training_sequence_match_the_executed_reference(tag, ni
             k = (l + "/" + w).replace(*rename) if rename else l + "/" + w
             got = _digest(W[k])
             n = int(np.prod(s))
+            if key != "G" and k in ("dis_9/bias", "dense_1/bias"):
+                # The critics' two output biases have a structurally zero WGAN-GP gradient (+1/N over the fake rows
+                # cancels -1/N over the real rows; the penalty does not see an additive constant).  What reaches Adam
+                # is rounding noise, which Adam (beta_1 = 0) normalises to steps of up to lr_t * sqrt(10) each -- in
+                # float32 here as in the reference's float32 TF graph, but not in the float64 run that made the golden
+                # vectors.  Bounded by the two steps taken, not compared digit for digit.
+                assert np.abs(got[2:] - want[2:]).max() <= 2 * 3.2e-4, (key, k, got, want)
+                continue
             assert np.allclose(got[2:], want[2:], rtol=1e-5, atol=2e-6), (key, k, got, want)       # first elements
             assert abs(got[0] - want[0]) <= 2e-6 * n + 1e-5 * abs(want[0]), (key, k, got[0], want[0])  # sum
     moved = np.abs(g.predict([x1, z]) - G[tag + "/gen_out"]).max()
