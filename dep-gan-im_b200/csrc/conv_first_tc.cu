@@ -526,6 +526,10 @@ int conv_first_tc_try(const ConvArgs& a, cudaStream_t st) {
   if (a.in_dt != DT_F32 || a.out_dt != DT_BF16 || a.C1 != 0 || a.out_pre || a.film_g || a.add_src || !a.out || a.deconv ||
       a.head_w || !a.w)
     return 0;
+  {  // conv2d_dis_0a without the im2col tile (conv_first_band.cu): any height, widths that are multiples of 8
+    const int rb = conv_first_band_try(a, st);
+    if (rb != 0) return rb;
+  }
   if (a.H % 16 || a.W % 16 || a.H < 16 || a.W < 16) return 0;
   int r = 1;
   // conv2d_dis_0a only: for conv2d_gen_0 (3x3, 9-18 taps, 32 outputs) the CUDA-core kernel is faster (0.087 vs
