@@ -211,4 +211,5 @@ int conv_wgrad_simt(const WgradArgs& a, cudaStream_t st);
 int conv_wgrad_tc(const WgradArgs& a, cudaStream_t st);  // tcgen05 path (bf16 x and dy); handles a.csum itself
 bool wgrad_tc_supported(const WgradArgs& a);
 int wgrad_tc_init();
+int wgrad_first_band_try(const WgradArgs& a, cudaStream_t st);  // wgrad_first_band.cu: 1 taken, 0 not a case, < 0 error
 int wgrad_first_tc_try(const WgradArgs& a, cudaStream_t st);  // tcgen05 first-layer wgrad (conv_first_tc.cu)

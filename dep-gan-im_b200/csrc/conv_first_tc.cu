@@ -544,6 +544,10 @@ int conv_first_tc_try(const ConvArgs& a, cudaStream_t st) {
 // Weight gradient of conv2d_dis_0a in a bf16 network (fp32 image, bf16 gradient): 1 taken, 0 not a case, < 0 error.
 int wgrad_first_tc_try(const WgradArgs& a, cudaStream_t st) {
   if (a.x_dt != DT_F32 || a.dy_dt != DT_BF16 || a.C1 != 0 || !a.dw) return 0;
+  {  // without the im2col tile (wgrad_first_band.cu): widths that are multiples of 128, any height
+    const int rb = wgrad_first_band_try(a, st);
+    if (rb != 0) return rb;
+  }
   if (a.H % 16 || a.W % 16 || a.H < 16 || a.W < 16) return 0;
   int r = 1;
   if (a.ks == 5 && a.C0 == 1 && a.Cout == 16) r = launch_wgrad_first_tc<5, 1, 16>(a, st);
