@@ -184,6 +184,7 @@ struct ConvArgs {
 int conv_fwd_simt(const ConvArgs& a, cudaStream_t st);
 int conv_fwd_tc(const ConvArgs& a, cudaStream_t st);  // tcgen05 path (bf16 in/out)
 int conv_first_band_try(const ConvArgs& a, cudaStream_t st);  // conv2d_dis_0a, image row as the A operand: 1 taken, 0 not a case
+int conv_last_band_try(const ConvArgs& a, cudaStream_t st);   // 16 -> 1 data gradient of conv2d_dis_0a: 1 taken, 0 not a case
 int conv_first_tc_try(const ConvArgs& a, cudaStream_t st);  // tcgen05 first layer (fp32 image in): 1 taken, 0 not a case
 bool conv_tc_supported(const ConvArgs& a);
 bool conv_tc_plan_query(const ConvArgs& a, int* plan16);  // host-only: the planner's geometry for a supported layer

@@ -723,6 +723,10 @@ int conv_fwd_simt(const ConvArgs& a, cudaStream_t st) {
                   : a.out_dt == DT_F16 ? try_first<__half>(a, st)
                   : a.out_dt == DT_F16S ? try_first<hsplit>(a, st) : try_first<float>(a, st);
     if (r != 0) return r < 0 ? r : 0;
+    {  // 16 -> 1 data gradient of conv2d_dis_0a on the tensor cores (conv_last_band.cu)
+      const int rl = conv_last_band_try(a, st);
+      if (rl != 0) return rl < 0 ? rl : 0;
+    }
     if (a.in_dt != DT_F16) {
       const int r2 = a.in_dt == DT_BF16 ? try_last<bf16>(a, st) : try_last<float>(a, st);
       if (r2 != 0) return r2 < 0 ? r2 : 0;
