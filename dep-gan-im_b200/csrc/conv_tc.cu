@@ -111,9 +111,20 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
   const int pool = a.pool_out ? 1 : 0;
   const uint32_t staging = (stage_out ? (split ? 4u : 2u) : 0u) * slot + 2u * n_side * slot + (pool ? slot / 2u : 0u);
   const uint32_t floats = 2u * ncols * 4 + (a.head_w ? 16u * a.Cout : 0u) + (a.film_g ? 24u * ncta : 0u) + 64u;
+  // padded 64-channel chunks are OFF by default: measured on the 160 -> 64 layer they do not pay (0.249 ms against 0.202 ms
+  // with exact 32-channel chunks), because a 64-channel stage of all nine taps no longer fits twice next to the
+  // activation ring and the weights fall back to one ring stage per kernel row.  DEPGAN_KPAD=1 turns them on (A/B).
+  static const bool no_pad = getenv("DEPGAN_KPAD") == nullptr;
   for (int kc = 64; kc >= 16; kc /= 2) {
-    if (a.C0 % kc || a.C1 % kc) continue;
-    const int nchunks = (split ? 3 : 1) * (a.C0 + a.C1) / kc;
+    // (opt-in) 64-channel chunks when a source is not a multiple of 64 channels: its last chunk runs past the tensor, TMA
+    // fills the missing channels with zeros, and the weights under them (the next source's, or out of bounds) multiply
+    // zeros; only while the padded K stays within 25 % of the real one (160 -> 192, 224 -> 256).
+    const int pc0 = (a.C0 + kc - 1) / kc, pc1 = (a.C1 + kc - 1) / kc;
+    const bool exact = a.C0 % kc == 0 && a.C1 % kc == 0;
+    const bool padded = !exact && !split && !no_pad && kc == 64 && a.C0 >= 64 && (a.C1 == 0 || a.C1 >= 64) &&
+                        4 * (pc0 + pc1) * kc <= 5 * (a.C0 + a.C1);
+    if (!exact && !padded) continue;
+    const int nchunks = split ? 3 * (a.C0 + a.C1) / kc : pc0 + pc1;
     const uint32_t a_bytes = round1024((uint32_t)ht * ht * kc * 2), b_bytes = round1024((uint32_t)ncta * kc * 2);
     int na = 0, nb = 0, resident = 0, tps = 1;
     const int nb_all = taps * nchunks;
@@ -149,8 +160,12 @@ bool plan(const ConvArgs& a, TcGeom* g, uint32_t* smem_bytes) {
       }
     }
     g->tiles_w = a.W / 16; g->tiles_h = a.H / 16;
-    g->nchunk0 = (split ? 2 : 1) * a.C0 / kc; g->nchunk1 = (split ? 2 : 1) * a.C1 / kc;
+    g->nchunk0 = split ? 2 * a.C0 / kc : pc0; g->nchunk1 = split ? 2 * a.C1 / kc : pc1;
     g->nchunk2 = split ? a.C0 / kc : 0; g->nchunk3 = split ? a.C1 / kc : 0;
+    // weight columns: [in0 | in1] as packed by k_pack_conv_weights, or the split-half order [2 C0 | 2 C1 | C0 | C1]
+    g->kofs1 = split ? 2 * a.C0 : a.C0;
+    g->kofs2 = split ? 2 * (a.C0 + a.C1) : 0;
+    g->kofs3 = split ? 2 * (a.C0 + a.C1) + a.C0 : 0;
     g->split = split ? 1 : 0;
     g->kc = kc; g->ncols_total = ncols; g->ncta = ncta; g->tmem_cols = tmem_cols;
     g->na = na; g->nb = nb; g->b_tps = tps; g->a_bytes = a_bytes; g->b_bytes = b_bytes;

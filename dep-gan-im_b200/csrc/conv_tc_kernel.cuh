@@ -44,6 +44,9 @@ struct TcGeom {
   int tiles_w, tiles_h;
   int nchunk0, nchunk1;  // channel chunks taken from in0 / in1
   int nchunk2, nchunk3;  // split-half storage: the hi halves of in0 / in1 once more (the x_hi * w_lo term); else 0
+  int kofs1, kofs2, kofs3;  // first weight column (K index) of the chunks of segments 1..3 (segment 0 starts at 0).  A
+                            // segment's last chunk may run past its tensor's channels (C not a multiple of kc): TMA fills
+                            // the missing activations with zeros, so whatever weights sit under them contribute nothing
   int kc;                // channels per chunk
   int ncols_total;       // weight rows per tap (Cout, or 4*Cout for the transposed conv)
   int ncta;              // output columns per CTA
@@ -411,7 +414,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (elect_one()) {
         mbar_expect_tx(fullB, g.b_tx * TAPS * nchunks);
         for (int c = 0; c < nchunks; ++c) {
-          const int kglob = c * g.kc;  // weight rows are packed in chunk order
+          int cs = c, kglob = 0;
+          if (cs >= g.nchunk0) {
+            cs -= g.nchunk0; kglob = g.kofs1;
+            if (cs >= g.nchunk1) {
+              cs -= g.nchunk1; kglob = g.kofs2;
+              if (cs >= g.nchunk2) { cs -= g.nchunk2; kglob = g.kofs3; }
+            }
+          }
+          kglob += cs * g.kc;
           for (int tap = 0; tap < TAPS; ++tap)
             tma_load_2d(b_base + (c * TAPS + tap) * g.b_bytes, &tm.b, fullB, kglob, tap * g.ncols_total);
         }
@@ -430,15 +441,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         mbar_wait(emptyA + 8 * ra.idx, ra.phase ^ 1u);
         if (c == 0) DG_TRACE(0, p_it, 1);
         // chunk -> (source, channel offset): in0, in1, then (split-half storage) the hi halves of in0 and in1 again
-        int cs = c;
+        int cs = c, kglob = 0;
         bool first = true;
         if (cs >= g.nchunk0) {
-          cs -= g.nchunk0; first = false;
+          cs -= g.nchunk0; first = false; kglob = g.kofs1;
           if (cs >= g.nchunk1) {
-            cs -= g.nchunk1; first = true;
-            if (cs >= g.nchunk2) { cs -= g.nchunk2; first = false; }
+            cs -= g.nchunk1; first = true; kglob = g.kofs2;
+            if (cs >= g.nchunk2) { cs -= g.nchunk2; first = false; kglob = g.kofs3; }
           }
         }
+        kglob += cs * g.kc;
         if (elect_one()) {
           mbar_expect_tx(fullA + 8 * ra.idx, g.a_tx);
           tma_load_4d(a_base + ra.idx * g.a_bytes, first ? &tm.a0 : &tm.a1, fullA + 8 * ra.idx, cs * g.kc, w0 - PAD,
@@ -448,7 +460,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         ra.advance(g.na);
         if (!RES) {
           // weight ring: one stage = b_tps consecutive taps of this channel chunk (all taps, one kernel row, or one tap)
-          const int kglob = c * g.kc;
           for (int tap = 0; tap < TAPS; tap += g.b_tps) {
             mbar_wait(emptyB + 8 * rb.idx, rb.phase ^ 1u);
             if (elect_one()) {
@@ -541,8 +552,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tc_commit(emptyA + 8 * ra.idx);
           }
           __syncwarp();
+        } else if (g.b_tps == TAPS) {
+          // streamed weights, one ring stage = all taps of the chunk: one wait, then the chunk's TAPS x 2 strips x KSTEPS
+          // MMAs back to back with immediate descriptor offsets, like the resident case.  (The tap-by-tap loop below costs
+          // the issuing thread ~330 clk of scalar work per tap -- measured with the role tracer on the 160 -> 64 layer:
+          // 14.9 k clk per item for 180 MMAs -- which is more than its four MMAs take.)
+          mbar_wait(fullB + 8 * rb.idx, rb.phase);
+          tc_fence_after();
+          const uint32_t b_lo0 = (((b_base + rb.idx * TAPS * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) {
+              const uint32_t at = a_lo + (uint32_t)(((tap / KS) * HT + (tap % KS)) * ROW16);
+              const uint32_t b_lo = b_lo0 + tap * b_step;
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint32_t acc = (tap | k) != 0 ? 1u : accc;
+                tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
+                tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
+                       idesc, acc);
+              }
+            }
+            tc_commit(emptyB + 8 * rb.idx);
+            tc_commit(emptyA + 8 * ra.idx);
+          }
+          __syncwarp();
+          rb.advance(g.nb);
         } else {
-          // streamed weights: a ring stage holds b_tps consecutive taps (TAPS, KS or 1); taps of a kernel row are
+          // streamed weights: a ring stage holds b_tps consecutive taps (KS or 1); taps of a kernel row are
           // unrolled so their descriptor offsets are immediates
           uint32_t b_lo0 = 0;
 #pragma unroll 1
