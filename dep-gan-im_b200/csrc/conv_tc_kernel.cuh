@@ -578,6 +578,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
           __syncwarp();
           rb.advance(g.nb);
+        } else if (g.b_tps == KS && KS > 1) {
+          // streamed weights, one ring stage = one kernel row: one wait and one election per row, its KS taps unrolled
+#pragma unroll 1
+          for (int dy = 0; dy < KS; ++dy) {
+            mbar_wait(fullB + 8 * rb.idx, rb.phase);
+            tc_fence_after();
+            const uint32_t b_lo0 = (((b_base + rb.idx * KS * g.b_bytes) & 0x3FFFFu) >> 4) | LBO1;
+            const uint32_t a_row = a_lo + (uint32_t)(dy * HT * ROW16);
+            if (elect_one()) {
+#pragma unroll
+              for (int dx = 0; dx < KS; ++dx) {
+                const uint32_t at = a_row + (uint32_t)(dx * ROW16);
+                const uint32_t b_lo = b_lo0 + dx * b_step;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  const uint32_t acc = (dx | k) != 0 ? 1u : (dy != 0 ? 1u : accc);
+                  tc_mma(d0, ((uint64_t)hiA << 32) | (at + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k), idesc, acc);
+                  tc_mma(d1, ((uint64_t)hiA << 32) | (at + 8 * ROW16 + 2 * k), ((uint64_t)hiB << 32) | (b_lo + 2 * k),
+                         idesc, acc);
+                }
+              }
+              tc_commit(emptyB + 8 * rb.idx);
+              if (dy == KS - 1) tc_commit(emptyA + 8 * ra.idx);
+            }
+            __syncwarp();
+            rb.advance(g.nb);
+          }
         } else {
           // streamed weights: a ring stage holds b_tps consecutive taps (KS or 1); taps of a kernel row are
           // unrolled so their descriptor offsets are immediates
