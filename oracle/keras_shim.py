@@ -71,7 +71,11 @@ def _binop(op, a, b):
 
 def evaluate(nodes, feed):
     """Values of `nodes` given {placeholder Sym: tensor}.  One memo per call: every node is computed once."""
-    memo = {id(k): v for k, v in feed.items()}
+    memo = {}
+    for k, v in feed.items():  # fed tensors are differentiable leaves, so K.gradients may name a placeholder
+        if torch.is_grad_enabled() and v.is_floating_point() and v.is_leaf and not v.requires_grad:
+            v = v.detach().clone().requires_grad_(True)
+        memo[id(k)] = v
 
     def ev(n):
         k = id(n)
