@@ -325,10 +325,74 @@ def host_functions(out):
     out["host/onehot"] = env["convert_to_1hot"](lab, 4)
 
 
+class _Vol:
+    def __init__(self, image):
+        self.image = image
+        self.pixdim = np.array([0.9375, 0.9375, 4.0], dtype=np.float32)
+
+
+class _FakeOs:
+    class path:  # the stroke-lesion files "exist"
+        @staticmethod
+        def isfile(p): return True
+
+
+def subject_preparation(out):
+    """The per-subject preparation of the two testing scripts, executed on synthetic (X, Y, Z) volumes: masking with the
+    intracranial-volume and stroke-lesion masks, clamping, FLAIR normalisation, channel concatenation (EG:533-611) and the
+    whole-volume z-score of the DEP-UResNet script (EU:506-538)."""
+    rng = np.random.default_rng(91)
+    X, Y, Zs = 12, 10, 6
+    vols = {"pm1": rng.uniform(-0.2, 1.0, (X, Y, Zs)).astype(np.float32), "pm2": rng.uniform(-0.2, 1.0, (X, Y, Zs)).astype(np.float32),
+            "im1": rng.uniform(-0.2, 1.0, (X, Y, Zs)).astype(np.float32), "flair": (rng.standard_normal((X, Y, Zs)) * 90 + 300).astype(np.float32),
+            "icv1": (rng.random((X, Y, Zs)) > 0.2).astype(np.float32), "icv2": (rng.random((X, Y, Zs)) > 0.25).astype(np.float32),
+            "sl1": (rng.random((X, Y, Zs)) > 0.9).astype(np.float32), "sl2": (rng.random((X, Y, Zs)) > 0.92).astype(np.float32),
+            "wmh1": (rng.random((X, Y, Zs)) > 0.8).astype(np.float32), "wmh2": (rng.random((X, Y, Zs)) > 0.8).astype(np.float32),
+            "code2": rng.integers(0, 4, (X, Y, Zs)).astype(np.float32)}
+    for k, v in vols.items():
+        out["prep/vol_" + k] = v
+    # ---- EG ----
+    env = dict(np=np, os=_FakeOs)
+    src, _ = cut(EG, r"^def data_prep\(", r"^# Calculate Dice coefficient score")
+    run(src, env, "EG:host")
+    dp = env["data_prep"]
+    sq = lambda k: np.squeeze(dp(_Vol(vols[k])))   # EG:511-531: data_prep, then np.squeeze
+    src, span = cut(EG, r"^\s+# Exclude non-brain tissues", r"# Produce 10 results by using 10 different sets of noise")
+    for nicg, PM in ((1, True), (1, False), (2, True)):
+        env2 = dict(env)
+        env2.update(loaded_image_f_1tp=sq("flair"), loaded_image_im_1tp=sq("im1"), loaded_image_p_1tp=sq("pm1"),
+                    loaded_image_p_2tp=sq("pm2"), loaded_image_i_1tp=sq("icv1"), loaded_image_w_1tp=sq("wmh1"),
+                    loaded_image_w_2tp=sq("wmh2"), loaded_image_i_2tp=sq("icv2"), loaded_image_c_2tp=sq("code2"),
+                    data_list_sl_1tp=["sl1"], data_list_sl_2tp=["sl2"], id=0, load_data=lambda p: _Vol(vols[p]),
+                    TRSH_VAL=0.5 if PM else 0.178, nicg=nicg, PM=PM)
+        run(src, env2, "EG:prepare")
+        tag = "prep/EG_nicg%d_%s" % (nicg, "pm" if PM else "im")
+        out[tag + "/x"] = env2["brain_prob__1tp"]
+        out[tag + "/mask1"] = env2["icv_and_sl_mask_1tp"]
+        out[tag + "/mask2"] = env2["icv_and_sl_mask_2tp"]
+    out["prep/EG_lines"] = np.array(span)
+    # ---- EU ----
+    env = dict(np=np, os=_FakeOs)
+    src, _ = cut(EU, r"^def data_prep\(", r"^# Change integer values|^def map_image_to_intensity_range|^# Calculate Dice")
+    run(src, env, "EU:host")
+    dp = env["data_prep"]
+    src, span = cut(EU, r"^\s+# Exclude non-brain tissues", r"# Create output directories for each data")
+    env.update(loaded_image_f_1tp=dp(_Vol(vols["flair"])), loaded_image_i_1tp=dp(_Vol(vols["icv1"])),
+               loaded_image_w_1tp=dp(_Vol(vols["wmh1"])), loaded_image_w_2tp=dp(_Vol(vols["wmh2"])),
+               loaded_image_i_2tp=dp(_Vol(vols["icv2"])), loaded_image_c_2tp=dp(_Vol(vols["code2"])),
+               data_list_sl_1tp=["sl1"], data_list_sl_2tp=["sl2"], id=0, load_data=lambda p: _Vol(vols[p]))
+    run(src, env, "EU:prepare")
+    out["prep/EU/x"] = env["brain_flair_1tp"]
+    out["prep/EU/mask1"] = env["icv_and_sl_mask_1tp"]
+    out["prep/EU/mask2"] = env["icv_and_sl_mask_2tp"]
+    out["prep/EU_lines"] = np.array(span)
+
+
 def main():
     torch.set_num_threads(8)
     out = {}
     host_functions(out)
+    subject_preparation(out)
     training_loop_trace(out)
     gan_training_graph(1, 0.178, out, "gan_im")
     gan_training_graph(2, 0.5, out, "gan_pf")

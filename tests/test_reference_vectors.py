@@ -212,3 +212,30 @@ def test_host_side_helpers_match_the_executed_reference_functions():
     lab = G["host/labels"]
     onehot = np.eye(4, dtype=np.int16)[lab.astype(int)[..., 0]][..., None, :]   # (N,H,W,1,C) like the reference returns
     assert np.array_equal(onehot, G["host/onehot"]) and G["host/onehot"].shape == lab.shape + (4,)
+
+
+@pytest.mark.parametrize("nicg,pm", [(1, True), (1, False), (2, True)])
+def test_depgan_subject_preparation_matches_the_executed_testing_script(nicg, pm):
+    """EG:533-611 executed on synthetic volumes (masks, stroke lesions, clamping, FLAIR min-max normalisation, channel
+    order) against depgan_b200.preproc.prepare_subject_dem."""
+    from depgan_b200 import preproc
+    v = {k: G["prep/vol_" + k] for k in ("pm1", "im1", "flair", "icv1", "icv2", "sl1", "sl2")}
+    x, m1, m2 = preproc.prepare_subject_dem(v["pm1"] if pm else v["im1"], v["icv1"], v["icv2"],
+                                            flair_1tp=v["flair"] if nicg == 2 else None, sl_1tp=v["sl1"], sl_2tp=v["sl2"],
+                                            nicg=nicg)
+    tag = "prep/EG_nicg%d_%s" % (nicg, "pm" if pm else "im")
+    want = G[tag + "/x"]
+    assert x.shape == want.shape and x.dtype == np.float32
+    np.testing.assert_allclose(x, want, rtol=0, atol=1e-7)     # the script keeps float64 where NumPy 2 promotes; values equal
+    assert np.array_equal(m1, G[tag + "/mask1"]) and np.array_equal(m2, G[tag + "/mask2"])
+
+
+def test_uresnet_subject_preparation_matches_the_executed_testing_script():
+    """EU:506-538 executed: masked FLAIR, whole-volume z-score, nan_to_num; masks keep their channel axis."""
+    from depgan_b200 import preproc
+    v = {k: G["prep/vol_" + k] for k in ("flair", "icv1", "icv2", "sl1", "sl2")}
+    x, m1, m2 = preproc.prepare_subject_uresnet(v["flair"], v["icv1"], v["icv2"], sl_1tp=v["sl1"], sl_2tp=v["sl2"])
+    want = G["prep/EU/x"]
+    assert x.shape == want.shape
+    np.testing.assert_allclose(x, want, rtol=2e-6, atol=2e-6)
+    assert np.array_equal(m1, G["prep/EU/mask1"]) and np.array_equal(m2, G["prep/EU/mask2"])
