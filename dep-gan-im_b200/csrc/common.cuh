@@ -131,6 +131,22 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w, bool f16) {
   if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
   return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
 }
+// the same conversion with the ReLU folded in (negative results become +0): one instruction instead of two max + one cvt
+__device__ __forceinline__ uint32_t pack_h2_relu(float lo, float hi, bool f16) {
+  uint32_t r;
+  if (f16) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// (x0, x1) = (x0, x1) * (s0, s1) + (t0, t1) as one packed fp32x2 FMA (per-lane IEEE fma: the bits are those of fmaf)
+__device__ __forceinline__ void fma_f32x2(float& x0, float& x1, float s0, float s1, float t0, float t1) {
+  unsigned long long xv, sv, tv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(xv) : "f"(x0), "f"(x1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(sv) : "f"(s0), "f"(s1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(tv) : "f"(t0), "f"(t1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(xv) : "l"(xv), "l"(sv), "l"(tv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xv));
+}
 // element-wise max of two packed pairs (2x2 max-pool on the stored values)
 __device__ __forceinline__ uint32_t max_h2(uint32_t a, uint32_t b, bool f16) {
   if (f16) {

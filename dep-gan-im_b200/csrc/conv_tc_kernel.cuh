@@ -777,10 +777,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           for (int i4 = 0; i4 < 4; ++i4) {
             const float4 sc = reinterpret_cast<const float4*>(s_scale + col)[i4];
             const float4 sh = reinterpret_cast<const float4*>(s_shift + col)[i4];
-            v[4 * i4 + 0] = fmaf(v[4 * i4 + 0], sc.x, sh.x);
-            v[4 * i4 + 1] = fmaf(v[4 * i4 + 1], sc.y, sh.y);
-            v[4 * i4 + 2] = fmaf(v[4 * i4 + 2], sc.z, sh.z);
-            v[4 * i4 + 3] = fmaf(v[4 * i4 + 3], sc.w, sh.w);
+            fma_f32x2(v[4 * i4 + 0], v[4 * i4 + 1], sc.x, sc.y, sh.x, sh.y);
+            fma_f32x2(v[4 * i4 + 2], v[4 * i4 + 3], sc.z, sc.w, sh.z, sh.w);
           }
           if (a.out_pre) st16_bf16(a.out_pre, pix0 * Cout + col, v, f16);
         }
@@ -802,15 +800,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = mkv[i] > 0.f ? v[i] : 0.f;
         }
-        if (a.relu) {
+        // the ReLU rides on the 16-bit conversion unless the fp32 values are used again (fused head)
+        const bool relu_cvt = a.relu && head_nc == 0 && !SPLIT;
+        if (a.relu && !relu_cvt) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (stage_out) {
           uint4 pk[2];
           uint32_t* hp = reinterpret_cast<uint32_t*>(pk);
+          if (relu_cvt) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) hp[i] = pack_h2(v[2 * i], v[2 * i + 1], f16);
+            for (int i = 0; i < 8; ++i) hp[i] = pack_h2_relu(v[2 * i], v[2 * i + 1], f16);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hp[i] = pack_h2(v[2 * i], v[2 * i + 1], f16);
+          }
           uint8_t* ogen = smem_raw + (o_base + (SPLIT ? 2u * oslot : oslot) * g.slot_bytes - raw);
           *reinterpret_cast<uint4*>(ogen + u0) = pk[0];
           *reinterpret_cast<uint4*>(ogen + u1) = pk[1];
