@@ -461,10 +461,10 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
             for (int k4 = 0; k4 < 8; ++k4) {
               const float4 sc4 = reinterpret_cast<const float4*>(tb)[k4];
               const float4 sh4 = reinterpret_cast<const float4*>(tb + 32)[k4];
-              v[4 * k4 + 0] = fmaf(__uint_as_float(va[u][4 * k4 + 0]), sc4.x, sh4.x);
-              v[4 * k4 + 1] = fmaf(__uint_as_float(va[u][4 * k4 + 1]), sc4.y, sh4.y);
-              v[4 * k4 + 2] = fmaf(__uint_as_float(va[u][4 * k4 + 2]), sc4.z, sh4.z);
-              v[4 * k4 + 3] = fmaf(__uint_as_float(va[u][4 * k4 + 3]), sc4.w, sh4.w);
+              v[4 * k4 + 0] = __uint_as_float(va[u][4 * k4 + 0]); v[4 * k4 + 1] = __uint_as_float(va[u][4 * k4 + 1]);
+              v[4 * k4 + 2] = __uint_as_float(va[u][4 * k4 + 2]); v[4 * k4 + 3] = __uint_as_float(va[u][4 * k4 + 3]);
+              fma_f32x2(v[4 * k4 + 0], v[4 * k4 + 1], sc4.x, sc4.y, sh4.x, sh4.y);   // packed fp32x2: the bits of fmaf
+              fma_f32x2(v[4 * k4 + 2], v[4 * k4 + 3], sc4.z, sc4.w, sh4.z, sh4.w);
             }
             if (side) {
               // side stage sequence: (output row, column block) in the producer's order
@@ -514,7 +514,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
               __syncwarp();
               if (lane == 0) mbar_arrive(sideEmpty + 8 * ss);
             }
-            if (a.relu) {
+            // the ReLU rides on the 16-bit conversion unless the fp32 values feed the fused head
+            const bool relu_cvt = a.relu && !HEAD;
+            if (a.relu && !relu_cvt) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) v[k] = fmaxf(v[k], 0.f);
             }
@@ -525,7 +527,9 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
                 uint4 pk;
                 uint32_t* hp = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) hp[e] = pack_h2(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16);
+                for (int e = 0; e < 4; ++e)
+                  hp[e] = relu_cvt ? pack_h2_relu(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16)
+                                   : pack_h2(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16);
                 *reinterpret_cast<uint4*>(ogen + (((uint32_t)uu ^ p_xor) << 4)) = pk;
               }
             }

@@ -585,10 +585,10 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
               for (int k4 = 0; k4 < CW / 4; ++k4) {
                 const float4 sc4 = reinterpret_cast<const float4*>(tb + h * CW)[k4];
                 const float4 sh4 = reinterpret_cast<const float4*>(tb + CO + h * CW)[k4];
-                v[4 * k4 + 0] = fmaf(__uint_as_float(va[u][4 * k4 + 0]), sc4.x, sh4.x);
-                v[4 * k4 + 1] = fmaf(__uint_as_float(va[u][4 * k4 + 1]), sc4.y, sh4.y);
-                v[4 * k4 + 2] = fmaf(__uint_as_float(va[u][4 * k4 + 2]), sc4.z, sh4.z);
-                v[4 * k4 + 3] = fmaf(__uint_as_float(va[u][4 * k4 + 3]), sc4.w, sh4.w);
+                v[4 * k4 + 0] = __uint_as_float(va[u][4 * k4 + 0]); v[4 * k4 + 1] = __uint_as_float(va[u][4 * k4 + 1]);
+                v[4 * k4 + 2] = __uint_as_float(va[u][4 * k4 + 2]); v[4 * k4 + 3] = __uint_as_float(va[u][4 * k4 + 3]);
+                fma_f32x2(v[4 * k4 + 0], v[4 * k4 + 1], sc4.x, sc4.y, sh4.x, sh4.y);   // packed fp32x2: the bits of fmaf
+                fma_f32x2(v[4 * k4 + 2], v[4 * k4 + 3], sc4.z, sc4.w, sh4.z, sh4.w);
               }
               if (side) {
                 // side stage sequence = real output row sequence (the producer's order)
@@ -641,10 +641,7 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
                   if (lane == 0) mbar_arrive(sideEmpty + 8 * ss);
                 }
               }
-              if (a.relu) {
-#pragma unroll
-                for (int k = 0; k < CW; ++k) v[k] = fmaxf(v[k], 0.f);
-              }
+              // (the ReLU rides on the 16-bit conversion below)
               // staging row: a step whose first slot is a phantom stages its one real row first
               const uint32_t srow = real[0] ? (uint32_t)u : 0u;
               uint8_t* ogen = smem_raw + (w_o + slot * G::WSLOT + srow * (32u * OSPAN) - raw) + p_off;
@@ -653,7 +650,9 @@ __global__ void __launch_bounds__(RG_THREADS, 1) conv_rowg_kernel(const __grid_c
                 uint4 pk;
                 uint32_t* hp = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) hp[e] = pack_h2(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16);
+                for (int e = 0; e < 4; ++e)
+                  hp[e] = a.relu ? pack_h2_relu(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16)
+                                 : pack_h2(v[8 * uu + 2 * e], v[8 * uu + 2 * e + 1], f16);
                 *reinterpret_cast<uint4*>(ogen + (((p_u0 + (uint32_t)(h * (CW / 8) + uu)) ^ p_xor) << 4)) = pk;
                 if (E_POOL) {
 #pragma unroll
