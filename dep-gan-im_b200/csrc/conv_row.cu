@@ -271,27 +271,33 @@ __global__ void __launch_bounds__(RW_THREADS, 1) conv_row_kernel(const __grid_co
       uint32_t o0 = 0, q = 0, acquired = 0;
       int j = 0, c = 0;
       // geometry of the step (si, j, c); advances the iteration state afterwards
+      Step rowc{};  // geometry of the current input row: the same for every channel chunk of the row
       auto make_step = [&]() -> Step {
         Step s{};
         s.valid = si.valid();
         if (!s.valid) return s;
-        const int cnt = si.cnt;
-        const int i_lo = j >= 2 ? j - 2 : 0, i_hi = j < cnt ? j : cnt - 1;
-        const uint32_t o_lo = o0 + (uint32_t)i_lo;
-        s.o_hi = o0 + (uint32_t)i_hi;
-        s.brow0 = (uint32_t)(i_lo - (j - 2));
-        const uint32_t blk0 = o_lo % NBLK, nblk = s.o_hi - o_lo + 1u;
-        s.n1 = blk0 + nblk > (uint32_t)NBLK ? (uint32_t)NBLK - blk0 : nblk;
-        s.n2 = nblk - s.n1;
-        s.d1 = tmem_base + blk0 * 32u;
-        s.idesc1 = make_idesc((int)(32u * s.n1), f16_in);
-        s.idesc2 = make_idesc((int)(32u * (s.n2 ? s.n2 : 1u)), f16_in);
+        if (c == 0) {
+          const int cnt = si.cnt;
+          const int i_lo = j >= 2 ? j - 2 : 0, i_hi = j < cnt ? j : cnt - 1;
+          const uint32_t o_lo = o0 + (uint32_t)i_lo;
+          s.o_hi = o0 + (uint32_t)i_hi;
+          s.brow0 = (uint32_t)(i_lo - (j - 2));
+          const uint32_t blk0 = o_lo % NBLK, nblk = s.o_hi - o_lo + 1u;
+          s.n1 = blk0 + nblk > (uint32_t)NBLK ? (uint32_t)NBLK - blk0 : nblk;
+          s.n2 = nblk - s.n1;
+          s.d1 = tmem_base + blk0 * 32u;
+          s.idesc1 = make_idesc((int)(32u * s.n1), f16_in);
+          s.idesc2 = make_idesc((int)(32u * (s.n2 ? s.n2 : 1u)), f16_in);
+          rowc = s;
+        } else {
+          s = rowc;  // (the 96-channel decoder layer has three chunks per row: its issuer was paced by this set-up)
+        }
         s.q = q; s.c = c;
         s.stage = ra.idx; s.phase = ra.phase;
         ra.advance(g.na);
         if (++c == nchunks) {
           c = 0; ++q;
-          if (++j == cnt + 2) { j = 0; o0 += (uint32_t)cnt; si.next(); }
+          if (++j == si.cnt + 2) { j = 0; o0 += (uint32_t)si.cnt; si.next(); }
         }
         return s;
       };
